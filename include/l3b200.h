@@ -1,0 +1,125 @@
+/* l3b200.h -- C ABI of the B200-native L3-Net AVC hot path (libl3b200.so).
+ *
+ * The reference (marl/l3embedding) has no FFI: its seam is the Keras Model API used by
+ *   l3embedding/train.py:267,282,408-414   (MODELS[...](), compile, fit_generator -> train_on_batch)
+ *   l3embedding/model.py:85-181            (load_model, load_embedding)
+ *   data/usc/features.py:304               (model.predict on (n,1,48000) frames)
+ * Each entry point below names the reference call it replaces.  Conventions:
+ *   - every function returns 0 on success, <0 on error; l3_last_error() gives the message (thread local);
+ *   - the caller owns every buffer: device pointers unless the name says _host;
+ *   - all work is asynchronous on the ctx stream unless the doc says it synchronises;
+ *   - activations NHWC, conv kernels HWIO, dense kernels (in,out) -- Keras array layouts;
+ *   - no torch / C++ types in any signature.
+ */
+#ifndef L3B200_H
+#define L3B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3_VERSION 1
+
+/* l3embedding/model.py:307-313 MODELS keys (tiny_L3 is non-functional upstream and not provided) */
+enum { L3_MODEL_ORIG = 0, L3_MODEL_KAPREDBINPUTBN = 1, L3_MODEL_MELSPEC1 = 2, L3_MODEL_MELSPEC2 = 3 };
+/* activation storage / conv operand precision: F32 = parity mode (SIMT fp32), BF16 = throughput mode (tcgen05) */
+enum { L3_DTYPE_F32 = 0, L3_DTYPE_BF16 = 1 };
+/* input formats */
+enum { L3_VIDEO_U8 = 0, L3_VIDEO_F32 = 1 };   /* u8 raw frames (scaled on device, train.py:186) | f32 in [-1,1] */
+enum { L3_AUDIO_I16 = 0, L3_AUDIO_F32 = 1 };  /* int16 PCM (pcm2float on device, audio.py:21-31) | f32 in [-1,1) */
+/* workspace flags */
+enum { L3_WS_TRAINING = 1, L3_WS_VISION = 2, L3_WS_AUDIO = 4, L3_WS_HOST_STAGING = 8 };
+/* embedding pooling (audio_model.py:461-478) */
+enum { L3_POOL_ORIGINAL = 0, L3_POOL_SHORT = 1 };
+
+typedef struct l3_ctx l3_ctx;
+
+int l3_version(void);
+const char* l3_last_error(void);
+
+/* ---- model inventory (replaces keras Model.get_weights()/weights introspection, model.py:77) ------------ */
+int64_t l3_param_count(int model_type);   /* trainable fp32 scalars in the flat arena (9 508 746 for melspec2) */
+int64_t l3_l2_count(int model_type);      /* leading scalars that are conv/dense kernels (l2 1e-5 regularised) */
+int64_t l3_state_count(int model_type);   /* BN moving mean/variance scalars */
+int l3_num_tensors(int model_type);
+/* tensor i: name (Keras-like 'audio/conv1a/kernel'), arena (0 = params, 1 = bn state), offset (floats), dims */
+int l3_tensor_info(int model_type, int i, char* name, int name_cap, int* arena, int64_t* offset, int* ndim,
+                   int64_t dims[4]);
+/* front-end output geometry: (n_freq_or_mels, n_frames) */
+int l3_frontend_shape(int model_type, int* n_out, int* n_frames);
+/* audio tower embedding-map geometry (H, W) of the raw conv4b output */
+int l3_embedding_map_shape(int model_type, int* h, int* w);
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+int64_t l3_workspace_bytes(int model_type, int max_batch, int dtype, int flags);
+/* params/grads/adam_m/adam_v: l3_param_count floats each (grads/adam may be NULL for inference);
+ * bn_state: l3_state_count floats; workspace: l3_workspace_bytes bytes, 256-byte aligned;
+ * stream: a cudaStream_t (NULL = legacy default stream).                                                   */
+l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float* params, float* grads,
+                      float* adam_m, float* adam_v, float* bn_state, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+void l3_ctx_destroy(l3_ctx* ctx);
+/* force the SIMT convolution path even in bf16 mode (debug / A-B checks) */
+int l3_ctx_set_use_tensor_cores(l3_ctx* ctx, int enable);
+int l3_ctx_uses_tensor_cores(l3_ctx* ctx);
+
+/* ---- hot path -------------------------------------------------------------------------------------------- */
+/* async H2D of one batch from (pinned) host memory into the ctx staging buffers (needs L3_WS_HOST_STAGING). */
+int l3_upload_batch_host(l3_ctx* ctx, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
+                         const float* labels_host, int batch);
+/* forward + backward of one AVC batch = the device part of keras train_on_batch (train.py:408-414).
+ * video/audio/labels are device pointers, or all NULL to use the staged batch.  Gradients of the mean loss
+ * over `global_batch` samples are left in the grads arena (sum over ranks == global gradient).              */
+int l3_forward_backward(l3_ctx* ctx, const void* video, int video_fmt, const void* audio, int audio_fmt,
+                        const float* labels, int batch, int global_batch);
+/* Keras-2.0.9 Adam (train.py:282) incl. the l2(1e-5) regulariser gradient; increments the step counter. */
+int l3_adam_step(l3_ctx* ctx, float lr);
+int l3_adam_set_t(l3_ctx* ctx, int64_t t);
+/* out[4] = {sum of per-sample cross-entropy, #correct, l2 penalty (1e-5*sum w^2), batch}; synchronises. */
+int l3_get_metrics(l3_ctx* ctx, float out[4]);
+/* single-GPU convenience: upload (host) + forward_backward + adam + metrics in one call; synchronises. */
+int l3_train_step_host(l3_ctx* ctx, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
+                       const float* labels_host, int batch, float lr, float out_metrics[4]);
+/* inference-mode forward (keras predict / evaluate, BN moving statistics): probs (batch,2) device floats;
+ * labels may be NULL; with labels, metrics are accumulated for l3_get_metrics.                              */
+int l3_predict(l3_ctx* ctx, const void* video, int video_fmt, const void* audio, int audio_fmt, const float* labels,
+               int batch, float* probs_out, float* logits_out);
+/* load_embedding(...,'audio', pooling) + model.predict (model.py:131-181, features.py:304):
+ * audio (n,1,48000) device -> out (n, 6144|512) device floats, n <= max_batch per call.                      */
+int l3_embed_audio(l3_ctx* ctx, const void* audio, int audio_fmt, int n, int pooling, float* out);
+/* load_embedding(...,'vision',...) (vision_model.py:198-218): video (n,224,224,3) -> (n, 8192) */
+int l3_embed_vision(l3_ctx* ctx, const void* video, int video_fmt, int n, float* out);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------- */
+/* kernel launches issued by this library in the calling process since it was loaded */
+uint64_t l3_launch_count(void);
+/* optional CUDA-event timing of the convolution / front-end launches on the ctx stream.  l3_ctx_profile_read
+ * synchronises and returns the milliseconds and launch counts accumulated since the previous read, per class:
+ * [0] conv forward, [1] conv dgrad, [2] conv wgrad, [3] audio front-end. */
+int l3_ctx_profile_enable(l3_ctx* ctx, int enable);
+int l3_ctx_profile_read(l3_ctx* ctx, float ms_out[4], int launches_out[4]);
+
+/* ---- single ops (unit tests / parity bisecting) ------------------------------------------------------------ */
+/* kapre Spectrogram/Melspectrogram (+pcm2float): audio (n,48000) -> out (n, n_out, n_frames) float */
+int l3_frontend_fwd(l3_ctx* ctx, const void* audio, int audio_fmt, int n, float* out);
+/* Conv2D 3x3 same: in zero-haloed padded (B,H+2,W+2,Cin), w HWIO fp32, bias fp32 (may be NULL), out unpadded
+ * (B,H,W,Cout); dtype of in/out per `dtype`; use_tc=1 runs the tcgen05 kernel (bf16 only, Cin%64==0, Cout%64==0),
+ * scratch then holds the packed weights (>= 2*9*Cin*Cout bytes). */
+int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                   int Cout, int dtype, int use_tc, void* scratch, void* stream);
+/* data gradient of the same conv: dz zero-haloed padded (B,H+2,W+2,Cout) -> da unpadded (B,H,W,Cin);
+ * scratch >= 9*Cin*Cout floats. */
+int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
+                     int use_tc, void* scratch, void* stream);
+/* weight/bias gradient: a zero-haloed padded (B,H+2,W+2,Cin), dz zero-haloed padded (B,H+2,W+2,Cout);
+ * dw (3,3,Cin,Cout) and db (Cout, may be NULL) are overwritten. */
+int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                     int dtype, int use_tc, void* stream);
+/* device-side peek at internal activations for tests: which = "audio/z3", "vision/a1", "audio/x0", "concat" ...
+ * copies up to `cap` floats (converted to f32) into out_host; returns element count or <0; synchronises. */
+int64_t l3_debug_read(l3_ctx* ctx, const char* which, int batch, float* out_host, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3B200_H */

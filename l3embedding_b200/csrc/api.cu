@@ -1,0 +1,922 @@
+// C ABI (include/l3b200.h) and step orchestration of the B200-native L3-Net AVC path.
+//
+// What the reference does with one keras `train_on_batch` / `predict` (l3embedding/train.py:408-414,
+// data/usc/features.py:304) over the graph built by l3embedding/model.py:198-284 is done here as an explicit
+// sequence of kernel launches on one CUDA stream over caller-owned arenas:
+//   params / grads / adam_m / adam_v : flat fp32 arenas, [conv+dense kernels (l2-regularised) | biases, BN gamma/beta]
+//   bn_state                         : BN moving mean / variance
+//   workspace                        : activations (NHWC; conv inputs in a zero-haloed (B,H+2,W+2,C) layout so a
+//                                      3x3 tap is a constant row shift of the flattened pixel index), BN scratch.
+// Data-parallel training: every rank calls l3_forward_backward on its slice with global_batch = N*batch, sums the
+// grads arena over ranks (NCCL all-reduce, done by the host), then calls l3_adam_step; BN statistics stay per
+// replica as under the reference's multi_gpu_model (l3embedding/training_utils.py:141-162).
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/l3b200.h"
+#include "kernels.h"
+
+namespace l3 {
+
+unsigned long long g_launch_count = 0;
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// model specifications (restated from l3embedding/audio_model.py, vision_model.py, model.py)
+// ---------------------------------------------------------------------------------------------------------
+struct ModelSpec {
+  int mel;          // kapre Melspectrogram (1) or Spectrogram (0)
+  int n_dft;        // audio_model.py:26,138,245,355
+  int n_mels;       // :248,358
+  int same_pad;     // padding='same' (mel models) / 'valid' (kapre default)
+  int decibel;      // return_decibel_* ; 0 -> log(max(x,1e-12))/5 (audio_model.py:43)
+  int audio_bn0;    // input BatchNormalization (audio_model.py:151,260,370)
+  int vision_bn0;   // vision_model.py:124
+  int embed_pool[2][2];  // audio_model.py:461-478: [original|short][h,w]
+};
+static const ModelSpec kSpecs[4] = {
+    /* orig           */ {0, 512, 0, 0, 0, 0, 0, {{8, 8}, {32, 24}}},
+    /* kapredbinputbn */ {0, 512, 0, 0, 1, 1, 1, {{8, 8}, {32, 24}}},
+    /* melspec1       */ {1, 2048, 128, 1, 1, 1, 1, {{4, 8}, {16, 24}}},
+    /* melspec2       */ {1, 2048, 256, 1, 1, 1, 1, {{8, 8}, {32, 24}}},
+};
+static const int kConvCh[9] = {0, 64, 64, 128, 128, 256, 256, 512, 512};  // Cout of conv l = kConvCh[l+1]
+static const char* kConvNames[8] = {"1a", "1b", "2a", "2b", "3a", "3b", "4a", "4b"};
+static const int kSR = 48000, kHop = 242;
+static const int kVisionEmbedPool = 7;  // vision_model.py:212
+
+static void audio_geometry(const ModelSpec& sp, int* n_out, int* n_frames, int* left_pad) {
+  *n_out = sp.mel ? sp.n_mels : sp.n_dft / 2 + 1;
+  if (sp.same_pad) {  // TF SAME: ceil(L/hop) frames, total pad split floor/ceil
+    *n_frames = (kSR + kHop - 1) / kHop;
+    int total = (*n_frames - 1) * kHop + sp.n_dft - kSR;
+    if (total < 0) total = 0;
+    *left_pad = total / 2;
+  } else {
+    *n_frames = (kSR - sp.n_dft) / kHop + 1;
+    *left_pad = 0;
+  }
+}
+
+struct TensorInfo {
+  std::string name;
+  int arena;  // 0 params, 1 bn state
+  long long offset;
+  int ndim;
+  long long dims[4];
+  long long size() const {
+    long long n = 1;
+    for (int i = 0; i < ndim; ++i) n *= dims[i];
+    return n;
+  }
+};
+struct Layout {
+  std::vector<TensorInfo> t;  // keras layer order (vision tower, audio tower, dense_1, dense_2)
+  long long n_params = 0, n_l2 = 0, n_state = 0;
+  int find(const std::string& nm) const {
+    for (size_t i = 0; i < t.size(); ++i)
+      if (t[i].name == nm) return (int)i;
+    return -1;
+  }
+};
+
+static Layout build_layout(int model_type) {
+  const ModelSpec& sp = kSpecs[model_type];
+  Layout L;
+  // pass 0 assigns the l2-regularised kernels (front of the params arena), pass 1 the rest
+  std::vector<TensorInfo> all;
+  auto add = [&](const std::string& nm, int arena, int nd, long long d0, long long d1, long long d2, long long d3) {
+    TensorInfo ti;
+    ti.name = nm;
+    ti.arena = arena;
+    ti.offset = -1;
+    ti.ndim = nd;
+    ti.dims[0] = d0; ti.dims[1] = d1; ti.dims[2] = d2; ti.dims[3] = d3;
+    all.push_back(ti);
+  };
+  auto add_bn = [&](const std::string& pre, int c) {
+    add(pre + "/gamma", 0, 1, c, 1, 1, 1);
+    add(pre + "/beta", 0, 1, c, 1, 1, 1);
+    add(pre + "/moving_mean", 1, 1, c, 1, 1, 1);
+    add(pre + "/moving_variance", 1, 1, c, 1, 1, 1);
+  };
+  for (int tw = 0; tw < 2; ++tw) {
+    std::string T = tw == 0 ? "vision" : "audio";
+    int c0 = tw == 0 ? 3 : 1;
+    if (tw == 0 ? sp.vision_bn0 : sp.audio_bn0) add_bn(T + "/bn0", c0);
+    for (int l = 0; l < 8; ++l) {
+      int ci = l == 0 ? c0 : kConvCh[l], co = kConvCh[l + 1];
+      add(T + "/conv" + kConvNames[l] + "/kernel", 0, 4, 3, 3, ci, co);
+      add(T + "/conv" + kConvNames[l] + "/bias", 0, 1, co, 1, 1, 1);
+      add_bn(T + "/bn" + kConvNames[l], co);
+    }
+  }
+  add("dense_1/kernel", 0, 2, 1024, 128, 1, 1);
+  add("dense_1/bias", 0, 1, 128, 1, 1, 1);
+  add("dense_2/kernel", 0, 2, 128, 2, 1, 1);
+  add("dense_2/bias", 0, 1, 2, 1, 1, 1);
+  auto is_kernel = [](const std::string& n) { return n.size() > 7 && n.compare(n.size() - 7, 7, "/kernel") == 0; };
+  long long po = 0, so = 0;
+  for (auto& ti : all)
+    if (ti.arena == 0 && is_kernel(ti.name)) { ti.offset = po; po += ti.size(); }
+  L.n_l2 = po;
+  for (auto& ti : all) {
+    if (ti.arena == 0 && !is_kernel(ti.name)) { ti.offset = po; po += ti.size(); }
+    if (ti.arena == 1) { ti.offset = so; so += ti.size(); }
+  }
+  L.n_params = po;
+  L.n_state = so;
+  L.t = all;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+struct ConvLayer {
+  int H, W, Cin, Cout;      // conv resolution
+  int pool;                 // 2x2 max-pool after the activation
+  int relu_first;           // vision conv1b: Conv -> ReLU -> BN (vision_model.py:39-43,135-139)
+  const float *w, *b;       // params
+  float *dw, *db;           // grads
+  BnRef bn;
+  void* in;                 // padded input  (B,H+2,W+2,Cin)
+  void* z;                  // raw conv output, unpadded (B,H,W,Cout)
+  void* a;                  // padded activation output at post-pool resolution (null for the last layer)
+  float* w_t;               // flipped/transposed fp32 kernel for dgrad-as-conv (SIMT path)
+  bf16* w_pk;               // tcgen05 operand packs (forward, dgrad)
+  bf16* wt_pk;
+  int tc;                   // this layer runs on the tcgen05 path
+};
+struct Tower {
+  int present;
+  int C0, H0, W0;
+  int has_bn0;
+  BnRef bn0;
+  float* x0;    // (B,H0,W0,C0) float: scaled video / front-end output
+  void* xin;    // padded T
+  ConvLayer L[8];
+  int* argmax;  // (B,512)
+  int concat_off;
+};
+
+}  // namespace l3
+
+using namespace l3;
+
+struct l3_ctx {
+  int model_type, max_batch, dtype, flags;
+  ModelSpec spec;
+  Layout layout;
+  float *params, *grads, *adam_m, *adam_v, *bn_state;
+  char* ws;
+  long long ws_bytes;
+  cudaStream_t stream;
+  FrontendPlan fe;
+  void* fe_tables;
+  int* clip_max;
+  Tower vision, audio;
+  HeadRef head;
+  double* l2_out;
+  void *g0, *g1;  // backward ping-pong: padded dz / unpadded da
+  // host staging
+  void *st_video, *st_audio;
+  float* st_labels;
+  int st_video_fmt, st_audio_fmt, st_batch;
+  long long adam_t;
+  int use_tc;
+  int last_batch;
+  // optional per-kernel-class device timing (CUDA events on the ctx stream)
+  int prof_on;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
+  std::vector<int> prof_cls;
+  size_t prof_used;
+};
+
+namespace l3 {
+
+// classes reported by l3_ctx_profile_read
+enum { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_FRONTEND = 3, PROF_N = 4 };
+struct ProfScope {
+  l3_ctx* c;
+  cudaEvent_t stop;
+  ProfScope(l3_ctx* ctx, int cls) : c(ctx), stop(nullptr) {
+    if (!c->prof_on) return;
+    if (c->prof_used * 2 + 2 > c->prof_ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      c->prof_ev.push_back(a);
+      c->prof_ev.push_back(b);
+      c->prof_cls.push_back(cls);
+    }
+    c->prof_cls[c->prof_used] = cls;
+    cudaEventRecord(c->prof_ev[c->prof_used * 2], c->stream);
+    stop = c->prof_ev[c->prof_used * 2 + 1];
+    c->prof_used++;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
+
+struct Bump {
+  char* base;
+  long long off;
+  void* take(long long bytes) {
+    long long o = off;
+    off += (bytes + 255) / 256 * 256;
+    return base ? (void*)(base + o) : nullptr;
+  }
+};
+
+static size_t esize(int dtype) { return dtype == L3_DTYPE_BF16 ? 2 : 4; }
+
+static void carve_bn(Bump& bp, BnRef& bn, int C) {
+  bn.C = C;
+  bn.sum = (double*)bp.take(sizeof(double) * 2 * C);
+  bn.mean = (float*)bp.take(4 * C);
+  bn.invstd = (float*)bp.take(4 * C);
+  bn.scale = (float*)bp.take(4 * C);
+  bn.shift = (float*)bp.take(4 * C);
+  bn.c1 = (float*)bp.take(4 * C);
+  bn.c2 = (float*)bp.take(4 * C);
+}
+
+// Walks every workspace allocation; with ctx->ws == nullptr it only measures.
+static long long carve(l3_ctx* c) {
+  Bump bp{c->ws, 0};
+  const long long B = c->max_batch;
+  const size_t es = esize(c->dtype);
+  const bool training = c->flags & L3_WS_TRAINING;
+  int n_out, n_frames, left;
+  audio_geometry(c->spec, &n_out, &n_frames, &left);
+  c->fe_tables = bp.take(frontend_table_bytes(c->spec.n_dft, c->spec.mel ? c->spec.n_mels : 1));
+  c->clip_max = (int*)bp.take(4 * B);
+  if (c->flags & L3_WS_HOST_STAGING) {
+    c->st_video = bp.take(B * 224 * 224 * 3 * 4);
+    c->st_audio = bp.take(B * kSR * 4);
+    c->st_labels = (float*)bp.take(B * 2 * 4);
+  } else {
+    c->st_video = c->st_audio = nullptr;
+    c->st_labels = nullptr;
+  }
+  long long g0_max = 0, g1_max = 0;
+  for (int t = 0; t < 2; ++t) {
+    Tower& tw = t == 0 ? c->vision : c->audio;
+    tw.present = (c->flags & (t == 0 ? L3_WS_VISION : L3_WS_AUDIO)) ? 1 : 0;
+    tw.C0 = t == 0 ? 3 : 1;
+    tw.H0 = t == 0 ? 224 : n_out;
+    tw.W0 = t == 0 ? 224 : n_frames;
+    tw.has_bn0 = t == 0 ? c->spec.vision_bn0 : c->spec.audio_bn0;
+    tw.concat_off = t == 0 ? 0 : 512;  // model.py:25 concatenate([vision, audio])
+    if (!tw.present) continue;
+    tw.x0 = (float*)bp.take(4 * B * tw.H0 * tw.W0 * tw.C0);
+    tw.xin = bp.take(es * B * (tw.H0 + 2) * (tw.W0 + 2) * tw.C0);
+    if (tw.has_bn0) carve_bn(bp, tw.bn0, tw.C0);
+    int H = tw.H0, W = tw.W0;
+    void* prev = tw.xin;
+    for (int l = 0; l < 8; ++l) {
+      ConvLayer& L = tw.L[l];
+      L.H = H; L.W = W;
+      L.Cin = l == 0 ? tw.C0 : kConvCh[l];
+      L.Cout = kConvCh[l + 1];
+      L.pool = (l == 1 || l == 3 || l == 5) ? 1 : 0;
+      L.relu_first = (t == 0 && l == 1) ? 1 : 0;
+      L.in = prev;
+      L.z = bp.take(es * B * H * W * L.Cout);
+      carve_bn(bp, L.bn, L.Cout);
+      int OH = L.pool ? H / 2 : H, OW = L.pool ? W / 2 : W;  // valid pooling floors; vision sizes are even
+      L.a = l < 7 ? bp.take(es * B * (OH + 2) * (OW + 2) * L.Cout) : nullptr;
+      L.w_t = training ? (float*)bp.take(4LL * 9 * L.Cin * L.Cout) : nullptr;
+      L.tc = (c->dtype == L3_DTYPE_BF16 && L.Cin % 64 == 0 && L.Cout % 64 == 0) ? 1 : 0;
+      L.w_pk = L.tc ? (bf16*)bp.take(2LL * 9 * L.Cin * L.Cout) : nullptr;
+      L.wt_pk = (L.tc && training) ? (bf16*)bp.take(2LL * 9 * L.Cin * L.Cout) : nullptr;
+      long long dz = B * (H + 2) * (W + 2) * L.Cout, da = B * H * W * L.Cin;
+      if (dz > g0_max) g0_max = dz;
+      if (da > g1_max) g1_max = da;
+      prev = L.a;
+      H = OH; W = OW;
+    }
+    tw.argmax = (int*)bp.take(4 * B * 512);
+  }
+  c->g0 = training ? bp.take(es * g0_max) : nullptr;
+  c->g1 = training ? bp.take(es * g1_max) : nullptr;
+  HeadRef& h = c->head;
+  h.concat = (float*)bp.take(4 * B * 1024);
+  h.hidden = (float*)bp.take(4 * B * 128);
+  h.probs = (float*)bp.take(4 * B * 2);
+  h.logits = (float*)bp.take(4 * B * 2);
+  h.dlogits = (float*)bp.take(4 * B * 2);
+  h.dhidden = (float*)bp.take(4 * B * 128);
+  h.dconcat = (float*)bp.take(4 * B * 1024);
+  h.metrics = (float*)bp.take(256);
+  c->l2_out = (double*)bp.take(256);
+  return bp.off;
+}
+
+static float* P(l3_ctx* c, const char* nm) { int i = c->layout.find(nm); return i < 0 ? nullptr : c->params + c->layout.t[i].offset; }
+static float* G(l3_ctx* c, const char* nm) { int i = c->layout.find(nm); return (i < 0 || !c->grads) ? nullptr : c->grads + c->layout.t[i].offset; }
+static float* S(l3_ctx* c, const char* nm) { int i = c->layout.find(nm); return i < 0 ? nullptr : c->bn_state + c->layout.t[i].offset; }
+
+static void bind_bn(l3_ctx* c, BnRef& bn, const std::string& pre) {
+  bn.gamma = P(c, (pre + "/gamma").c_str());
+  bn.beta = P(c, (pre + "/beta").c_str());
+  bn.d_gamma = G(c, (pre + "/gamma").c_str());
+  bn.d_beta = G(c, (pre + "/beta").c_str());
+  bn.moving_mean = S(c, (pre + "/moving_mean").c_str());
+  bn.moving_var = S(c, (pre + "/moving_variance").c_str());
+}
+static void bind_params(l3_ctx* c) {
+  for (int t = 0; t < 2; ++t) {
+    Tower& tw = t == 0 ? c->vision : c->audio;
+    if (!tw.present) continue;
+    std::string T = t == 0 ? "vision" : "audio";
+    if (tw.has_bn0) bind_bn(c, tw.bn0, T + "/bn0");
+    for (int l = 0; l < 8; ++l) {
+      ConvLayer& L = tw.L[l];
+      std::string cn = T + "/conv" + kConvNames[l];
+      L.w = P(c, (cn + "/kernel").c_str());
+      L.b = P(c, (cn + "/bias").c_str());
+      L.dw = G(c, (cn + "/kernel").c_str());
+      L.db = G(c, (cn + "/bias").c_str());
+      bind_bn(c, L.bn, T + "/bn" + kConvNames[l]);
+    }
+  }
+  HeadRef& h = c->head;
+  h.w1 = P(c, "dense_1/kernel"); h.b1 = P(c, "dense_1/bias");
+  h.w2 = P(c, "dense_2/kernel"); h.b2 = P(c, "dense_2/bias");
+  h.dw1 = G(c, "dense_1/kernel"); h.db1 = G(c, "dense_1/bias");
+  h.dw2 = G(c, "dense_2/kernel"); h.db2 = G(c, "dense_2/bias");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+static const float kBnMomentum = 0.99f, kBnEps = 1e-3f;  // keras BatchNormalization defaults
+static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm feeds the Bessel-corrected variance
+
+template <typename T>
+static int conv_forward(l3_ctx* c, ConvLayer& L, int B) {
+  ProfScope ps(c, PROF_CONV_FWD);
+  if (L.tc && c->use_tc) {
+    if (launch_pack_weights_tc(L.w, L.w_pk, L.Cin, L.Cout, 0, c->stream)) return -1;
+    return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
+  }
+  return launch_conv3x3_simt<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
+}
+
+// input: raw (device) video or audio -> x0 -> (input BN) -> xin
+template <typename T>
+static int tower_input(l3_ctx* c, Tower& tw, bool is_audio, const void* src, int fmt, int B, bool training) {
+  cudaStream_t s = c->stream;
+  if (is_audio) {
+    ProfScope ps(c, PROF_FRONTEND);
+    if (launch_frontend(c->fe, src, fmt == L3_AUDIO_I16, B, tw.x0, c->clip_max, s)) return -1;
+  } else {
+    long long n = (long long)B * 224 * 224 * 3;
+    if (fmt == L3_VIDEO_U8) {
+      if (launch_video_to_f32((const uint8_t*)src, tw.x0, n, s)) return -1;
+    } else {
+      L3_CHECK_CUDA(cudaMemcpyAsync(tw.x0, src, n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  const float *sc = nullptr, *sh = nullptr;
+  if (tw.has_bn0) {
+    long long rows = (long long)B * tw.H0 * tw.W0;
+    if (training && launch_channel_stats<float>(tw.x0, rows, tw.C0, 0, tw.bn0.sum, s)) return -1;
+    if (launch_bn_finalize(tw.bn0, rows, training, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
+    sc = tw.bn0.scale;
+    sh = tw.bn0.shift;
+  }
+  return launch_affine_small<T>(tw.x0, (T*)tw.xin, B, tw.H0, tw.W0, tw.C0, sc, sh, s);
+}
+
+// n_layers_act: layers [0, 7) always activate into the next input; the last conv's z is the embedding tap
+template <typename T>
+static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_only) {
+  cudaStream_t s = c->stream;
+  for (int l = 0; l < 8; ++l) {
+    ConvLayer& L = tw.L[l];
+    if (conv_forward<T>(c, L, B)) return -1;
+    if (l == 7 && embed_only) return 0;  // raw conv4b output incl. bias, before BN/ReLU (audio_model.py:482)
+    long long rows = (long long)B * L.H * L.W;
+    if (training && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
+    if (launch_bn_finalize(L.bn, rows, training, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
+    if (l < 7) {
+      if (launch_act_fwd<T>((const T*)L.z, (T*)L.a, B, L.H, L.W, L.Cout, L.bn.scale, L.bn.shift, L.pool, L.relu_first, s))
+        return -1;
+    } else {
+      // MaxPooling2D over the whole final map + Flatten (audio_model.py:436-437, vision_model.py:189-190)
+      if (launch_gmaxpool_fwd<T>((const T*)L.z, B, L.H * L.W, L.Cout, L.bn.scale, L.bn.shift,
+                                 c->head.concat + tw.concat_off, 1024, tw.argmax, s))
+        return -1;
+    }
+  }
+  return 0;
+}
+
+template <typename T>
+static int tower_backward(l3_ctx* c, Tower& tw, int B) {
+  cudaStream_t s = c->stream;
+  T* dz = (T*)c->g0;
+  T* da = (T*)c->g1;
+  {
+    ConvLayer& L = tw.L[7];
+    if (launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, dz, L.bn, B, L.H, L.W,
+                               L.Cout, s))
+      return -1;
+  }
+  for (int l = 7; l >= 0; --l) {
+    ConvLayer& L = tw.L[l];
+    long long rows = (long long)B * L.H * L.W;
+    // dz currently holds dy (grad wrt the BN output, or wrt BN input side for relu_first) + bn.sum holds the sums
+    if (launch_bn_bwd_finalize(L.bn, rows, s)) return -1;
+    if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
+    // weight / bias gradient
+    {
+    ProfScope ps(c, PROF_CONV_WGRAD);
+    if (L.tc && c->use_tc) {
+      if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+    } else {
+      if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+    }
+    }
+    if (l == 0 && !tw.has_bn0) break;
+    // data gradient: da = conv(dz, flip/transpose(w))
+    {
+    ProfScope ps(c, PROF_CONV_DGRAD);
+    if (L.tc && c->use_tc) {
+      if (launch_pack_weights_tc(L.w, L.wt_pk, L.Cin, L.Cout, 1, s)) return -1;
+      if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+    } else {
+      if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
+      if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+    }
+    }
+    if (l == 0) {
+      if (launch_input_bn_bwd_stats<T>(da, tw.x0, rows, tw.C0, tw.bn0, s)) return -1;
+      if (launch_bn_bwd_finalize(tw.bn0, rows, s)) return -1;  // writes d_gamma / d_beta of the input BN
+      break;
+    }
+    ConvLayer& Lp = tw.L[l - 1];
+    if (launch_act_bwd<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+  }
+  return 0;
+}
+
+template <typename T>
+static int forward_all(l3_ctx* c, const void* video, int vfmt, const void* audio, int afmt, const float* labels, int B,
+                       bool training, float grad_scale) {
+  if (tower_input<T>(c, c->vision, false, video, vfmt, B, training)) return -1;
+  if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
+  if (tower_input<T>(c, c->audio, true, audio, afmt, B, training)) return -1;
+  if (tower_forward<T>(c, c->audio, B, training, false)) return -1;
+  return launch_head_fwd(c->head, labels, B, grad_scale, c->stream);
+}
+
+static int check_batch(l3_ctx* c, int batch) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  L3_REQUIRE(batch >= 1 && batch <= c->max_batch, "batch %d outside [1, %d]", batch, c->max_batch);
+  return 0;
+}
+
+// ---- activation peek for parity bisecting -----------------------------------------------------------------
+template <typename T>
+__global__ void k_gather_unpad(const T* __restrict__ src, float* __restrict__ dst, long long n, int H, int W, int C,
+                               int padded) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!padded) {
+      dst[i] = to_f(src[i]);
+    } else {
+      int ch = (int)(i % C);
+      long long p = i / C;
+      int x = (int)(p % W);
+      int y = (int)((p / W) % H);
+      long long b = p / ((long long)W * H);
+      dst[i] = to_f(src[pad_off(b, y, x, H, W, C) + ch]);
+    }
+  }
+}
+
+}  // namespace l3
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int l3_version(void) { return L3_VERSION; }
+const char* l3_last_error(void) { return g_err; }
+
+static int valid_model(int m) {
+  if (m < 0 || m > 3) {
+    set_error("invalid model type %d", m);
+    return 0;
+  }
+  return 1;
+}
+int64_t l3_param_count(int m) { return valid_model(m) ? build_layout(m).n_params : -1; }
+int64_t l3_l2_count(int m) { return valid_model(m) ? build_layout(m).n_l2 : -1; }
+int64_t l3_state_count(int m) { return valid_model(m) ? build_layout(m).n_state : -1; }
+int l3_num_tensors(int m) { return valid_model(m) ? (int)build_layout(m).t.size() : -1; }
+int l3_tensor_info(int m, int i, char* name, int name_cap, int* arena, int64_t* offset, int* ndim, int64_t dims[4]) {
+  if (!valid_model(m)) return -2;
+  Layout L = build_layout(m);
+  L3_REQUIRE(i >= 0 && i < (int)L.t.size(), "tensor index %d out of range", i);
+  const TensorInfo& t = L.t[i];
+  if (name && name_cap > 0) {
+    strncpy(name, t.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (arena) *arena = t.arena;
+  if (offset) *offset = t.offset;
+  if (ndim) *ndim = t.ndim;
+  if (dims)
+    for (int k = 0; k < 4; ++k) dims[k] = t.dims[k];
+  return 0;
+}
+int l3_frontend_shape(int m, int* n_out, int* n_frames) {
+  if (!valid_model(m)) return -2;
+  int a, b, lp;
+  audio_geometry(kSpecs[m], &a, &b, &lp);
+  if (n_out) *n_out = a;
+  if (n_frames) *n_frames = b;
+  return 0;
+}
+int l3_embedding_map_shape(int m, int* h, int* w) {
+  if (!valid_model(m)) return -2;
+  int H, W, lp;
+  audio_geometry(kSpecs[m], &H, &W, &lp);
+  for (int i = 0; i < 3; ++i) { H /= 2; W /= 2; }
+  if (h) *h = H;
+  if (w) *w = W;
+  return 0;
+}
+
+int64_t l3_workspace_bytes(int model_type, int max_batch, int dtype, int flags) {
+  if (!valid_model(model_type)) return -2;
+  if (max_batch < 1 || (dtype != L3_DTYPE_F32 && dtype != L3_DTYPE_BF16)) {
+    set_error("bad max_batch %d / dtype %d", max_batch, dtype);
+    return -2;
+  }
+  l3_ctx tmp{};
+  tmp.model_type = model_type;
+  tmp.max_batch = max_batch;
+  tmp.dtype = dtype;
+  tmp.flags = flags;
+  tmp.spec = kSpecs[model_type];
+  tmp.ws = nullptr;
+  return carve(&tmp);
+}
+
+l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float* params, float* grads, float* adam_m,
+                      float* adam_v, float* bn_state, void* workspace, int64_t workspace_bytes, void* stream) {
+  int64_t need = l3_workspace_bytes(model_type, max_batch, dtype, flags);
+  if (need < 0) return nullptr;
+  if (!params || !bn_state || !workspace) {
+    set_error("params, bn_state and workspace must be non-null");
+    return nullptr;
+  }
+  if ((flags & L3_WS_TRAINING) && (!grads || !adam_m || !adam_v)) {
+    set_error("training context needs grads / adam_m / adam_v arenas");
+    return nullptr;
+  }
+  if (workspace_bytes < need) {
+    set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+    return nullptr;
+  }
+  if (((uintptr_t)workspace & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libl3b200 has no CPU fallback");
+    return nullptr;
+  }
+  l3_ctx* c = new l3_ctx();
+  c->model_type = model_type;
+  c->max_batch = max_batch;
+  c->dtype = dtype;
+  c->flags = flags;
+  c->spec = kSpecs[model_type];
+  c->layout = build_layout(model_type);
+  c->params = params; c->grads = grads; c->adam_m = adam_m; c->adam_v = adam_v; c->bn_state = bn_state;
+  c->ws = (char*)workspace;
+  c->ws_bytes = workspace_bytes;
+  c->stream = (cudaStream_t)stream;
+  c->adam_t = 0;
+  c->use_tc = (dtype == L3_DTYPE_BF16) && conv_tc_supported();
+  c->st_batch = 0;
+  c->last_batch = 0;
+  c->prof_on = 0;
+  c->prof_used = 0;
+  carve(c);
+  bind_params(c);
+  // zero the workspace once: the halos of every fixed-geometry padded activation buffer stay zero forever
+  if (cudaMemsetAsync(workspace, 0, need, c->stream) != cudaSuccess) {
+    set_error("workspace memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  int n_out, n_frames, left;
+  audio_geometry(c->spec, &n_out, &n_frames, &left);
+  FrontendPlan& fe = c->fe;
+  fe.n_dft = c->spec.n_dft; fe.n_hop = kHop; fe.n_frames = n_frames; fe.left_pad = left; fe.n_out = n_out;
+  fe.mel = c->spec.mel; fe.decibel = c->spec.decibel; fe.n_samples = kSR;
+  if (frontend_build_tables(&fe, kSR, c->spec.n_mels, c->fe_tables, c->stream)) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void l3_ctx_destroy(l3_ctx* ctx) {
+  if (!ctx) return;
+  for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+  delete ctx;
+}
+
+uint64_t l3_launch_count(void) { return g_launch_count; }
+
+int l3_ctx_profile_enable(l3_ctx* c, int enable) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  c->prof_on = enable ? 1 : 0;
+  c->prof_used = 0;
+  return 0;
+}
+int l3_ctx_profile_read(l3_ctx* c, float ms_out[4], int launches_out[4]) {
+  L3_REQUIRE(c != nullptr && ms_out != nullptr, "null argument");
+  L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < PROF_N; ++i) {
+    ms_out[i] = 0.f;
+    if (launches_out) launches_out[i] = 0;
+  }
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    float ms = 0.f;
+    L3_CHECK_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    ms_out[c->prof_cls[i]] += ms;
+    if (launches_out) launches_out[c->prof_cls[i]]++;
+  }
+  c->prof_used = 0;
+  return 0;
+}
+
+int l3_ctx_set_use_tensor_cores(l3_ctx* c, int enable) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  L3_REQUIRE(!enable || (c->dtype == L3_DTYPE_BF16 && conv_tc_supported()), "tensor-core path needs a bf16 context on sm_100");
+  c->use_tc = enable ? 1 : 0;
+  return 0;
+}
+int l3_ctx_uses_tensor_cores(l3_ctx* c) { return c ? c->use_tc : 0; }
+
+int l3_upload_batch_host(l3_ctx* c, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
+                         const float* labels_host, int batch) {
+  if (check_batch(c, batch)) return -2;
+  L3_REQUIRE(c->flags & L3_WS_HOST_STAGING, "context was created without L3_WS_HOST_STAGING");
+  if (video_host) {
+    size_t n = (size_t)batch * 224 * 224 * 3 * (video_fmt == L3_VIDEO_U8 ? 1 : 4);
+    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_video, video_host, n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (audio_host) {
+    size_t n = (size_t)batch * kSR * (audio_fmt == L3_AUDIO_I16 ? 2 : 4);
+    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_audio, audio_host, n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (labels_host) L3_CHECK_CUDA(cudaMemcpyAsync(c->st_labels, labels_host, (size_t)batch * 8, cudaMemcpyHostToDevice, c->stream));
+  c->st_video_fmt = video_fmt;
+  c->st_audio_fmt = audio_fmt;
+  c->st_batch = batch;
+  return 0;
+}
+
+static int resolve_inputs(l3_ctx* c, const void*& video, int& vfmt, const void*& audio, int& afmt, const float*& labels,
+                          int batch, bool need_labels) {
+  if (!video && !audio) {
+    L3_REQUIRE(c->st_batch == batch, "no staged batch of size %d (staged %d)", batch, c->st_batch);
+    video = c->st_video; vfmt = c->st_video_fmt;
+    audio = c->st_audio; afmt = c->st_audio_fmt;
+    if (!labels) labels = c->st_labels;
+  }
+  L3_REQUIRE(video && audio, "video and audio must both be given (or both NULL for the staged batch)");
+  L3_REQUIRE(!need_labels || labels, "labels required");
+  L3_REQUIRE(c->vision.present && c->audio.present, "context lacks a tower (L3_WS_VISION | L3_WS_AUDIO)");
+  return 0;
+}
+
+int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void* audio, int audio_fmt,
+                        const float* labels, int batch, int global_batch) {
+  if (check_batch(c, batch)) return -2;
+  L3_REQUIRE(c->flags & L3_WS_TRAINING, "context was created without L3_WS_TRAINING");
+  L3_REQUIRE(global_batch >= batch, "global_batch %d < batch %d", global_batch, batch);
+  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, true)) return -2;
+  const float gs = 1.0f / (float)global_batch;
+  L3_CHECK_CUDA(cudaMemsetAsync(c->grads, 0, sizeof(float) * c->layout.n_params, c->stream));
+  int rc;
+  if (c->dtype == L3_DTYPE_BF16) {
+    rc = forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
+    if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc) rc = tower_backward<bf16>(c, c->vision, batch);
+    if (!rc) rc = tower_backward<bf16>(c, c->audio, batch);
+  } else {
+    rc = forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
+    if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc) rc = tower_backward<float>(c, c->vision, batch);
+    if (!rc) rc = tower_backward<float>(c, c->audio, batch);
+  }
+  c->last_batch = batch;
+  return rc;
+}
+
+int l3_adam_step(l3_ctx* c, float lr) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  L3_REQUIRE(c->flags & L3_WS_TRAINING, "context was created without L3_WS_TRAINING");
+  // keras 2.0.9 Adam.get_updates: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t); p -= lr_t * m / (sqrt(v) + eps)
+  c->adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const double t = (double)c->adam_t;
+  const double lr_t = (double)lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
+  return launch_adam(c->params, c->grads, c->adam_m, c->adam_v, c->layout.n_params, c->layout.n_l2, (float)lr_t,
+                     (float)b1, (float)b2, 1e-8f, 1e-5f, c->stream);
+}
+int l3_adam_set_t(l3_ctx* c, int64_t t) {
+  L3_REQUIRE(c != nullptr && t >= 0, "bad adam step");
+  c->adam_t = t;
+  return 0;
+}
+
+int l3_get_metrics(l3_ctx* c, float out[4]) {
+  L3_REQUIRE(c != nullptr && out != nullptr, "null argument");
+  if (launch_l2_penalty(c->params, c->layout.n_l2, c->l2_out, c->stream)) return -1;
+  float m[2];
+  double l2;
+  L3_CHECK_CUDA(cudaMemcpyAsync(m, c->head.metrics, 8, cudaMemcpyDeviceToHost, c->stream));
+  L3_CHECK_CUDA(cudaMemcpyAsync(&l2, c->l2_out, 8, cudaMemcpyDeviceToHost, c->stream));
+  L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  out[0] = m[0];
+  out[1] = m[1];
+  out[2] = (float)(1e-5 * l2);
+  out[3] = (float)c->last_batch;
+  return 0;
+}
+
+int l3_train_step_host(l3_ctx* c, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
+                       const float* labels_host, int batch, float lr, float out_metrics[4]) {
+  int rc = l3_upload_batch_host(c, video_host, video_fmt, audio_host, audio_fmt, labels_host, batch);
+  if (!rc) rc = l3_forward_backward(c, nullptr, 0, nullptr, 0, nullptr, batch, batch);
+  if (!rc && out_metrics) rc = l3_get_metrics(c, out_metrics);  // loss terms of the weights the batch was run with
+  if (!rc) rc = l3_adam_step(c, lr);
+  if (!rc) L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+int l3_predict(l3_ctx* c, const void* video, int video_fmt, const void* audio, int audio_fmt, const float* labels,
+               int batch, float* probs_out, float* logits_out) {
+  if (check_batch(c, batch)) return -2;
+  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, false)) return -2;
+  int rc = c->dtype == L3_DTYPE_BF16
+               ? forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, false, 1.0f / batch)
+               : forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, false, 1.0f / batch);
+  if (rc) return rc;
+  if (probs_out) L3_CHECK_CUDA(cudaMemcpyAsync(probs_out, c->head.probs, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (logits_out) L3_CHECK_CUDA(cudaMemcpyAsync(logits_out, c->head.logits, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));
+  c->last_batch = batch;
+  return 0;
+}
+
+int l3_embed_audio(l3_ctx* c, const void* audio, int audio_fmt, int n, int pooling, float* out) {
+  if (check_batch(c, n)) return -2;
+  L3_REQUIRE(c->audio.present, "context lacks the audio tower");
+  L3_REQUIRE(pooling == L3_POOL_ORIGINAL || pooling == L3_POOL_SHORT, "bad pooling %d", pooling);
+  L3_REQUIRE(audio && out, "null argument");
+  Tower& tw = c->audio;
+  const int ph = c->spec.embed_pool[pooling][0], pw = c->spec.embed_pool[pooling][1];
+  ConvLayer& L = tw.L[7];
+  if (c->dtype == L3_DTYPE_BF16) {
+    if (tower_input<bf16>(c, tw, true, audio, audio_fmt, n, false)) return -1;
+    if (tower_forward<bf16>(c, tw, n, false, true)) return -1;
+    return launch_embed_pool<bf16>((const bf16*)L.z, n, L.H, L.W, L.Cout, ph, pw, out, c->stream);
+  }
+  if (tower_input<float>(c, tw, true, audio, audio_fmt, n, false)) return -1;
+  if (tower_forward<float>(c, tw, n, false, true)) return -1;
+  return launch_embed_pool<float>((const float*)L.z, n, L.H, L.W, L.Cout, ph, pw, out, c->stream);
+}
+
+int l3_embed_vision(l3_ctx* c, const void* video, int video_fmt, int n, float* out) {
+  if (check_batch(c, n)) return -2;
+  L3_REQUIRE(c->vision.present, "context lacks the vision tower");
+  L3_REQUIRE(video && out, "null argument");
+  Tower& tw = c->vision;
+  ConvLayer& L = tw.L[7];
+  if (c->dtype == L3_DTYPE_BF16) {
+    if (tower_input<bf16>(c, tw, false, video, video_fmt, n, false)) return -1;
+    if (tower_forward<bf16>(c, tw, n, false, true)) return -1;
+    return launch_embed_pool<bf16>((const bf16*)L.z, n, L.H, L.W, L.Cout, kVisionEmbedPool, kVisionEmbedPool, out, c->stream);
+  }
+  if (tower_input<float>(c, tw, false, video, video_fmt, n, false)) return -1;
+  if (tower_forward<float>(c, tw, n, false, true)) return -1;
+  return launch_embed_pool<float>((const float*)L.z, n, L.H, L.W, L.Cout, kVisionEmbedPool, kVisionEmbedPool, out, c->stream);
+}
+
+int l3_frontend_fwd(l3_ctx* c, const void* audio, int audio_fmt, int n, float* out) {
+  if (check_batch(c, n)) return -2;
+  L3_REQUIRE(audio && out, "null argument");
+  return launch_frontend(c->fe, audio, audio_fmt == L3_AUDIO_I16, n, out, c->clip_max, c->stream);
+}
+
+// ---- stand-alone ops (unit tests) -------------------------------------------------------------------------
+int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                   int dtype, int use_tc, void* scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_tc) {
+    L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0 && scratch, "tc conv: bf16, C%%64, scratch");
+    L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+    if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 0, s)) return -1;
+    return launch_conv3x3_tc((const bf16*)in, (const bf16*)scratch, bias, (bf16*)out, B, H, W, Cin, Cout, s);
+  }
+  if (dtype == L3_DTYPE_BF16) return launch_conv3x3_simt<bf16>((const bf16*)in, w, bias, (bf16*)out, B, H, W, Cin, Cout, s);
+  return launch_conv3x3_simt<float>((const float*)in, w, bias, (float*)out, B, H, W, Cin, Cout, s);
+}
+int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
+                     int use_tc, void* scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  L3_REQUIRE(scratch, "dgrad needs scratch of 9*Cin*Cout floats");
+  if (use_tc) {
+    L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0, "tc dgrad: bf16, C%%64");
+    L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+    if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 1, s)) return -1;
+    return launch_conv3x3_tc((const bf16*)dz, (const bf16*)scratch, nullptr, (bf16*)da, B, H, W, Cout, Cin, s);
+  }
+  if (launch_flip_transpose(w, (float*)scratch, Cin, Cout, s)) return -1;
+  if (dtype == L3_DTYPE_BF16)
+    return launch_conv3x3_simt<bf16>((const bf16*)dz, (const float*)scratch, nullptr, (bf16*)da, B, H, W, Cout, Cin, s);
+  return launch_conv3x3_simt<float>((const float*)dz, (const float*)scratch, nullptr, (float*)da, B, H, W, Cout, Cin, s);
+}
+int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                     int dtype, int use_tc, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  L3_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * Cin * Cout, s));
+  if (db) L3_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
+  if (use_tc) {
+    L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0, "tc wgrad: bf16, C%%64");
+    L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+    return launch_wgrad3x3_tc((const bf16*)a, (const bf16*)dz, dw, db, B, H, W, Cin, Cout, s);
+  }
+  if (dtype == L3_DTYPE_BF16) return launch_wgrad3x3_simt<bf16>((const bf16*)a, (const bf16*)dz, dw, db, B, H, W, Cin, Cout, s);
+  return launch_wgrad3x3_simt<float>((const float*)a, (const float*)dz, dw, db, B, H, W, Cin, Cout, s);
+}
+
+int64_t l3_debug_read(l3_ctx* c, const char* which, int batch, float* out_host, int64_t cap) {
+  if (check_batch(c, batch)) return -2;
+  L3_REQUIRE(which && out_host, "null argument");
+  std::string w(which);
+  const void* src = nullptr;
+  long long n = 0;
+  int H = 1, W = 1, C = 1, padded = 0, is_float = 0;
+  auto tower_of = [&](const std::string& t) -> Tower* { return t == "vision" ? &c->vision : t == "audio" ? &c->audio : nullptr; };
+  size_t slash = w.find('/');
+  if (w == "concat") { src = c->head.concat; n = (long long)batch * 1024; is_float = 1; }
+  else if (w == "hidden") { src = c->head.hidden; n = (long long)batch * 128; is_float = 1; }
+  else if (w == "logits") { src = c->head.logits; n = (long long)batch * 2; is_float = 1; }
+  else if (w == "probs") { src = c->head.probs; n = (long long)batch * 2; is_float = 1; }
+  else if (w == "dconcat") { src = c->head.dconcat; n = (long long)batch * 1024; is_float = 1; }
+  else if (slash != std::string::npos) {
+    Tower* tw = tower_of(w.substr(0, slash));
+    std::string k = w.substr(slash + 1);
+    L3_REQUIRE(tw && tw->present, "unknown tower in '%s'", which);
+    if (k == "x0") { src = tw->x0; n = (long long)batch * tw->H0 * tw->W0 * tw->C0; is_float = 1; }
+    else if (k == "xin") { src = tw->xin; H = tw->H0; W = tw->W0; C = tw->C0; padded = 1; n = (long long)batch * H * W * C; }
+    else if (k.size() == 2 && (k[0] == 'z' || k[0] == 'a') && k[1] >= '0' && k[1] <= '7') {
+      ConvLayer& L = tw->L[k[1] - '0'];
+      if (k[0] == 'z') { src = L.z; H = L.H; W = L.W; C = L.Cout; }
+      else {
+        L3_REQUIRE(L.a, "layer 7 has no activation buffer");
+        src = L.a; H = L.pool ? L.H / 2 : L.H; W = L.pool ? L.W / 2 : L.W; C = L.Cout; padded = 1;
+      }
+      n = (long long)batch * H * W * C;
+    }
+  }
+  L3_REQUIRE(src, "unknown buffer '%s'", which);
+  L3_REQUIRE(n <= cap, "buffer '%s' has %lld elements, capacity %lld", which, n, (long long)cap);
+  float* tmp = nullptr;
+  L3_CHECK_CUDA(cudaMalloc(&tmp, n * 4));
+  int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+  if (is_float) k_gather_unpad<float><<<blocks, 256, 0, c->stream>>>((const float*)src, tmp, n, H, W, C, 0);
+  else if (c->dtype == L3_DTYPE_BF16) k_gather_unpad<bf16><<<blocks, 256, 0, c->stream>>>((const bf16*)src, tmp, n, H, W, C, padded);
+  else k_gather_unpad<float><<<blocks, 256, 0, c->stream>>>((const float*)src, tmp, n, H, W, C, padded);
+  cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  L3_CHECK_CUDA(e);
+  return n;
+}
+
+}  // extern "C"

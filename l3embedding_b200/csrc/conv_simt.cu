@@ -1,0 +1,215 @@
+// fp32-accumulate SIMT 3x3 'same' convolutions (implicit GEMM, shared-memory tiled, 4x4 register blocking).
+// This is the parity-mode (fp32 storage) path and the K=9 / K=27 first-layer path of the throughput mode;
+// the bf16 tensor-core path is conv_tc.cu.  Semantics: keras Conv2D(3x3, padding='same', bias) with HWIO kernels
+// (l3embedding/audio_model.py:376-432, l3embedding/vision_model.py:130-186), NHWC activations.
+#include "kernels.h"
+
+namespace l3 {
+
+static const int BM = 64, BN = 64, BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_conv3x3_simt(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+               T* __restrict__ out, int B, int H, int W, int Cin, int Cout) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const long long M = (long long)B * H * W;
+  const int K = 9 * Cin;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int t = threadIdx.x;
+  // A-load assignment: k_local = t % 16, pixels m_local = t/16 + 16*i
+  const int ak = t & 15;
+  long long pbase[4];
+  bool pvalid[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + (t >> 4) + 16 * i;
+    pvalid[i] = m < M;
+    long long mm = pvalid[i] ? m : 0;
+    int x = (int)(mm % W);
+    int y = (int)((mm / W) % H);
+    long long b = mm / ((long long)W * H);
+    pbase[i] = pad_off(b, y - 1, x - 1, H, W, Cin);  // top-left tap of the 3x3 window in the padded input
+  }
+  const int bn = t & 63, bk = t >> 6;
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    {
+      int k = k0 + ak;
+      bool kv = k < K;
+      int tap = kv ? k / Cin : 0;
+      int ci = k - tap * Cin;
+      long long doff = ((long long)(tap / 3) * (W + 2) + tap % 3) * Cin + ci;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+        if (kv && pvalid[i]) v = to_f(in[pbase[i] + doff]);
+        As[ak][(t >> 4) + 16 * i] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int kk = bk + 4 * i;
+        int kg = k0 + kk;
+        float v = 0.f;
+        if (kg < K && n0 + bn < Cout) v = w[(long long)kg * Cout + n0 + bn];
+        Bs[kk][bn] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < Cout) out[m * Cout + n] = from_f<T>(acc[i][j] + (bias ? bias[n] : 0.f));
+    }
+  }
+}
+
+template <typename T>
+int launch_conv3x3_simt(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int Cin, int Cout,
+                        cudaStream_t s) {
+  long long M = (long long)B * H * W;
+  dim3 grid(ceil_div(M, BM), ceil_div(Cout, BN));
+  k_conv3x3_simt<T><<<grid, 256, 0, s>>>(in, w, bias, out, B, H, W, Cin, Cout);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_conv3x3_simt<float>(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_conv3x3_simt<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
+
+// ---- weight gradient ----------------------------------------------------------------------------------
+// a: padded (B,H+2,W+2,Cin); dz: padded (B,H+2,W+2,Cout)
+// grid.x = ci tiles * co tiles * 9 taps ; grid.y = split-K slices over the B*H*W pixels (fp32 atomics)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_wgrad3x3_simt(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
+                int B, int H, int W, int Cin, int Cout, int ci_tiles, int co_tiles, long long m_per_slice) {
+  __shared__ __align__(16) float As[BK][BM];  // [pixel][ci]
+  __shared__ __align__(16) float Bs[BK][BN];  // [pixel][co]
+  const long long M = (long long)B * H * W;
+  int bid = blockIdx.x;
+  const int tap = bid % 9;
+  bid /= 9;
+  const int co0 = (bid % co_tiles) * BN;
+  const int ci0 = (bid / co_tiles) * BM;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  const long long mbeg = (long long)blockIdx.y * m_per_slice;
+  const long long mend = min(M, mbeg + m_per_slice);
+  const int t = threadIdx.x;
+  const int lc = t & 63, lk = t >> 6;
+  const int tx = t & 15, ty = t >> 4;
+  const bool do_bias = (tap == 4) && (ci0 == 0) && (db != nullptr);
+  float bsum = 0.f;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long mc = mbeg; mc < mend; mc += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int kk = lk + 4 * i;
+      long long m = mc + kk;
+      float va = 0.f, vb = 0.f;
+      if (m < mend) {
+        int x = (int)(m % W);
+        int y = (int)((m / W) % H);
+        long long b = m / ((long long)W * H);
+        if (ci0 + lc < Cin) va = to_f(a[pad_off(b, y + dy, x + dx, H, W, Cin) + ci0 + lc]);
+        if (co0 + lc < Cout) vb = to_f(dz[pad_off(b, y, x, H, W, Cout) + co0 + lc]);
+      }
+      As[kk][lc] = va;
+      Bs[kk][lc] = vb;
+    }
+    __syncthreads();
+    if (do_bias && t < 64) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) bsum += Bs[kk][t];
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 av4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 bv4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {av4.x, av4.y, av4.z, av4.w}, bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int ci = ci0 + ty * 4 + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = co0 + tx * 4 + j;
+      if (co < Cout) atomicAdd(&dw[((long long)tap * Cin + ci) * Cout + co], acc[i][j]);
+    }
+  }
+  if (do_bias && t < 64 && co0 + t < Cout) atomicAdd(&db[co0 + t], bsum);
+}
+
+template <typename T>
+int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                         cudaStream_t s) {
+  long long M = (long long)B * H * W;
+  int ci_tiles = ceil_div(Cin, BM), co_tiles = ceil_div(Cout, BN);
+  int tiles = ci_tiles * co_tiles * 9;
+  long long slices = (148LL * 8 + tiles - 1) / tiles;
+  long long max_slices = (M + 255) / 256;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  long long m_per_slice = ((M + slices - 1) / slices + BK - 1) / BK * BK;
+  slices = (M + m_per_slice - 1) / m_per_slice;
+  dim3 grid(tiles, (unsigned)slices);
+  k_wgrad3x3_simt<T><<<grid, 256, 0, s>>>(a, dz, dw, db, B, H, W, Cin, Cout, ci_tiles, co_tiles, m_per_slice);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_wgrad3x3_simt<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_wgrad3x3_simt<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t);
+
+__global__ void k_flip_transpose(const float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout) {
+  long long n = 9LL * Cin * Cout;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // i indexes wt[tap][co][ci]
+  int ci = (int)(i % Cin);
+  int co = (int)((i / Cin) % Cout);
+  int tap = (int)(i / ((long long)Cin * Cout));
+  wt[i] = w[((long long)(8 - tap) * Cin + ci) * Cout + co];
+}
+int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStream_t s) {
+  long long n = 9LL * Cin * Cout;
+  k_flip_transpose<<<ceil_div(n, 256), 256, 0, s>>>(w, w_t, Cin, Cout);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace l3

@@ -1,0 +1,674 @@
+// HBM-bound kernels of the L3 AVC step: input scaling, BatchNorm statistics / finalize / backward,
+// activation (+2x2 max-pool) forward and backward, global max-pool, embedding pool, Adam.
+// Reference semantics: keras BatchNormalization / Activation('relu') / MaxPooling2D as instantiated in
+// l3embedding/audio_model.py:370-437 and l3embedding/vision_model.py:124-190; Adam at l3embedding/train.py:282.
+// All activations are NHWC; per-thread work is 8 channels (one 16-byte bf16 vector) with coalesced access.
+#include "kernels.h"
+
+namespace l3 {
+
+static const int kThreads = 256;
+static const int kMaxBlocks = 148 * 8;  // grid-stride kernels: a multiple of the SM count
+
+// --------------------------------------------------------------------------------------------
+// video u8 -> float : 2*(x/255) - 1      (train.py:186; divide in fp64 then fp32 affine, as skimage does)
+// --------------------------------------------------------------------------------------------
+__global__ void k_video_to_f32(const uint8_t* __restrict__ v, float* __restrict__ out, long long n4) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const uchar4* v4 = reinterpret_cast<const uchar4*>(v);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (; i < n4; i += stride) {
+    uchar4 u = v4[i];
+    float4 f;
+    f.x = 2.0f * (float)((double)u.x / 255.0) - 1.0f;
+    f.y = 2.0f * (float)((double)u.y / 255.0) - 1.0f;
+    f.z = 2.0f * (float)((double)u.z / 255.0) - 1.0f;
+    f.w = 2.0f * (float)((double)u.w / 255.0) - 1.0f;
+    o4[i] = f;
+  }
+}
+int launch_video_to_f32(const uint8_t* v, float* out, long long n, cudaStream_t s) {
+  L3_REQUIRE(n % 4 == 0, "video element count must be a multiple of 4");
+  long long n4 = n / 4;
+  int blocks = (int)((n4 + kThreads - 1) / kThreads);
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  k_video_to_f32<<<blocks, kThreads, 0, s>>>(v, out, n4);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares over [rows][C]
+// --------------------------------------------------------------------------------------------
+template <typename T, bool RELU>
+__global__ void k_channel_stats_vec(const T* __restrict__ x, long long rows, int C, double* __restrict__ sum) {
+  extern __shared__ float sh[];  // 2*C
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+    float v[8];
+    load8(x + r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = RELU ? fmaxf(v[i], 0.f) : v[i];
+      s1[i] += t;
+      s2[i] += t * t;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sh[g * 8 + i], s1[i]);
+    atomicAdd(&sh[C + g * 8 + i], s2[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sum[i], (double)sh[i]);
+}
+
+// small C (1..4): one thread per row-strided pixel
+template <typename T>
+__global__ void k_channel_stats_small(const T* __restrict__ x, long long rows, int C, double* __restrict__ sum) {
+  __shared__ float sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0.f;
+  __syncthreads();
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) {
+      float t = to_f(x[r * C + c]);
+      s1[c] += t;
+      s2[c] += t * t;
+    }
+  for (int c = 0; c < C; ++c) {
+    float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sh[c], a);
+      atomicAdd(&sh[4 + c], b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    atomicAdd(&sum[threadIdx.x], (double)sh[threadIdx.x]);
+    atomicAdd(&sum[C + threadIdx.x], (double)sh[4 + threadIdx.x]);
+  }
+}
+
+template <typename T>
+int launch_channel_stats(const T* x, long long rows, int C, int relu, double* sum, cudaStream_t s) {
+  L3_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * C, s));
+  if (C <= 4) {
+    L3_REQUIRE(!relu, "relu stats unsupported for small C");
+    int blocks = (int)((rows + kThreads * 8 - 1) / (kThreads * 8));
+    if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    k_channel_stats_small<T><<<blocks, kThreads, 0, s>>>(x, rows, C, sum);
+  } else {
+    L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "channel_stats: unsupported C=%d", C);
+    int lanes = kThreads / (C / 8);
+    long long want = (rows + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+    int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+    if (relu)
+      k_channel_stats_vec<T, true><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(x, rows, C, sum);
+    else
+      k_channel_stats_vec<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(x, rows, C, sum);
+  }
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_channel_stats<float>(const float*, long long, int, int, double*, cudaStream_t);
+template int launch_channel_stats<bf16>(const bf16*, long long, int, int, double*, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// BN finalize: mean / biased var -> invstd, scale, shift ; moving-stat update (momentum 0.99, eps 1e-3)
+// --------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(BnRef bn, double count, int training, float momentum, float eps, int unbiased) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= bn.C) return;
+  float mean, var;
+  if (training) {
+    double m = bn.sum[c] / count;
+    double v = bn.sum[bn.C + c] / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m;
+    var = (float)v;
+    double vu = (unbiased && count > 1.0) ? v * (count / (count - 1.0)) : v;
+    bn.moving_mean[c] = bn.moving_mean[c] * momentum + mean * (1.f - momentum);
+    bn.moving_var[c] = bn.moving_var[c] * momentum + (float)vu * (1.f - momentum);
+  } else {
+    mean = bn.moving_mean[c];
+    var = bn.moving_var[c];
+  }
+  float inv = rsqrtf(var + eps);
+  inv = inv * (1.5f - 0.5f * (var + eps) * inv * inv);  // one Newton step: full fp32 accuracy
+  float sc = bn.gamma[c] * inv;
+  bn.mean[c] = mean;
+  bn.invstd[c] = inv;
+  bn.scale[c] = sc;
+  bn.shift[c] = bn.beta[c] - mean * sc;
+}
+int launch_bn_finalize(const BnRef& bn, long long count, int training, float momentum, float eps, int unbiased,
+                       cudaStream_t s) {
+  k_bn_finalize<<<ceil_div(bn.C, 128), 128, 0, s>>>(bn, (double)count, training, momentum, eps, unbiased);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// input BN apply (C = 1 or 3), float (B,H,W,C) -> T in the zero-haloed layout (B,H+2,W+2,C) that every
+// convolution reads.  scale == nullptr: plain convert.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_affine_small(const float* __restrict__ x, T* __restrict__ out, long long n, int H, int W, int C,
+                               const float* __restrict__ scale, const float* __restrict__ shift) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = x[i];
+    int c = (int)(i % C);
+    long long p = i / C;
+    int xx = (int)(p % W);
+    int yy = (int)((p / W) % H);
+    long long b = p / ((long long)W * H);
+    if (scale) v = v * scale[c] + shift[c];
+    out[pad_off(b, yy, xx, H, W, C) + c] = from_f<T>(v);
+  }
+}
+template <typename T>
+int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, const float* scale, const float* shift,
+                        cudaStream_t s) {
+  long long n = (long long)B * H * W * C;
+  long long want = (n + kThreads * 4 - 1) / (kThreads * 4);
+  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+  k_affine_small<T><<<blocks, kThreads, 0, s>>>(x, out, n, H, W, C, scale, shift);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_affine_small<float>(const float*, float*, int, int, int, int, const float*, const float*, cudaStream_t);
+template int launch_affine_small<bf16>(const float*, bf16*, int, int, int, int, const float*, const float*, cudaStream_t);
+
+// zero the one-pixel halo of a padded (B,H+2,W+2,C) buffer (buffers re-used at several geometries)
+template <typename T>
+__global__ void k_zero_halo(T* __restrict__ buf, int B, int H, int W, int C) {
+  const int per_img = 2 * (W + 2) + 2 * H;  // halo pixels per image
+  long long total = (long long)B * per_img * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long q = i / C;
+    int h = (int)(q % per_img);
+    long long b = q / per_img;
+    int yp, xp;
+    if (h < W + 2) { yp = 0; xp = h; }
+    else if (h < 2 * (W + 2)) { yp = H + 1; xp = h - (W + 2); }
+    else { int r = h - 2 * (W + 2); yp = 1 + (r >> 1); xp = (r & 1) ? W + 1 : 0; }
+    buf[((b * (H + 2) + yp) * (long long)(W + 2) + xp) * C + c] = from_f<T>(0.f);
+  }
+}
+template <typename T>
+int launch_zero_halo(T* buf, int B, int H, int W, int C, cudaStream_t s) {
+  long long total = (long long)B * (2 * (W + 2) + 2 * H) * C;
+  long long want = (total + kThreads - 1) / kThreads;
+  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+  k_zero_halo<T><<<blocks, kThreads, 0, s>>>(buf, B, H, W, C);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_zero_halo<float>(float*, int, int, int, int, cudaStream_t);
+template int launch_zero_halo<bf16>(bf16*, int, int, int, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// activation forward: a = pool2x2?( relu_first ? relu(z)*s+t : relu(z*s+t) );  z unpadded, a zero-haloed padded
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void act8(const float (&z)[8], const float (&sc)[8], const float (&sh)[8], int relu_first,
+                                     float (&y)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    y[i] = relu_first ? fmaxf(z[i], 0.f) * sc[i] + sh[i] : fmaxf(z[i] * sc[i] + sh[i], 0.f);
+}
+
+template <typename T>
+__global__ void k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int OH, int OW,
+                          long long total, const float* __restrict__ scale, const float* __restrict__ shift, int pool,
+                          int relu_first) {
+  const int groups = C >> 3;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int g = (int)(idx % groups);
+  long long p = idx / groups;
+  int ox = (int)(p % OW);
+  int oy = (int)((p / OW) % OH);
+  long long b = p / ((long long)OW * OH);
+  float sc[8], sh[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+  float y[8];
+  if (!pool) {
+    float v[8];
+    load8(z + ((b * H + oy) * W + ox) * C + g * 8, v);
+    act8(v, sc, sh, relu_first, y);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8], t[8];
+      load8(z + ((b * H + 2 * oy + (k >> 1)) * W + 2 * ox + (k & 1)) * C + g * 8, v);
+      act8(v, sc, sh, relu_first, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = k == 0 ? t[i] : fmaxf(y[i], t[i]);
+    }
+  }
+  store8(a + pad_off(b, oy, ox, OH, OW, C) + g * 8, y);
+}
+template <typename T>
+int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
+                   int relu_first, cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0, "act_fwd: C%%8");
+  int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
+  long long total = (long long)B * OH * OW * (C / 8);
+  k_act_fwd<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(z, a, H, W, C, OH, OW, total, scale, shift, pool,
+                                                               relu_first);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_act_fwd<float>(const float*, float*, int, int, int, int, const float*, const float*, int, int, cudaStream_t);
+template int launch_act_fwd<bf16>(const bf16*, bf16*, int, int, int, int, const float*, const float*, int, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// global max-pool forward over relu(bn(z)) -> (B,C) float + argmax pixel (first max in row-major order)
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_gmaxpool_fwd(const T* __restrict__ z, int HW, int C, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float* __restrict__ out, int out_stride,
+                               int* __restrict__ argmax) {
+  extern __shared__ float shm[];  // lanes*C floats + lanes*C ints
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  const int b = blockIdx.x;
+  float* smax = shm;
+  int* sidx = reinterpret_cast<int*>(shm + lanes * C);
+  float sc[8], sh[8], best[8];
+  int bi[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+  for (int p = lane; p < HW; p += lanes) {
+    float v[8], y[8];
+    load8(z + ((long long)b * HW + p) * C + g * 8, v);
+    act8(v, sc, sh, 0, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (y[i] > best[i]) { best[i] = y[i]; bi[i] = p; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { smax[lane * C + g * 8 + i] = best[i]; sidx[lane * C + g * 8 + i] = bi[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = smax[c];
+    int mi = sidx[c];
+    for (int l = 1; l < lanes; ++l) {
+      float v = smax[l * C + c];
+      int vi = sidx[l * C + c];
+      if (v > m || (v == m && vi < mi)) { m = v; mi = vi; }
+    }
+    out[(long long)b * out_stride + c] = m;
+    argmax[b * C + c] = mi;
+  }
+}
+template <typename T>
+int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, const float* shift, float* out,
+                        int out_stride, int* argmax, cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "gmaxpool: C=%d", C);
+  int lanes = kThreads / (C / 8);
+  size_t sm = (size_t)lanes * C * 8;
+  k_gmaxpool_fwd<T><<<B, kThreads, sm, s>>>(z, HW, C, scale, shift, out, out_stride, argmax);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_gmaxpool_fwd<float>(const float*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
+template int launch_gmaxpool_fwd<bf16>(const bf16*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
+
+// global max-pool backward: dy = scatter(dpool) masked by relu; BN-backward sums (deterministic, one thread / channel)
+template <typename T>
+__global__ void k_gmaxpool_bwd(const float* __restrict__ dpool, int dpool_stride, const int* __restrict__ argmax,
+                               const T* __restrict__ z, T* __restrict__ dy, BnRef bn, int B, int H, int W, int C) {
+  const int HW = H * W;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = bn.scale[c], sh = bn.shift[c], mean = bn.mean[c], inv = bn.invstd[c];
+  double s1 = 0, s2 = 0;
+  for (int b = 0; b < B; ++b) {
+    int p = argmax[b * C + c];
+    long long off = ((long long)b * HW + p) * C + c;
+    float zz = to_f(z[off]);
+    float g = dpool[(long long)b * dpool_stride + c];
+    if (zz * sc + sh > 0.f) {
+      T gt = from_f<T>(g);
+      dy[pad_off(b, p / W, p % W, H, W, C) + c] = gt;
+      float gq = to_f(gt);
+      s1 += gq;
+      s2 += gq * ((zz - mean) * inv);
+    }
+  }
+  bn.sum[c] = s1;
+  bn.sum[C + c] = s2;
+}
+template <typename T>
+int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax, const T* z, T* dy, const BnRef& bn,
+                        int B, int H, int W, int C, cudaStream_t s) {
+  L3_CHECK_CUDA(cudaMemsetAsync(dy, 0, sizeof(T) * (size_t)B * (H + 2) * (W + 2) * C, s));
+  k_gmaxpool_bwd<T><<<ceil_div(C, 32), 32, 0, s>>>(dpool, dpool_stride, argmax, z, dy, bn, B, H, W, C);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_gmaxpool_bwd<float>(const float*, int, const int*, const float*, float*, const BnRef&, int, int, int, int, cudaStream_t);
+template int launch_gmaxpool_bwd<bf16>(const float*, int, const int*, const bf16*, bf16*, const BnRef&, int, int, int, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// activation backward: da (pooled res) -> dy (grad wrt BN output, full res) + sum(dy), sum(dy*xhat)
+//   normal     : a = pool(relu(bn(z)))      dy = unpool(da) * [bn(z) > 0]      xhat from z
+//   relu_first : a = pool(bn(relu(z)))      dy = unpool(da)                    xhat from relu(z)
+// max-pool routes to the first maximum in window order (0,0),(0,1),(1,0),(1,1); rows/cols dropped by
+// 'valid' pooling of odd sizes receive zero gradient.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_act_bwd(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dy, int H, int W, int C,
+                          int OH, int OW, long long npix, BnRef bn, int pool, int relu_first) {
+  extern __shared__ float sh[];  // 2*C
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float sc[8], sf[8], mean[8], inv[8], s1[8], s2[8];
+  load8(bn.scale + g * 8, sc);
+  load8(bn.shift + g * 8, sf);
+  load8(bn.mean + g * 8, mean);
+  load8(bn.invstd + g * 8, inv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+    float g8[8];
+    load8(da + p * C + g * 8, g8);
+    const int ox = (int)(p % OW);
+    const int oy = (int)((p / OW) % OH);
+    const long long b = p / ((long long)OW * OH);
+    if (!pool) {
+      float v[8], y[8], o[8];
+      load8(z + p * C + g * 8, v);
+      act8(v, sc, sf, relu_first, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
+        d = to_f(from_f<T>(d));
+        float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
+        o[i] = d;
+        s1[i] += d;
+        s2[i] += d * ((xin - mean[i]) * inv[i]);
+      }
+      store8(dy + pad_off(b, oy, ox, H, W, C) + g * 8, o);
+    } else {
+      float v[4][8], y[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        load8(z + ((b * H + 2 * oy + (k >> 1)) * W + 2 * ox + (k & 1)) * C + g * 8, v[k]);
+        act8(v[k], sc, sf, relu_first, y[k]);
+      }
+      float o[4][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int arg = 0;
+        float m = y[0][i];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (y[k][i] > m) { m = y[k][i]; arg = k; }
+        float d = relu_first ? g8[i] : (m > 0.f ? g8[i] : 0.f);
+        d = to_f(from_f<T>(d));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][i] = (k == arg) ? d : 0.f;
+        float zin = arg == 0 ? v[0][i] : arg == 1 ? v[1][i] : arg == 2 ? v[2][i] : v[3][i];
+        float xin = relu_first ? fmaxf(zin, 0.f) : zin;
+        s1[i] += d;
+        s2[i] += d * ((xin - mean[i]) * inv[i]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) store8(dy + pad_off(b, 2 * oy + (k >> 1), 2 * ox + (k & 1), H, W, C) + g * 8, o[k]);
+      // rows / columns dropped by valid pooling of odd sizes get zero gradient
+      if ((W & 1) && ox == OW - 1) {
+        store8(dy + pad_off(b, 2 * oy, W - 1, H, W, C) + g * 8, zero8);
+        store8(dy + pad_off(b, 2 * oy + 1, W - 1, H, W, C) + g * 8, zero8);
+      }
+      if ((H & 1) && oy == OH - 1) {
+        store8(dy + pad_off(b, H - 1, 2 * ox, H, W, C) + g * 8, zero8);
+        store8(dy + pad_off(b, H - 1, 2 * ox + 1, H, W, C) + g * 8, zero8);
+        if ((W & 1) && ox == OW - 1) store8(dy + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, zero8);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sh[g * 8 + i], s1[i]);
+    atomicAdd(&sh[C + g * 8 + i], s2[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn.sum[i], (double)sh[i]);
+}
+// da: unpadded (B,OH,OW,C); z: unpadded (B,H,W,C); dy: zero-haloed padded (B,H+2,W+2,C) (halo zeroed here)
+template <typename T>
+int launch_act_bwd(const T* da, const T* z, T* dy, int B, int H, int W, int C, const BnRef& bn, int pool,
+                   int relu_first, cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "act_bwd: C=%d", C);
+  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
+  if (launch_zero_halo<T>(dy, B, H, W, C, s)) return -1;
+  int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
+  long long npix = (long long)B * OH * OW;
+  int lanes = kThreads / (C / 8);
+  long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
+  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+  k_act_bwd<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, dy, H, W, C, OH, OW, npix, bn, pool, relu_first);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_act_bwd<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_act_bwd<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+
+// BN backward finalize: dgamma, dbeta, c1 = mean(dy), c2 = mean(dy*xhat)
+__global__ void k_bn_bwd_finalize(BnRef bn, double count) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= bn.C) return;
+  double s1 = bn.sum[c], s2 = bn.sum[bn.C + c];
+  bn.d_beta[c] = (float)s1;
+  bn.d_gamma[c] = (float)s2;
+  bn.c1[c] = (float)(s1 / count);
+  bn.c2[c] = (float)(s2 / count);
+}
+int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s) {
+  k_bn_bwd_finalize<<<ceil_div(bn.C, 128), 128, 0, s>>>(bn, (double)count);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// BN backward apply (in place on the padded dy buffer; z unpadded):
+//   dz = scale*(dy - c1 - xhat*c2)  [ * (z>0) and xhat from relu(z) when relu_first ]
+template <typename T>
+__global__ void k_bn_bwd_apply(T* __restrict__ dy, const T* __restrict__ z, long long total, int H, int W, int C,
+                               BnRef bn, int relu_first) {
+  const int groups = C >> 3;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int g = (int)(idx % groups);
+  long long p = idx / groups;
+  const int xx = (int)(p % W);
+  const int yy = (int)((p / W) % H);
+  const long long b = p / ((long long)W * H);
+  T* dptr = dy + pad_off(b, yy, xx, H, W, C) + g * 8;
+  float sc[8], mean[8], inv[8], c1[8], c2[8], d[8], v[8], o[8];
+  load8(bn.scale + g * 8, sc);
+  load8(bn.mean + g * 8, mean);
+  load8(bn.invstd + g * 8, inv);
+  load8(bn.c1 + g * 8, c1);
+  load8(bn.c2 + g * 8, c2);
+  load8(dptr, d);
+  load8(z + p * C + g * 8, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
+    float xh = (xin - mean[i]) * inv[i];
+    float r = sc[i] * (d[i] - c1[i] - xh * c2[i]);
+    if (relu_first && !(v[i] > 0.f)) r = 0.f;
+    o[i] = r;
+  }
+  store8(dptr, o);
+}
+template <typename T>
+int launch_bn_bwd_apply(T* dy, const T* z, int B, int H, int W, int C, const BnRef& bn, int relu_first,
+                        cudaStream_t s) {
+  long long total = (long long)B * H * W * (C / 8);
+  k_bn_bwd_apply<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(dy, z, total, H, W, C, bn, relu_first);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_bn_bwd_apply<float>(float*, const float*, int, int, int, int, const BnRef&, int, cudaStream_t);
+template int launch_bn_bwd_apply<bf16>(bf16*, const bf16*, int, int, int, int, const BnRef&, int, cudaStream_t);
+
+// input BN (C=1|3) backward sums from da (T) and x0 (float)
+template <typename T>
+__global__ void k_input_bn_bwd_stats(const T* __restrict__ da, const float* __restrict__ x0, long long rows, int C,
+                                     BnRef bn) {
+  __shared__ float sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0.f;
+  __syncthreads();
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) {
+      float d = to_f(da[r * C + c]);
+      float xh = (x0[r * C + c] - bn.mean[c]) * bn.invstd[c];
+      s1[c] += d;
+      s2[c] += d * xh;
+    }
+  for (int c = 0; c < C; ++c) {
+    float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sh[c], a);
+      atomicAdd(&sh[4 + c], b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    atomicAdd(&bn.sum[threadIdx.x], (double)sh[threadIdx.x]);
+    atomicAdd(&bn.sum[C + threadIdx.x], (double)sh[4 + threadIdx.x]);
+  }
+}
+template <typename T>
+int launch_input_bn_bwd_stats(const T* da, const float* x0, long long rows, int C, const BnRef& bn, cudaStream_t s) {
+  L3_REQUIRE(C <= 4, "input bn: C<=4");
+  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
+  int blocks = (int)((rows + kThreads * 8 - 1) / (kThreads * 8));
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  k_input_bn_bwd_stats<T><<<blocks, kThreads, 0, s>>>(da, x0, rows, C, bn);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_input_bn_bwd_stats<float>(const float*, const float*, long long, int, const BnRef&, cudaStream_t);
+template int launch_input_bn_bwd_stats<bf16>(const bf16*, const float*, long long, int, const BnRef&, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// embedding head: MaxPooling2D(pool, padding='same') over the raw conv4b map, Flatten (h,w,c)
+// (audio_model.py:480-484, vision_model.py:212-215).  Windows divide evenly for every model type.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_embed_pool(const T* __restrict__ z, int H, int W, int C, int ph, int pw, int OH, int OW,
+                             long long total, float* __restrict__ out) {
+  const int groups = C >> 3;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int g = (int)(idx % groups);
+  long long p = idx / groups;
+  int ox = (int)(p % OW);
+  int oy = (int)((p / OW) % OH);
+  long long b = p / ((long long)OW * OH);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int dy = 0; dy < ph; ++dy)
+    for (int dx = 0; dx < pw; ++dx) {
+      int y = oy * ph + dy, x = ox * pw + dx;
+      if (y >= H || x >= W) continue;
+      float v[8];
+      load8(z + ((b * H + y) * W + x) * C + g * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+    }
+  store8(out + p * C + g * 8, m);
+}
+template <typename T>
+int launch_embed_pool(const T* z, int B, int H, int W, int C, int ph, int pw, float* out, cudaStream_t s) {
+  L3_REQUIRE(H % ph == 0 && W % pw == 0, "embed_pool: pool must divide the map (%dx%d by %dx%d)", H, W, ph, pw);
+  int OH = H / ph, OW = W / pw;
+  long long total = (long long)B * OH * OW * (C / 8);
+  k_embed_pool<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(z, H, W, C, ph, pw, OH, OW, total, out);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_embed_pool<float>(const float*, int, int, int, int, int, int, float*, cudaStream_t);
+template int launch_embed_pool<bf16>(const bf16*, int, int, int, int, int, int, float*, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------
+// Keras-2.0.9 Adam over the flat trainable arena; the first n_l2 scalars are conv/dense kernels and
+// receive the l2(1e-5) regulariser gradient 2*l2*w (model.py:23-31, audio_model.py:376-432).
+// --------------------------------------------------------------------------------------------
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, long long n_l2, float lr_t, float b1, float b2, float eps,
+                       float l2) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float w = p[i];
+    float gi = g[i] + (i < n_l2 ? 2.f * l2 * w : 0.f);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = w - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float lr_t, float b1,
+                float b2, float eps, float l2, cudaStream_t s) {
+  k_adam<<<kMaxBlocks, kThreads, 0, s>>>(p, g, m, v, n, n_l2, lr_t, b1, b2, eps, l2);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void k_l2_penalty(const float* __restrict__ p, long long n, double* __restrict__ out) {
+  __shared__ double sh[8];
+  double acc = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    acc += (double)w * w;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+int launch_l2_penalty(const float* p, long long n_l2, double* out, cudaStream_t s) {
+  L3_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+  k_l2_penalty<<<148 * 2, kThreads, 0, s>>>(p, n_l2, out);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_zero(void* p, size_t bytes, cudaStream_t s) {
+  L3_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, s));
+  return 0;
+}
+
+}  // namespace l3

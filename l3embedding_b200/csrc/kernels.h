@@ -1,0 +1,117 @@
+// Internal launcher declarations (host side). Every launcher is asynchronous on `s`.
+#pragma once
+#include "common.cuh"
+
+namespace l3 {
+
+// ---- front-end (frontend.cu) ------------------------------------------------------------
+struct FrontendPlan {
+  int n_dft;        // 512 | 2048
+  int n_hop;        // 242
+  int n_frames;     // 197 | 199
+  int left_pad;     // 0 | 982
+  int n_out;        // 257 (linear) | n_mels
+  int mel;          // 1 -> mel filterbank
+  int decibel;      // 1 -> 10*log10, per-clip max, clip -80 ; 0 -> log(max(x,1e-12))/5
+  int n_samples;    // 48000
+  // device constants (built once per ctx by frontend_build_tables)
+  const float2* twiddle;    // n_dft/2 entries exp(-2 pi i j / n_dft)
+  const float* window;      // n_dft periodic hann
+  const int* mel_start;     // [n_mels]
+  const int* mel_count;     // [n_mels]
+  const int* mel_offset;    // [n_mels] into mel_weight
+  const float* mel_weight;  // packed non-zeros
+};
+// bytes of device memory needed for the tables
+size_t frontend_table_bytes(int n_dft, int n_mels);
+// fills `dev_mem` (device) with tables and completes `plan` pointers. Synchronous H2D copies on `s`.
+int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem, cudaStream_t s);
+// audio: int16 (is_i16=1) or float (B, n_samples). raw: (B, n_out, n_frames) float scratch; clip_max: int[B].
+// out: (B, n_out, n_frames) float final.
+int launch_frontend(const FrontendPlan& p, const void* audio, int is_i16, int B, float* out, int* clip_max,
+                    cudaStream_t s);
+
+// ---- elementwise / reductions (elementwise.cu) ------------------------------------------
+int launch_video_to_f32(const uint8_t* v, float* out, long long n, cudaStream_t s);
+template <typename T>
+int launch_channel_stats(const T* x, long long rows, int C, int relu, double* sum2C, cudaStream_t s);
+int launch_bn_finalize(const BnRef& bn, long long count, int training, float momentum, float eps, int unbiased,
+                       cudaStream_t s);
+template <typename T>
+int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, const float* scale, const float* shift,
+                        cudaStream_t s);   // out: zero-haloed padded (B,H+2,W+2,C)
+template <typename T>
+int launch_zero_halo(T* buf, int B, int H, int W, int C, cudaStream_t s);
+template <typename T>
+int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
+                   int relu_first, cudaStream_t s);
+template <typename T>
+int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, const float* shift, float* out,
+                        int out_stride, int* argmax, cudaStream_t s);
+template <typename T>
+int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax, const T* z, T* dy, const BnRef& bn,
+                        int B, int H, int W, int C, cudaStream_t s);   // dy: padded
+template <typename T>
+int launch_act_bwd(const T* da, const T* z, T* dy, int B, int H, int W, int C, const BnRef& bn, int pool,
+                   int relu_first, cudaStream_t s);
+int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s);
+template <typename T>
+int launch_bn_bwd_apply(T* dy_inout, const T* z, int B, int H, int W, int C, const BnRef& bn, int relu_first,
+                        cudaStream_t s);   // dy: padded, z: unpadded
+// input BN backward reductions: sum(da), sum(da*xhat) with xhat from float x0
+template <typename T>
+int launch_input_bn_bwd_stats(const T* da, const float* x0, long long rows, int C, const BnRef& bn, cudaStream_t s);
+// embedding head: MaxPooling2D(pool,'same') over raw z (B,H,W,C) -> (B, OH*OW*C) float, flatten (h,w,c)
+template <typename T>
+int launch_embed_pool(const T* z, int B, int H, int W, int C, int ph, int pw, float* out, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, long long n_l2, float lr_t, float b1,
+                float b2, float eps, float l2, cudaStream_t s);
+int launch_l2_penalty(const float* p, long long n_l2, double* out, cudaStream_t s);
+int launch_zero(void* p, size_t bytes, cudaStream_t s);
+
+// ---- SIMT fp32-accumulate convolutions (conv_simt.cu) --------------------------------------
+// out[b,y,x,co] = bias[co] + sum_{ky,kx,ci} in[b,y+ky-1,x+kx-1,ci] * w[(ky*3+kx)*Cin*Cout + ci*Cout + co]
+template <typename T>
+int launch_conv3x3_simt(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int Cin,
+                        int Cout, cudaStream_t s);
+// dw[(ky*3+kx)*Cin*Cout + ci*Cout + co] += sum_{b,y,x} a[b,y+ky-1,x+kx-1,ci] * dz[b,y,x,co]   (dw pre-zeroed)
+// db[co] += sum dz
+template <typename T>
+int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                         cudaStream_t s);
+// w_t[(ky*3+kx)*Cout*Cin + co*Cin + ci] = w[((2-ky)*3+(2-kx))*Cin*Cout + ci*Cout + co]  (for dgrad-as-conv)
+int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStream_t s);
+
+// ---- head (head.cu) ----------------------------------------------------------------------------
+struct HeadRef {
+  const float *w1, *b1, *w2, *b2;   // params: (1024,128),(128),(128,2),(2)
+  float *dw1, *db1, *dw2, *db2;     // grads
+  float* concat;                    // (B,1024) [vision | audio]
+  float* hidden;                    // (B,128)
+  float* probs;                     // (B,2)
+  float* logits;                    // (B,2)
+  float* dlogits;                   // (B,2)
+  float* dhidden;                   // (B,128)
+  float* dconcat;                   // (B,1024)
+  float* metrics;                   // [0]=sum ce, [1]=#correct   (device, accumulated with atomics; zero first)
+};
+int launch_head_fwd(const HeadRef& h, const float* labels, int B, float grad_scale, cudaStream_t s);
+int launch_head_bwd(const HeadRef& h, int B, cudaStream_t s);
+
+// ---- tcgen05 bf16 implicit-GEMM convolutions (conv_tc.cu) ---------------------------------------
+// 1 when the running device is sm_100 and the driver exposes cuTensorMapEncodeTiled.
+int conv_tc_supported();
+// Weight pre-pack: fp32 HWIO (3,3,Cin,Cout) -> bf16 K-major rows [(tap*Cin/64 + kc)*Cout + co][64 ci] (one TMA box
+// row = 128 B).  flip_transpose=1 packs the dgrad operand: taps flipped and Cin/Cout swapped, i.e. the result is the
+// forward pack of a conv with Cin' = Cout, Cout' = Cin.
+int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int flip_transpose, cudaStream_t s);
+// Forward / dgrad conv on tensor cores. in: zero-haloed padded bf16 (B,H+2,W+2,Cin), Cin%64==0, Cout%64==0;
+// out: unpadded bf16 (B,H,W,Cout); bias may be null.
+int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
+                      int Cout, cudaStream_t s);
+// Weight gradient on tensor cores: a padded (B,H+2,W+2,Cin), dz padded (B,H+2,W+2,Cout) with zero halos;
+// dw (3,3,Cin,Cout) fp32 and db (Cout) are accumulated into (pre-zeroed by the caller).
+int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                       cudaStream_t s);
+
+}  // namespace l3

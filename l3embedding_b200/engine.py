@@ -1,0 +1,258 @@
+"""Device-side state of one L3 model replica: flat arenas + workspace (torch tensors used as storage only) and
+the calls into libl3b200.so that replace keras `train_on_batch` / `predict` (l3embedding/train.py:408-414,
+data/usc/features.py:304).  All arithmetic happens in the CUDA library; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import L3Error
+from .weights_io import he_normal_weights
+
+SR = 48000
+
+
+def _as_device(x, device, dtypes):
+    """numpy / torch (host or device) -> contiguous device tensor of one of `dtypes` (no value conversion)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("expected numpy array or torch tensor, got %r" % type(x))
+    if x.dtype not in dtypes:
+        raise TypeError("unsupported dtype %s (want one of %s)" % (x.dtype, dtypes))
+    return x.to(device, non_blocking=True).contiguous()
+
+
+class Engine:
+    """One replica on one GPU.  dtype 'f32' = parity mode (fp32 storage, fp32 SIMT convolutions);
+    'bf16' = throughput mode (bf16 activations, tcgen05 convolutions with fp32 accumulation)."""
+
+    def __init__(self, model_type: str, max_batch: int, dtype: str = "f32", training: bool = True,
+                 towers=("vision", "audio"), device: Optional[torch.device] = None, host_staging: bool = True,
+                 weights: Optional[Dict[str, np.ndarray]] = None, seed: int = 20180123):
+        self.lib = _lib.load()
+        self.model_type = model_type
+        self.mid = _lib.model_id(model_type)
+        if dtype not in ("f32", "bf16"):
+            raise ValueError("dtype must be 'f32' or 'bf16'")
+        if not torch.cuda.is_available():
+            raise L3Error("no CUDA device: the L3 B200 path has no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.dtype = dtype
+        self.training = bool(training)
+        self.max_batch = int(max_batch)
+        self.table = _lib.tensor_table(model_type)
+        self.index = {n: (a, o, s) for n, a, o, s in self.table}
+        self.n_params = int(self.lib.l3_param_count(self.mid))
+        self.n_l2 = int(self.lib.l3_l2_count(self.mid))
+        self.n_state = int(self.lib.l3_state_count(self.mid))
+        self.flags = (_lib.WS_TRAINING if training else 0) | (_lib.WS_HOST_STAGING if host_staging else 0)
+        if "vision" in towers:
+            self.flags |= _lib.WS_VISION
+        if "audio" in towers:
+            self.flags |= _lib.WS_AUDIO
+        dt = _lib.DTYPE_BF16 if dtype == "bf16" else _lib.DTYPE_F32
+        with torch.cuda.device(self.device):
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.params = torch.zeros(self.n_params, **f32)
+            self.bn_state = torch.zeros(self.n_state, **f32)
+            self.grads = torch.zeros(self.n_params, **f32) if training else None
+            self.adam_m = torch.zeros(self.n_params, **f32) if training else None
+            self.adam_v = torch.zeros(self.n_params, **f32) if training else None
+            ws_bytes = _lib.check(self.lib.l3_workspace_bytes(self.mid, self.max_batch, dt, self.flags), "l3_workspace_bytes")
+            self.workspace = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            self._ws_ptr = (base + 255) // 256 * 256
+            self.stream = torch.cuda.current_stream(self.device)
+            ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+            self.ctx = self.lib.l3_ctx_create(self.mid, self.max_batch, dt, self.flags, ptr(self.params), ptr(self.grads),
+                                              ptr(self.adam_m), ptr(self.adam_v), ptr(self.bn_state),
+                                              C.c_void_p(self._ws_ptr), ws_bytes, C.c_void_p(self.stream.cuda_stream))
+            if not self.ctx:
+                raise L3Error("l3_ctx_create failed: " + _lib.last_error())
+        self.set_weights(weights if weights is not None else he_normal_weights(model_type, seed))
+        n_out, n_frames = C.c_int(), C.c_int()
+        self.lib.l3_frontend_shape(self.mid, C.byref(n_out), C.byref(n_frames))
+        self.frontend_shape = (n_out.value, n_frames.value)
+        eh, ew = C.c_int(), C.c_int()
+        self.lib.l3_embedding_map_shape(self.mid, C.byref(eh), C.byref(ew))
+        self.embedding_map_shape = (eh.value, ew.value)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.l3_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -----------------------------------------------------------------------------------------
+    def _arena(self, arena: int, grads: bool = False):
+        if arena == 1:
+            return self.bn_state
+        return self.grads if grads else self.params
+
+    def set_weights(self, weights: Dict[str, np.ndarray]):
+        for name, (arena, off, shape) in self.index.items():
+            if name not in weights:
+                raise KeyError("missing weight '%s'" % name)
+            w = np.asarray(weights[name], dtype=np.float32)
+            if tuple(w.shape) != tuple(shape):
+                raise ValueError("weight '%s' has shape %s, expected %s" % (name, w.shape, shape))
+            n = int(np.prod(shape))
+            self._arena(arena)[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(w).reshape(-1)))
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        torch.cuda.synchronize(self.device)
+        p, s = self.params.cpu().numpy(), self.bn_state.cpu().numpy()
+        out = {}
+        for name, (arena, off, shape) in self.index.items():
+            src = s if arena == 1 else p
+            out[name] = src[off:off + int(np.prod(shape))].reshape(shape).copy()
+        return out
+
+    def get_grads(self) -> Dict[str, np.ndarray]:
+        """Gradients of the mean cross-entropy (the l2 term is applied inside l3_adam_step)."""
+        torch.cuda.synchronize(self.device)
+        g = self.grads.cpu().numpy()
+        return {name: g[off:off + int(np.prod(shape))].reshape(shape).copy()
+                for name, (arena, off, shape) in self.index.items() if arena == 0}
+
+    # ---- hot path ----------------------------------------------------------------------------------------
+    def _inputs(self, video, audio, labels=None):
+        v = _as_device(video, self.device, (torch.uint8, torch.float32)) if video is not None else None
+        a = _as_device(audio, self.device, (torch.int16, torch.float32)) if audio is not None else None
+        lab = _as_device(labels, self.device, (torch.float32,)) if labels is not None else None
+        B = (v if v is not None else a).shape[0]
+        if v is not None and tuple(v.shape) != (B, 224, 224, 3):
+            raise ValueError("video must be (B,224,224,3), got %s" % (tuple(v.shape),))
+        if a is not None and a.numel() != B * SR:
+            raise ValueError("audio must be (B,1,48000), got %s" % (tuple(a.shape),))
+        if lab is not None and tuple(lab.shape) != (B, 2):
+            raise ValueError("labels must be (B,2), got %s" % (tuple(lab.shape),))
+        if B > self.max_batch:
+            raise ValueError("batch %d exceeds max_batch %d" % (B, self.max_batch))
+        vf = _lib.VIDEO_U8 if (v is not None and v.dtype == torch.uint8) else _lib.VIDEO_F32
+        af = _lib.AUDIO_I16 if (a is not None and a.dtype == torch.int16) else _lib.AUDIO_F32
+        return v, vf, a, af, lab, B
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def forward_backward(self, video, audio, labels, global_batch: Optional[int] = None):
+        with torch.cuda.device(self.device):
+            v, vf, a, af, lab, B = self._inputs(video, audio, labels)
+            self._keep = (v, a, lab)  # keep inputs alive until the stream has consumed them
+            _lib.check(self.lib.l3_forward_backward(self.ctx, self._p(v), vf, self._p(a), af, self._p(lab), B,
+                                                    int(global_batch or B)), "l3_forward_backward")
+        return B
+
+    def adam_step(self, lr: float):
+        _lib.check(self.lib.l3_adam_step(self.ctx, float(lr)), "l3_adam_step")
+
+    def set_adam_t(self, t: int):
+        _lib.check(self.lib.l3_adam_set_t(self.ctx, int(t)), "l3_adam_set_t")
+
+    def metrics(self) -> Dict[str, float]:
+        """Synchronises.  ce = mean cross-entropy over the local batch; loss = ce + l2 penalty (keras `loss`)."""
+        out = (C.c_float * 4)()
+        _lib.check(self.lib.l3_get_metrics(self.ctx, out), "l3_get_metrics")
+        n = max(out[3], 1.0)
+        return dict(ce_sum=out[0], correct=out[1], l2=out[2], batch=out[3], ce=out[0] / n, acc=out[1] / n,
+                    loss=out[0] / n + out[2])
+
+    def train_step_host(self, video: np.ndarray, audio: np.ndarray, labels: np.ndarray, lr: float) -> Dict[str, float]:
+        """One keras train_on_batch from HOST buffers: H2D + forward + backward + Adam, metrics read back."""
+        video = np.ascontiguousarray(video)
+        audio = np.ascontiguousarray(audio)
+        labels = np.ascontiguousarray(labels, dtype=np.float32)
+        B = video.shape[0]
+        vf = _lib.VIDEO_U8 if video.dtype == np.uint8 else _lib.VIDEO_F32
+        af = _lib.AUDIO_I16 if audio.dtype == np.int16 else _lib.AUDIO_F32
+        if video.dtype not in (np.uint8, np.float32) or audio.dtype not in (np.int16, np.float32):
+            raise TypeError("video must be uint8|float32 and audio int16|float32")
+        out = (C.c_float * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_train_step_host(self.ctx, video.ctypes.data_as(C.c_void_p), vf,
+                                                   audio.ctypes.data_as(C.c_void_p), af,
+                                                   labels.ctypes.data_as(C.c_void_p), B, float(lr), out),
+                       "l3_train_step_host")
+        n = max(out[3], 1.0)
+        return dict(ce=out[0] / n, acc=out[1] / n, l2=out[2], loss=out[0] / n + out[2], batch=out[3])
+
+    def predict(self, video, audio, labels=None):
+        """Inference-mode forward (BN moving statistics): returns (probs, logits) as (B,2) numpy arrays."""
+        with torch.cuda.device(self.device):
+            v, vf, a, af, lab, B = self._inputs(video, audio, labels)
+            probs = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+            logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.l3_predict(self.ctx, self._p(v), vf, self._p(a), af, self._p(lab), B, self._p(probs),
+                                           self._p(logits)), "l3_predict")
+            return probs.cpu().numpy(), logits.cpu().numpy()
+
+    def embed_audio(self, audio, pooling: str = "original", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio (n,1,48000) -> (n, 6144|512) device tensor (load_embedding 'audio' + predict)."""
+        if pooling not in ("original", "short"):
+            raise KeyError(pooling)
+        with torch.cuda.device(self.device):
+            _, _, a, af, _, n = self._inputs(None, audio)
+            eh, ew = self.embedding_map_shape
+            full = {"cnn_L3_melspec1": {"original": (4, 8), "short": (16, 24)}}.get(
+                self.model_type, {"original": (8, 8), "short": (32, 24)})[pooling]
+            dim = (eh // full[0]) * (ew // full[1]) * 512
+            if out is None:
+                out = torch.empty(n, dim, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.l3_embed_audio(self.ctx, self._p(a), af, n,
+                                               _lib.POOL_ORIGINAL if pooling == "original" else _lib.POOL_SHORT,
+                                               self._p(out)), "l3_embed_audio")
+            self._keep = (a,)
+            return out
+
+    def embed_vision(self, video) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            v, vf, _, _, _, n = self._inputs(video, None)
+            out = torch.empty(n, 4 * 4 * 512, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.l3_embed_vision(self.ctx, self._p(v), vf, n, self._p(out)), "l3_embed_vision")
+            self._keep = (v,)
+            return out
+
+    def frontend(self, audio) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            _, _, a, af, _, n = self._inputs(None, audio)
+            out = torch.empty(n, self.frontend_shape[0], self.frontend_shape[1], dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.l3_frontend_fwd(self.ctx, self._p(a), af, n, self._p(out)), "l3_frontend_fwd")
+            self._keep = (a,)
+            return out
+
+    def debug_read(self, which: str, batch: int, cap: int = 1 << 26) -> np.ndarray:
+        """Copy an internal activation ('audio/z3', 'vision/a1', 'audio/x0', 'concat', ...) to the host as float32."""
+        buf = np.empty(cap, dtype=np.float32)
+        n = self.lib.l3_debug_read(self.ctx, which.encode(), int(batch), buf.ctypes.data_as(C.POINTER(C.c_float)), cap)
+        _lib.check(int(n), "l3_debug_read(%s)" % which)
+        return buf[:n].copy()
+
+    def profile(self, enable: bool):
+        _lib.check(self.lib.l3_ctx_profile_enable(self.ctx, int(bool(enable))), "l3_ctx_profile_enable")
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} accumulated since the last read (synchronises)."""
+        ms, n = (C.c_float * 4)(), (C.c_int * 4)()
+        _lib.check(self.lib.l3_ctx_profile_read(self.ctx, ms, n), "l3_ctx_profile_read")
+        return {k: (ms[i], n[i]) for i, k in enumerate(("conv_fwd", "conv_dgrad", "conv_wgrad", "frontend"))}
+
+    @property
+    def uses_tensor_cores(self) -> bool:
+        return bool(self.lib.l3_ctx_uses_tensor_cores(self.ctx))
+
+    def set_use_tensor_cores(self, enable: bool):
+        _lib.check(self.lib.l3_ctx_set_use_tensor_cores(self.ctx, int(bool(enable))), "l3_ctx_set_use_tensor_cores")

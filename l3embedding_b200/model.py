@@ -1,0 +1,521 @@
+"""Host-side mirror of the reference's model-builder interface (l3embedding/model.py), backed by libl3b200.so.
+
+Same names, argument meaning and error behaviour as the reference:
+    MODELS, construct_cnn_L3_{orig,kapredbinputbn,melspec1,melspec2}, gpu_wrapper      model.py:184-313
+    load_model, load_embedding, convert_num_gpus                                       model.py:38-181
+    convert_audio_model_to_embedding, construct_cnn_l3_orig_vision_embedding_model     audio_model.py:445, vision_model.py:198
+The returned objects implement the subset of the keras Model API the reference's callers use:
+compile / fit_generator / train_on_batch / predict / get_weights / set_weights / load_weights / save_weights /
+layers / get_layer / to_json / name.  Building a model and moving weights around works without a GPU; anything
+that computes requires the CUDA library and a device and raises L3Error otherwise (no CPU fallback).
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import namedtuple
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib, weights_io
+from ._lib import L3Error
+
+TensorSpec = namedtuple("TensorSpec", ["name", "shape"])
+
+CONV_NAMES = ["1a", "1b", "2a", "2b", "3a", "3b", "4a", "4b"]
+CONV_CH = [64, 64, 128, 128, 256, 256, 512, 512]
+# audio_model.py:461-478
+AUDIO_EMBED_POOL = {
+    "cnn_L3_orig": {"original": (8, 8), "short": (32, 24)},
+    "cnn_L3_kapredbinputbn": {"original": (8, 8), "short": (32, 24)},
+    "cnn_L3_melspec1": {"original": (4, 8), "short": (16, 24)},
+    "cnn_L3_melspec2": {"original": (8, 8), "short": (32, 24)},
+}
+AUDIO_FRONTEND = {  # audio_model.py:26-43,138-151,245-260,355-370
+    "cnn_L3_orig": dict(n_dft=512, n_mels=None, input_bn=False),
+    "cnn_L3_kapredbinputbn": dict(n_dft=512, n_mels=None, input_bn=True),
+    "cnn_L3_melspec1": dict(n_dft=2048, n_mels=128, input_bn=True),
+    "cnn_L3_melspec2": dict(n_dft=2048, n_mels=256, input_bn=True),
+}
+VISION_INPUT_BN = {"cnn_L3_orig": False, "cnn_L3_kapredbinputbn": True, "cnn_L3_melspec1": True, "cnn_L3_melspec2": True}
+
+
+class Adam:
+    """Stand-in for keras.optimizers.Adam(lr) (train.py:282); only the learning rate is configurable, the
+    update rule is keras 2.0.9's (beta 0.9/0.999, eps 1e-8), fused on the device."""
+
+    def __init__(self, lr=0.001, **kwargs):
+        if kwargs:
+            raise TypeError("unsupported Adam arguments: %s" % sorted(kwargs))
+        self.lr = float(lr)
+
+
+class History:
+    def __init__(self):
+        self.history: Dict[str, list] = {}
+        self.epoch: List[int] = []
+
+
+class _Layer:
+    def __init__(self, name, weight_names=(), owner=None, prefix=None):
+        self.name = name
+        self._weight_names = list(weight_names)   # canonical names, trainable first then non-trainable
+        self._owner = owner
+        self.prefix = prefix
+
+    def get_weights(self):
+        w = self._owner._weights_dict()
+        return [w[n] if not n.startswith("kapre/") else self._owner._kapre(n) for n in self._weight_names]
+
+    def set_weights(self, arrays):
+        self._owner._assign(self._weight_names, arrays)
+
+
+def _bn_names(prefix):
+    return ([prefix + "/gamma", prefix + "/beta"], [prefix + "/moving_mean", prefix + "/moving_variance"])
+
+
+class TowerModel(_Layer):
+    """'vision_model' / 'audio_model' nested model (a keras Container inside the AVC model)."""
+
+    def __init__(self, owner, tower, model_type):
+        super().__init__(tower + "_model", owner=owner)
+        self.tower = tower
+        self.model_type = model_type
+        self.layers = []
+        inp = _Layer("input_1" if tower == "vision" else "input_2", owner=owner)
+        self.layers.append(inp)
+        if tower == "audio":
+            fe = AUDIO_FRONTEND[model_type]
+            kn = ["kapre/real_kernels", "kapre/imag_kernels"] + (["kapre/freq2mel"] if fe["n_mels"] else [])
+            self.layers.append(_Layer("melspectrogram_1" if fe["n_mels"] else "spectrogram_1", kn, owner))
+            has_bn0 = fe["input_bn"]
+        else:
+            has_bn0 = VISION_INPUT_BN[model_type]
+        if has_bn0:
+            tr, nt = _bn_names(tower + "/bn0")
+            self.layers.append(_Layer("batch_normalization_0", tr + nt, owner, tower + "/bn0"))
+        for i, nm in enumerate(CONV_NAMES):
+            lname = "conv2d_" + nm
+            if nm == "4b":
+                lname = tower + "_embedding_layer"     # audio_model.py:428, vision_model.py:182
+            self.layers.append(_Layer(lname, [f"{tower}/conv{nm}/kernel", f"{tower}/conv{nm}/bias"], owner, f"{tower}/conv{nm}"))
+            tr, nt = _bn_names(f"{tower}/bn{nm}")
+            self.layers.append(_Layer("batch_normalization_" + nm, tr + nt, owner, f"{tower}/bn{nm}"))
+        # Container.weights: all trainable (layer order) then all non-trainable (layer order)
+        tr_all, nt_all = [], []
+        for l in self.layers:
+            for n in l._weight_names:
+                (nt_all if (n.startswith("kapre/") or n.endswith(("moving_mean", "moving_variance"))) else tr_all).append(n)
+        self._weight_names = tr_all + nt_all
+
+    def get_layer(self, name):
+        for l in self.layers:
+            if l.name == name:
+                return l
+        raise ValueError("No such layer: " + name)
+
+    def layerwise_weight_names(self):
+        """keras Model.get_weights() order when called on the tower itself (layer by layer)."""
+        return [n for l in self.layers for n in l._weight_names]
+
+
+class L3Model:
+    """The AVC model object `MODELS[model_type]()` returns (keras Model in the reference, model.py:32-35)."""
+
+    def __init__(self, model_type: str, name: str, num_gpus: int = 0, seed: int = 20180123):
+        if model_type not in _lib.MODEL_IDS:
+            raise ValueError('Invalid model type: "{}"'.format(model_type))
+        self.model_type = model_type
+        self.name = name
+        self.num_gpus = int(num_gpus)
+        self._seed = seed
+        self._host_weights: Optional[Dict[str, np.ndarray]] = None
+        self._engine = None
+        self.dtype = os.environ.get("L3B200_DTYPE", "bf16")
+        self.optimizer = None
+        self.loss = None
+        self.metrics_names = ["loss", "acc"]
+        self.stop_training = False
+        self.vision_model = TowerModel(self, "vision", model_type)
+        self.audio_model = TowerModel(self, "audio", model_type)
+        self.layers = [self.vision_model.layers[0], self.audio_model.layers[0], self.vision_model, self.audio_model,
+                       _Layer("concatenate_1", owner=self),
+                       _Layer("dense_1", ["dense_1/kernel", "dense_1/bias"], self, "dense_1"),
+                       _Layer("dense_2", ["dense_2/kernel", "dense_2/bias"], self, "dense_2")]
+        self.inputs = [TensorSpec("input_1", (None, 224, 224, 3)), TensorSpec("input_2", (None, 1, 48000))]
+        self.outputs = [TensorSpec("dense_2/Softmax", (None, 2))]
+
+    # ---- configuration ---------------------------------------------------------------------------------
+    def configure(self, dtype: Optional[str] = None):
+        """dtype 'f32' (parity mode) or 'bf16' (tcgen05 throughput mode).  Re-creates the device state."""
+        if dtype is not None and dtype != self.dtype:
+            if dtype not in ("f32", "bf16"):
+                raise ValueError("dtype must be 'f32' or 'bf16'")
+            self._pull()
+            self._drop_engine()
+            self.dtype = dtype
+        return self
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def _weights_dict(self) -> Dict[str, np.ndarray]:
+        if self._engine is not None:
+            return self._engine.get_weights()
+        if self._host_weights is None:
+            self._host_weights = weights_io.he_normal_weights(self.model_type, self._seed)
+        return self._host_weights
+
+    def _pull(self):
+        if self._engine is not None:
+            self._host_weights = self._engine.get_weights()
+
+    def _drop_engine(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+    
+    def _kapre(self, name):
+        return weights_io.kapre_constants(self.model_type)[name]
+
+    def _assign(self, names, arrays):
+        arrays = list(arrays)
+        if len(arrays) != len(names):
+            raise ValueError("You called `set_weights(weights)` with a weight list of length %d, but the layer was "
+                             "expecting %d weights." % (len(arrays), len(names)))
+        w = dict(self._weights_dict())
+        shapes = weights_io.weight_shapes(self.model_type)
+        for n, a in zip(names, arrays):
+            a = np.asarray(a, dtype=np.float32)
+            if n.startswith("kapre/"):
+                if tuple(a.shape) != tuple(self._kapre(n).shape):
+                    raise ValueError("Layer weight shape %s not compatible with provided weight shape %s"
+                                     % (self._kapre(n).shape, a.shape))
+                continue  # constants of the on-device front-end; regenerated, not stored
+            if tuple(a.shape) != tuple(shapes[n]):
+                raise ValueError("Layer weight shape %s not compatible with provided weight shape %s" % (shapes[n], a.shape))
+            w[n] = a
+        self._host_weights = w
+        if self._engine is not None:
+            self._engine.set_weights(w)
+
+    def weight_names(self) -> List[str]:
+        """Order of keras Model.get_weights() on the AVC model (nested towers: trainable then non-trainable)."""
+        return [n for l in self.layers for n in l._weight_names]
+
+    def get_weights(self):
+        w = self._weights_dict()
+        return [w[n] if not n.startswith("kapre/") else self._kapre(n) for n in self.weight_names()]
+
+    def set_weights(self, arrays):
+        self._assign(self.weight_names(), arrays)
+
+    def named_weights(self) -> Dict[str, np.ndarray]:
+        return dict(self._weights_dict())
+
+    def set_named_weights(self, w: Dict[str, np.ndarray]):
+        names = [n for n in self.weight_names() if not n.startswith("kapre/")]
+        self._assign(names, [w[n] for n in names])
+
+    def save_weights(self, path):
+        weights_io.save_weights(path, self)
+
+    def load_weights(self, path):
+        weights_io.load_weights(path, self)
+
+    def count_params(self):
+        return int(sum(int(np.prod(a.shape)) for a in self.get_weights()))
+
+    def get_layer(self, name):
+        for l in self.layers:
+            if l.name == name:
+                return l
+        raise ValueError("No such layer: " + name)
+
+    def to_json(self):
+        return json.dumps(dict(class_name="Model", backend="l3embedding_b200",
+                               config=dict(name=self.name, model_type=self.model_type, num_gpus=self.num_gpus,
+                                           layers=[l.name for l in self.layers])))
+
+    def get_config(self):
+        return json.loads(self.to_json())["config"]
+
+    # ---- device state ------------------------------------------------------------------------------------
+    def _get_engine(self, batch: int, training: bool):
+        from .engine import Engine  # imports torch
+        e = self._engine
+        if e is not None and (e.dtype != self.dtype or (training and not e.training) or e.max_batch < batch):
+            self._pull()
+            self._drop_engine()
+        if self._engine is None:
+            self._engine = Engine(self.model_type, max_batch=max(batch, 1), dtype=self.dtype, training=training,
+                                  weights=self._weights_dict())
+        return self._engine
+
+    # ---- keras training API ------------------------------------------------------------------------------
+    def compile(self, optimizer, loss="categorical_crossentropy", metrics=("accuracy",)):
+        if loss != "categorical_crossentropy":
+            raise ValueError("only loss='categorical_crossentropy' is implemented (train.py:270)")
+        if not hasattr(optimizer, "lr"):
+            raise TypeError("optimizer must expose .lr (use l3embedding_b200.model.Adam)")
+        self.optimizer = optimizer
+        self.loss = loss
+
+    def _dp(self):
+        from . import dp
+        return dp.current(self.num_gpus)
+
+    def train_on_batch(self, x, y):
+        """x = [video (B,224,224,3), audio (B,1,48000)]; float inputs in [-1,1] as the reference generator yields
+        (train.py:186,189), or raw uint8 / int16 (scaled on the device).  Returns [loss, acc] (global batch)."""
+        if self.optimizer is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        video, audio = x
+        par = self._dp()
+        B = len(video)
+        sl = par.slice(B)
+        eng = self._get_engine(sl.stop - sl.start, True)
+        eng.forward_backward(video[sl], audio[sl], y[sl], global_batch=B)
+        par.allreduce_grads(eng)
+        m = eng.metrics()            # loss of the weights the batch was run with, as keras reports
+        eng.adam_step(self.optimizer.lr)
+        ce_sum, correct = par.sum_scalars(m["ce_sum"], m["correct"])
+        return [ce_sum / B + m["l2"], correct / B]
+
+    def test_on_batch(self, x, y):
+        video, audio = x
+        eng = self._get_engine(len(video), False)
+        eng.predict(video, audio, y)
+        m = eng.metrics()
+        return [m["loss"], m["acc"]]
+
+    def predict(self, x, batch_size=32, verbose=0):
+        video, audio = x
+        n = len(video)
+        eng = self._get_engine(min(batch_size, max(n, 1)), False)
+        out = np.empty((n, 2), np.float32)
+        for s in range(0, n, batch_size):
+            out[s:s + batch_size] = eng.predict(video[s:s + batch_size], audio[s:s + batch_size])[0]
+        return out
+
+    def evaluate_generator(self, generator, steps, **_):
+        tot, loss, acc = 0, 0.0, 0.0
+        for _i in range(steps):
+            x, y = next(generator)[:2]
+            l, a = self.test_on_batch(x, y)
+            b = len(y)
+            tot += b; loss += l * b; acc += a * b
+        return [loss / max(tot, 1), acc / max(tot, 1)]
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None, validation_data=None,
+                      validation_steps=None, initial_epoch=0, **_):
+        """keras fit_generator as used at train.py:408-414: one train_on_batch per generator item, epoch logs
+        {loss, acc, val_loss, val_acc} as batch-size-weighted means."""
+        callbacks = list(callbacks or [])
+        hist = History()
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            elif hasattr(cb, "model"):
+                cb.model = self
+        _call(callbacks, "on_train_begin")
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            _call(callbacks, "on_epoch_begin", epoch)
+            tot, loss, acc = 0, 0.0, 0.0
+            for step in range(steps_per_epoch):
+                item = next(generator)
+                x, y = item[0], item[1]
+                b = len(y)
+                _call(callbacks, "on_batch_begin", step, {"batch": step, "size": b})
+                l, a = self.train_on_batch(x, y)
+                tot += b; loss += l * b; acc += a * b
+                _call(callbacks, "on_batch_end", step, {"batch": step, "size": b, "loss": l, "acc": a})
+            logs = {"loss": loss / max(tot, 1), "acc": acc / max(tot, 1)}
+            if validation_data is not None:
+                vl, va = self.evaluate_generator(validation_data, validation_steps)
+                logs["val_loss"], logs["val_acc"] = vl, va
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            if verbose:
+                print("Epoch %d/%d - %s" % (epoch + 1, epochs, " - ".join("%s: %.4f" % kv for kv in logs.items())))
+            _call(callbacks, "on_epoch_end", epoch, logs)
+            if self.stop_training:
+                break
+        _call(callbacks, "on_train_end")
+        return hist
+
+
+def _call(callbacks, hook, *args):
+    for cb in callbacks:
+        fn = getattr(cb, hook, None)
+        if fn is not None:
+            fn(*args) if args else fn()
+
+
+class EmbeddingModel:
+    """What load_embedding returns: `.predict(x)` maps (n,1,48000) audio to (n,6144|512) embeddings
+    (or (n,224,224,3) frames to (n,8192)) with inference-mode BN, cut at the raw conv4b output."""
+
+    def __init__(self, parent: L3Model, embedding_type: str, pooling_type: Optional[str]):
+        self.parent = parent
+        self.embedding_type = embedding_type
+        self.pooling_type = pooling_type
+        self.name = embedding_type + "_embedding_model"
+        self._engine = None
+        if embedding_type == "audio":
+            eh, ew = {"cnn_L3_melspec1": (16, 24)}.get(parent.model_type, (32, 24))
+            ph, pw = AUDIO_EMBED_POOL[parent.model_type][pooling_type]
+            self.output_dim = (eh // ph) * (ew // pw) * 512
+        else:
+            self.output_dim = 4 * 4 * 512
+
+    def _get_engine(self, batch):
+        from .engine import Engine
+        if self._engine is None or self._engine.max_batch < batch:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(self.parent.model_type, max_batch=batch, dtype=self.parent.dtype, training=False,
+                                  towers=(self.embedding_type,), weights=self.parent._weights_dict(), host_staging=False)
+        return self._engine
+
+    def predict(self, x, batch_size=32, verbose=0):
+        x = np.asarray(x) if not hasattr(x, "shape") else x
+        n = len(x)
+        eng = self._get_engine(min(batch_size, max(n, 1)))
+        out = np.empty((n, self.output_dim), np.float32)
+        for s in range(0, n, batch_size):
+            xb = x[s:s + batch_size]
+            e = eng.embed_audio(xb, self.pooling_type) if self.embedding_type == "audio" else eng.embed_vision(xb)
+            out[s:s + batch_size] = e.cpu().numpy()
+        return out
+
+
+# ---- builders (model.py:184-313) -----------------------------------------------------------------------------
+
+def gpu_wrapper(model_f):
+    """Decorator for creating multi-gpu models (model.py:184-195).  With num_gpus > 1 the model trains
+    data-parallel: one process per GPU (torchrun), each taking its contiguous slice of every batch
+    (training_utils.py:121-133) and all-reducing gradients over NCCL."""
+    def wrapped(num_gpus=0, *args, **kwargs):
+        m, inp, out = model_f(*args, **kwargs)
+        if num_gpus > 1:
+            m = multi_gpu_model(m, gpus=num_gpus)
+        return m, inp, out
+    wrapped.__name__ = model_f.__name__
+    wrapped.__doc__ = model_f.__doc__
+    return wrapped
+
+
+def multi_gpu_model(model, gpus):
+    """training_utils.py:21 -- here a flag on the model; the replicas are the torchrun ranks."""
+    if gpus <= 1:
+        raise ValueError("For multi-gpu usage to be effective, call `multi_gpu_model` with `gpus >= 2`. "
+                         "Received: `gpus=%d`" % gpus)
+    model.num_gpus = int(gpus)
+    return model
+
+
+def _construct(model_type, name):
+    m = L3Model(model_type, name)
+    return m, list(m.inputs), m.outputs[0]
+
+
+@gpu_wrapper
+def construct_cnn_L3_orig():
+    """Original L3 model (model.py:198-218)."""
+    return _construct("cnn_L3_orig", "cnn_L3_orig")
+
+
+@gpu_wrapper
+def construct_cnn_L3_kapredbinputbn():
+    """L3 with kapre dB spectrogram and input batch normalisation (model.py:220-240)."""
+    return _construct("cnn_L3_kapredbinputbn", "cnn_L3_kapredbinputbn")
+
+
+@gpu_wrapper
+def construct_cnn_L3_melspec1():
+    """L3 with a 128-band mel front-end (model.py:242-262)."""
+    return _construct("cnn_L3_melspec1", "cnn_L3_melspec1")
+
+
+@gpu_wrapper
+def construct_cnn_L3_melspec2():
+    """L3 with a 256-band mel front-end (model.py:264-284)."""
+    return _construct("cnn_L3_melspec2", "cnn_L3_melspec2")
+
+
+def construct_tiny_L3(*_a, **_k):
+    raise NotImplementedError("tiny_L3 passes n_win to kapre.Spectrogram, which stock kapre 0.1.3.1/0.1.4 rejects "
+                              "(audio_model.py:516); it is not part of the B200 path")
+
+
+MODELS = {
+    "cnn_L3_orig": construct_cnn_L3_orig,
+    "tiny_L3": construct_tiny_L3,
+    "cnn_L3_kapredbinputbn": construct_cnn_L3_kapredbinputbn,
+    "cnn_L3_melspec1": construct_cnn_L3_melspec1,
+    "cnn_L3_melspec2": construct_cnn_L3_melspec2,
+}
+
+
+def convert_num_gpus(model, inputs, outputs, model_type, src_num_gpus, tgt_num_gpus):
+    """model.py:38-82.  Checkpoints written by this package are always in the single-model layout."""
+    if src_num_gpus <= 1 and tgt_num_gpus <= 1:
+        return model, inputs, outputs
+    m_new, inputs_new, output_new = MODELS[model_type]()
+    m_new.set_weights(model.get_weights())
+    m_new.dtype = model.dtype
+    if tgt_num_gpus > 1:
+        m_new = multi_gpu_model(m_new, gpus=tgt_num_gpus)
+    return m_new, inputs_new, output_new
+
+
+def load_model(weights_path, model_type, src_num_gpus=0, tgt_num_gpus=None, return_io=False):
+    """Loads an audio-visual correspondence model (model.py:85-128)."""
+    if model_type not in MODELS:
+        raise ValueError('Invalid model type: "{}"'.format(model_type))
+    m, inputs, output = MODELS[model_type]()
+    if src_num_gpus > 1:
+        m = multi_gpu_model(m, gpus=src_num_gpus)
+    m.load_weights(weights_path)
+    if tgt_num_gpus is not None and src_num_gpus != tgt_num_gpus:
+        m, inputs, output = convert_num_gpus(m, inputs, output, model_type, src_num_gpus, tgt_num_gpus)
+    if return_io:
+        return m, inputs, output
+    return m
+
+
+def convert_audio_model_to_embedding(audio_model, x_a, model_type, pooling_type="original"):
+    """audio_model.py:445-487: MaxPooling2D(pool,'same') over the raw 'audio_embedding_layer' output + Flatten."""
+    pool_size = AUDIO_EMBED_POOL[model_type][pooling_type]   # KeyError on unknown keys, as in the reference
+    del pool_size
+    audio_model.get_layer("audio_embedding_layer")
+    m = EmbeddingModel(audio_model._owner, "audio", pooling_type)
+    return m, x_a, TensorSpec("audio_embedding", (None, m.output_dim))
+
+
+def construct_cnn_l3_orig_vision_embedding_model(vision_model, x_i):
+    """vision_model.py:198-218: MaxPooling2D((7,7),'same') over the raw 'vision_embedding_layer' output + Flatten."""
+    vision_model.get_layer("vision_embedding_layer")
+    m = EmbeddingModel(vision_model._owner, "vision", None)
+    return m, x_i, TensorSpec("vision_embedding", (None, m.output_dim))
+
+
+def load_embedding(weights_path, model_type, embedding_type, pooling_type, src_num_gpus=0, tgt_num_gpus=None,
+                   return_io=False):
+    """Loads an embedding model (model.py:131-181)."""
+    m, inputs, output = load_model(weights_path, model_type, src_num_gpus=src_num_gpus, tgt_num_gpus=tgt_num_gpus,
+                                   return_io=True)
+    x_i, x_a = inputs
+    if embedding_type == "vision":
+        m_embed, x_embed, y_embed = construct_cnn_l3_orig_vision_embedding_model(m.get_layer("vision_model"), x_i)
+    elif embedding_type == "audio":
+        m_embed, x_embed, y_embed = convert_audio_model_to_embedding(m.get_layer("audio_model"), x_a, model_type,
+                                                                     pooling_type)
+    else:
+        raise ValueError('Invalid embedding type: "{}"'.format(embedding_type))
+    if return_io:
+        return m_embed, x_embed, y_embed
+    return m_embed

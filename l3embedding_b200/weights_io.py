@@ -1,0 +1,165 @@
+"""Weight inventory and checkpoint I/O in the reference's saved-weight layout.
+
+The reference saves with keras `save_weights` (HDF5; l3embedding/train.py:316-355) and loads with `load_weights`
+(l3embedding/model.py:119).  h5py does not exist in the build environment, so the canonical interchange format
+here is an ordered .npz whose entries are the arrays of keras `Model.get_weights()` in that order, stored under
+the keras-style names below; when h5py is importable the same arrays are read from / written to the keras 2.0.9
+HDF5 layout (one group per top-level layer, `weight_names` attributes).  The HDF5 branch could not be exercised
+here (no h5py) and is marked unverified in DESIGN.md.  Files are recognised by magic bytes, not by extension, so
+`model_latest.h5` written by this package loads back regardless of which branch wrote it.
+"""
+from __future__ import annotations
+
+import math
+import zipfile
+from functools import lru_cache
+from typing import Dict
+
+import numpy as np
+
+from . import _lib
+
+SR = 48000
+
+
+@lru_cache(maxsize=None)
+def weight_shapes(model_type: str) -> Dict[str, tuple]:
+    return {name: shape for name, _a, _o, shape in _lib.tensor_table(model_type)}
+
+
+def he_normal_weights(model_type: str, seed: int = 20180123) -> Dict[str, np.ndarray]:
+    """Fresh weights as the reference builders create them: he_normal kernels (truncated normal, std sqrt(2/fan_in);
+    l3embedding/audio_model.py:376-432, vision_model.py:130-186, model.py:26-31), zero biases, BN gamma 1 / beta 0 /
+    moving mean 0 / moving variance 1."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in weight_shapes(model_type).items():
+        leaf = name.rsplit("/", 1)[1]
+        if leaf == "kernel":
+            std = math.sqrt(2.0 / float(np.prod(shape[:-1])))
+            x = rng.standard_normal(shape)
+            bad = np.abs(x) > 2.0
+            while bad.any():
+                x[bad] = rng.standard_normal(int(bad.sum()))
+                bad = np.abs(x) > 2.0
+            out[name] = (x * std).astype(np.float32)
+        elif leaf in ("gamma", "moving_variance"):
+            out[name] = np.ones(shape, np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
+def mel_filterbank(sr: int, n_fft: int, n_mels: int) -> np.ndarray:
+    """librosa 0.5.1 filters.mel(sr, n_fft, n_mels, fmin=0, fmax=sr/2, htk=True, norm=1): (n_mels, 1+n_fft/2)."""
+    fftfreqs = np.linspace(0.0, sr / 2.0, 1 + n_fft // 2)
+    mels = np.linspace(0.0, 2595.0 * np.log10(1.0 + (sr / 2.0) / 700.0), n_mels + 2)
+    mel_f = 700.0 * (10.0 ** (mels / 2595.0) - 1.0)
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        w[i] = np.maximum(0.0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    return w * (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+
+
+@lru_cache(maxsize=4)
+def kapre_constants(model_type: str) -> Dict[str, np.ndarray]:
+    """The non-trainable arrays the kapre (Mel)Spectrogram layer holds in a keras checkpoint (real/imag DFT
+    kernels (n_dft,1,1,n_freq) and freq2mel (n_freq,n_mels)).  The device front-end computes the same transform
+    with an FFT and does not read them; they exist so get_weights()/save_weights keep the reference's layout."""
+    from .model import AUDIO_FRONTEND
+    fe = AUDIO_FRONTEND[model_type]
+    n = fe["n_dft"]
+    nf = n // 2 + 1
+    t = np.arange(n, dtype=np.float64)[:, None]
+    k = np.arange(nf, dtype=np.float64)[None, :]
+    win = (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n))[:, None]
+    ang = 2.0 * np.pi * k * t / n
+    out = {"kapre/real_kernels": (np.cos(ang) * win).astype(np.float32).reshape(n, 1, 1, nf),
+           "kapre/imag_kernels": (-np.sin(ang) * win).astype(np.float32).reshape(n, 1, 1, nf)}
+    if fe["n_mels"]:
+        out["kapre/freq2mel"] = mel_filterbank(SR, n, fe["n_mels"]).T.astype(np.float32)
+    return out
+
+
+# ---- file formats ----------------------------------------------------------------------------------------------
+
+def _is_hdf5(path) -> bool:
+    with open(path, "rb") as f:
+        return f.read(8) == b"\x89HDF\r\n\x1a\n"
+
+
+def save_weights(path, model):
+    names = model.weight_names()
+    arrays = model.get_weights()
+    try:
+        import h5py  # noqa: F401
+        if str(path).endswith((".h5", ".hdf5")):
+            return _save_h5(path, model, names, arrays)
+    except ImportError:
+        pass
+    payload = {"__order__": np.array(names), "__model_type__": np.array(model.model_type)}
+    for n, a in zip(names, arrays):
+        payload[n] = a
+    with open(path, "wb") as f:   # a file object keeps numpy from appending '.npz'
+        np.savez(f, **payload)
+
+
+def load_weights(path, model):
+    if _is_hdf5(path):
+        try:
+            import h5py  # noqa: F401
+        except ImportError as e:
+            raise ImportError("%s is a keras HDF5 checkpoint; reading it needs h5py (convert it to .npz with "
+                              "tools/h5_to_npz.py where h5py exists)" % path) from e
+        return _load_h5(path, model)
+    if not zipfile.is_zipfile(path):
+        raise ValueError("%s is neither a keras HDF5 file nor an l3embedding_b200 .npz checkpoint" % path)
+    with np.load(path, allow_pickle=False) as z:
+        names = [str(n) for n in z["__order__"]]
+        if names != model.weight_names():
+            raise ValueError("checkpoint %s holds the weights of a different model layout" % path)
+        model.set_weights([z[n] for n in names])
+
+
+def _keras_groups(model):
+    """[(top-level layer name, [(keras weight name, canonical name)])] as keras 2.0.9 save_weights groups them."""
+    groups = []
+    for layer in model.layers:
+        if not layer._weight_names:
+            continue
+        entries = []
+        for cn in layer._weight_names:
+            parts = cn.split("/")
+            entries.append(("%s/%s:0" % ("_".join(parts[:-1]), parts[-1]), cn))
+        groups.append((layer.name, entries))
+    return groups
+
+
+def _save_h5(path, model, names, arrays):   # unverified: no h5py in the build environment
+    import h5py
+    by_name = dict(zip(names, arrays))
+    with h5py.File(path, "w") as f:
+        groups = _keras_groups(model)
+        f.attrs["layer_names"] = [g.encode("utf8") for g, _ in groups]
+        f.attrs["backend"] = b"tensorflow"
+        f.attrs["keras_version"] = b"2.0.9"
+        for gname, entries in groups:
+            g = f.create_group(gname)
+            g.attrs["weight_names"] = [kn.encode("utf8") for kn, _ in entries]
+            for kn, cn in entries:
+                g.create_dataset(kn, data=by_name[cn])
+
+
+def _load_h5(path, model):   # unverified: no h5py in the build environment
+    import h5py
+    with h5py.File(path, "r") as f:
+        arrays = []
+        layer_names = [n.decode("utf8") if isinstance(n, bytes) else n for n in f.attrs["layer_names"]]
+        for ln in layer_names:
+            g = f[ln]
+            for wn in g.attrs["weight_names"]:
+                wn = wn.decode("utf8") if isinstance(wn, bytes) else wn
+                arrays.append(np.asarray(g[wn]))
+        model.set_weights(arrays)

@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (stated per SURVEY 7.2 / north_star):
+  front-end dB map            <= 1e-3 dB max-abs vs the fp64 oracle (the reference's own fp32 DFT-as-matmul is 5e-4 off)
+  embeddings / logits (f32)   <= 1e-3 max-abs vs the fp64 oracle       (north_star: "within 1e-3 max-abs")
+  gradients (f32)             <= 2e-3 relative L2 per tensor vs fp64 autograd
+  bf16 throughput mode        reported, bounded loosely (bf16 cannot meet 1e-3)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import l3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODEL_TYPES = ["cnn_L3_orig", "cnn_L3_kapredbinputbn", "cnn_L3_melspec1", "cnn_L3_melspec2"]
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz")
+F64 = O.OracleConfig(dtype=torch.float64)
+
+
+def _engine(*a, **k):
+    from l3embedding_b200.engine import Engine
+    return Engine(*a, **k)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------- front-end
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+def test_frontend_matches_oracle(model_type):
+    _, audio, _ = O.synthetic_batch(3, seed=101)
+    audio[2] = 0                                 # a silent clip: every cell at the amin floor
+    audio[1, 0, :24000] = 0                      # half-silent
+    eng = _engine(model_type, 3, "f32", training=False, towers=("audio",))
+    got = eng.frontend(audio).cpu().numpy()
+    ref = O.frontend(torch.from_numpy(O.pcm2float(audio, "float64")), model_type, F64)[..., 0].numpy()
+    assert got.shape == ref.shape
+    tol = 1e-3   # dB for the decibel models; log(x)/5 units for cnn_L3_orig (audio_model.py:43)
+    assert np.abs(got - ref).max() <= tol, np.abs(got - ref).max()
+    # float32 input path == int16 input path (pcm2float is exact in fp32)
+    got_f = eng.frontend(O.pcm2float(audio, "float32")).cpu().numpy()
+    assert np.array_equal(got, got_f)
+
+
+def test_frontend_matches_golden_fixture():
+    with np.load(GOLDEN) as z:
+        meta = json.loads(str(z["meta"]))
+        _, audio, _ = O.synthetic_batch(meta["batch"], seed=meta["data_seed"])
+        for mt in meta["model_types"]:
+            eng = _engine(mt, meta["batch"], "f32", training=False, towers=("audio",))
+            got = eng.frontend(audio).cpu().numpy()[:, ::meta["stride_f"], ::meta["stride_t"]]
+            assert np.abs(got - z[mt + "/frontend"]).max() <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- conv ops
+def _pad(x):  # (B,H,W,C) -> zero-haloed (B,H+2,W+2,C)
+    return torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 7, 3, 64), (1, 16, 13, 64, 64), (2, 8, 24, 128, 256), (3, 5, 5, 1, 64)])
+def test_conv_simt_fwd_dgrad_wgrad_f32(shape):
+    import ctypes as C
+    from l3embedding_b200 import _lib
+    lib = _lib.load()
+    B, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, Ci, generator=g)
+    w = torch.randn(3, 3, Ci, Co, generator=g) * 0.1
+    b = torch.randn(Co, generator=g)
+    dz = torch.randn(B, H, W, Co, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), b, padding=1).permute(0, 2, 3, 1)
+    y.backward(dz)
+    dev = "cuda"
+    p = lambda t: C.c_void_p(t.data_ptr())
+    xp, dzp = _pad(x).contiguous().to(dev), _pad(dz).contiguous().to(dev)
+    wd, bd = w.contiguous().to(dev), b.to(dev)
+    out = torch.empty(B, H, W, Co, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.l3_conv3x3_fwd(p(xp), p(wd), p(bd), p(out), B, H, W, Ci, Co, 0, 0, None, st), "fwd")
+    assert torch.allclose(out.cpu(), y.detach(), atol=2e-4, rtol=1e-4)
+    da = torch.empty(B, H, W, Ci, device=dev)
+    scratch = torch.empty(9 * Ci * Co, device=dev)
+    _lib.check(lib.l3_conv3x3_dgrad(p(dzp), p(wd), p(da), B, H, W, Ci, Co, 0, 0, p(scratch), st), "dgrad")
+    assert torch.allclose(da.cpu(), xr.grad, atol=2e-4, rtol=1e-4)
+    dw = torch.empty(3, 3, Ci, Co, device=dev)
+    db = torch.empty(Co, device=dev)
+    _lib.check(lib.l3_conv3x3_wgrad(p(xp), p(dzp), p(dw), p(db), B, H, W, Ci, Co, 0, 0, st), "wgrad")
+    assert torch.allclose(dw.cpu(), wr.grad, atol=1e-3, rtol=1e-4)
+    assert torch.allclose(db.cpu(), dz.sum(dim=(0, 1, 2)), atol=1e-3, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- whole model
+def _oracle_inputs(video, audio):
+    return (torch.from_numpy(O.scale_video(video)).double(), torch.from_numpy(O.pcm2float(audio, "float64")))
+
+
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+def test_inference_logits_and_embeddings_f32(model_type):
+    """keras predict path (BN moving statistics): AVC logits/probabilities and both audio embeddings + the vision
+    embedding within 1e-3 max-abs of the fp64 oracle."""
+    B = 2
+    w_np = O.init_weights(model_type, seed=20180123, randomize_bn=True)
+    video, audio, _ = O.synthetic_batch(B, seed=202)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64)
+    ref_logits = O.avc_forward(vf, af, w, model_type, False, F64).numpy()
+    eng = _engine(model_type, B, "f32", training=False, weights=w_np)
+    probs, logits = eng.predict(video, audio)
+    assert np.abs(logits - ref_logits).max() <= 1e-3, np.abs(logits - ref_logits).max()
+    ref_p = torch.softmax(torch.from_numpy(ref_logits), dim=1).numpy()
+    assert np.abs(probs - ref_p).max() <= 1e-3
+    for pooling in ("original", "short"):
+        ref = O.audio_embedding(af, w, model_type, pooling, F64).numpy()
+        got = eng.embed_audio(audio, pooling).cpu().numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-3, (pooling, np.abs(got - ref).max())
+    ref_v = O.vision_embedding(vf, w, model_type, F64).numpy()
+    got_v = eng.embed_vision(video).cpu().numpy()
+    assert got_v.shape == (B, 8192) and np.abs(got_v - ref_v).max() <= 1e-3
+    # float inputs as the reference generator yields them (train.py:186,189) give the same result as raw u8/i16
+    p2, _ = eng.predict(O.scale_video(video), O.pcm2float(audio, "float32"))
+    assert np.abs(p2 - probs).max() <= 1e-6
+
+
+def test_embedding_matches_golden_fixture():
+    with np.load(GOLDEN) as z:
+        meta = json.loads(str(z["meta"]))
+        _, audio, _ = O.synthetic_batch(meta["batch"], seed=meta["data_seed"])
+        for mt in meta["embedding_types"]:
+            w_np = O.init_weights(mt, seed=meta["weight_seed"], randomize_bn=True)
+            eng = _engine(mt, meta["batch"], "f32", training=False, towers=("audio",), weights=w_np)
+            assert np.abs(eng.embed_audio(audio, "short").cpu().numpy() - z[mt + "/embedding_short"]).max() <= 1e-3
+            assert np.abs(eng.embed_audio(audio, "original").cpu().numpy() - z[mt + "/embedding_original"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_orig"])
+def test_training_step_gradients_f32(model_type):
+    """train_on_batch: loss, accuracy, every gradient tensor, BN moving statistics and the Adam update against
+    fp64 autograd of the oracle."""
+    B = 2
+    w_np = O.init_weights(model_type, seed=7, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(B, seed=303)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
+    grads, out, stats = O.compute_grads(vf, af, torch.from_numpy(label), w, model_type, F64)
+    eng = _engine(model_type, B, "f32", training=True, weights=w_np)
+    eng.forward_backward(video, audio, label)
+    m = eng.metrics()
+    assert abs(m["loss"] - float(out["loss"])) <= 1e-4 * max(1.0, abs(float(out["loss"])))
+    assert abs(m["acc"] - float(out["acc"])) < 1e-6
+    got = eng.get_grads()
+    worst = 0.0
+    for name, g_ref in grads.items():
+        g_ref = g_ref.numpy()
+        if name.endswith("/kernel"):
+            g_ref = g_ref - 2e-5 * w_np[name]          # the device applies the l2 term inside Adam
+        err = rel_l2(got[name], g_ref)
+        worst = max(worst, err)
+        assert err <= 2e-3, (name, err)
+    # BN moving statistics (momentum 0.99, Bessel-corrected variance)
+    O.update_moving_stats(w, stats, F64)
+    w_after = eng.get_weights()
+    for name in w_np:
+        if name.endswith(("moving_mean", "moving_variance")):
+            assert np.abs(w_after[name] - w[name].detach().numpy()).max() <= 1e-5, name
+    # keras Adam step
+    st = O.AdamState()
+    O.adam_update(w, grads, st, 1e-3, F64)
+    eng.adam_step(1e-3)
+    w_after = eng.get_weights()
+    for name in grads:
+        assert np.abs(w_after[name] - w[name].detach().numpy()).max() <= 2e-5, name
+
+
+def test_train_steps_from_host_decrease_loss():
+    """BASELINE config 1 on the device path: cnn_L3_orig, batch 4, 8 steps from host buffers."""
+    mt = "cnn_L3_orig"
+    video, audio, label = O.synthetic_batch(4, seed=11)
+    eng = _engine(mt, 4, "f32", training=True)
+    losses = [eng.train_step_host(video, audio, label, 1e-4)["loss"] for _ in range(8)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def test_keras_style_api_end_to_end(tmp_path):
+    from l3embedding_b200 import model as M
+    m, _, _ = M.MODELS["cnn_L3_melspec2"]()
+    m.configure(dtype="f32")
+    m.compile(M.Adam(lr=1e-4), loss="categorical_crossentropy", metrics=["accuracy"])
+    video, audio, label = O.synthetic_batch(2, seed=17)
+
+    def gen():
+        while True:
+            yield [O.scale_video(video), O.pcm2float(audio, "float32")], label
+    h = m.fit_generator(gen(), steps_per_epoch=2, epochs=2, validation_data=gen(), validation_steps=1, verbose=0)
+    assert set(h.history) == {"loss", "acc", "val_loss", "val_acc"} and len(h.history["loss"]) == 2
+    p = str(tmp_path / "model_latest.h5")
+    m.save_weights(p)
+    e = M.load_embedding(p, "cnn_L3_melspec2", "audio", "original")
+    e.parent.configure(dtype="f32")
+    x = O.pcm2float(audio, "float32")
+    emb = e.predict(x)
+    assert emb.shape == (2, 6144)
+    w = O.to_torch(m.named_weights(), dtype=torch.float64)
+    ref = O.audio_embedding(torch.from_numpy(x).double(), w, "cnn_L3_melspec2", "original", F64).numpy()
+    assert np.abs(emb - ref).max() <= 1e-3
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2"])
+def test_bf16_throughput_mode_reports_error(model_type):
+    """bf16 storage/operands cannot meet 1e-3; bound it loosely and print the measured error."""
+    B = 2
+    w_np = O.init_weights(model_type, seed=20180123, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(B, seed=202)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64)
+    ref = O.audio_embedding(af, w, model_type, "original", F64).numpy()
+    eng = _engine(model_type, B, "bf16", training=True, weights=w_np)
+    got = eng.embed_audio(audio, "original").cpu().numpy()
+    err = np.abs(got - ref).max()
+    print("bf16 embedding max|d| = %.4g (|e|max %.3g), tensor cores: %s" % (err, np.abs(ref).max(), eng.uses_tensor_cores))
+    assert err <= 0.25
+    eng.forward_backward(video, audio, label)
+    assert np.isfinite(eng.metrics()["loss"])
+    g = eng.get_grads()
+    assert all(np.isfinite(v).all() for v in g.values())

@@ -1,0 +1,192 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/l3b200.h declares, the
+weight inventory matches the oracle's, the keras-compatible model objects behave like the reference's at the
+boundary (names, argument meaning, error behaviour), and the N>1 data-parallel glue works over gloo."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+from l3embedding_b200 import _lib, dp, weights_io
+from l3embedding_b200 import model as M
+from oracle import l3_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODEL_TYPES = ["cnn_L3_orig", "cnn_L3_kapredbinputbn", "cnn_L3_melspec1", "cnn_L3_melspec2"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "l3b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(l3_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libl3b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.l3_version() == 1
+
+
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+def test_tensor_table_matches_oracle_layout(model_type):
+    table = _lib.tensor_table(model_type)
+    lay = O.model_layout(model_type)
+    assert [(n, s) for n, _a, _o, s in table] == [(n, tuple(s)) for n, s, _t in lay]
+    assert [a for _n, a, _o, _s in table] == [0 if t else 1 for _n, _s, t in lay]
+    lib = _lib.load()
+    mid = _lib.model_id(model_type)
+    c = O.count_params(model_type)
+    assert lib.l3_param_count(mid) == c["trainable"] and lib.l3_state_count(mid) == c["bn_moving"]
+    # arenas are dense and the l2-regularised kernels come first
+    for arena in (0, 1):
+        spans = sorted((o, o + int(np.prod(s))) for _n, a, o, s in table if a == arena)
+        assert spans[0][0] == 0 and all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    kernels = [(o, int(np.prod(s))) for n, a, o, s in table if n.endswith("/kernel")]
+    assert max(o + k for o, k in kernels) == lib.l3_l2_count(mid) == sum(k for _o, k in kernels)
+
+
+def test_geometry_queries():
+    lib = _lib.load()
+    import ctypes as C
+    a, b = C.c_int(), C.c_int()
+    for mt, fe, emb in (("cnn_L3_melspec2", (256, 199), (32, 24)), ("cnn_L3_melspec1", (128, 199), (16, 24)),
+                        ("cnn_L3_orig", (257, 197), (32, 24)), ("cnn_L3_kapredbinputbn", (257, 197), (32, 24))):
+        assert lib.l3_frontend_shape(_lib.model_id(mt), C.byref(a), C.byref(b)) == 0 and (a.value, b.value) == fe
+        assert lib.l3_embedding_map_shape(_lib.model_id(mt), C.byref(a), C.byref(b)) == 0 and (a.value, b.value) == emb
+    assert lib.l3_frontend_shape(9, C.byref(a), C.byref(b)) < 0 and b"invalid model type" in lib.l3_last_error()
+    assert lib.l3_workspace_bytes(3, 0, 0, 7) < 0
+    assert lib.l3_workspace_bytes(3, 64, 1, 7) > lib.l3_workspace_bytes(3, 64, 1, 6) > 0   # training needs more
+
+
+def test_models_registry_and_errors():
+    # model.py:307-313 keys; model.py:113-114 / :175-176 error behaviour
+    assert set(M.MODELS) == {"cnn_L3_orig", "tiny_L3", "cnn_L3_kapredbinputbn", "cnn_L3_melspec1", "cnn_L3_melspec2"}
+    with pytest.raises(ValueError, match='Invalid model type: "nope"'):
+        M.load_model("/nonexistent", "nope")
+    m, inputs, y = M.MODELS["cnn_L3_melspec2"]()
+    assert m.name == "cnn_L3_melspec2" and len(inputs) == 2 and inputs[0].shape == (None, 224, 224, 3)
+    assert inputs[1].shape == (None, 1, 48000) and y.shape == (None, 2)
+    assert [l.name for l in m.layers[2:]] == ["vision_model", "audio_model", "concatenate_1", "dense_1", "dense_2"]
+    assert m.get_layer("audio_model").get_layer("audio_embedding_layer").name == "audio_embedding_layer"
+    assert m.get_layer("vision_model").get_layer("vision_embedding_layer") is not None
+    with pytest.raises(ValueError):
+        m.get_layer("missing")
+    m4, _, _ = M.MODELS["cnn_L3_melspec2"](num_gpus=4)
+    assert m4.num_gpus == 4
+    with pytest.raises(RuntimeError, match="compile"):
+        m.train_on_batch([np.zeros((1, 224, 224, 3), np.float32), np.zeros((1, 1, 48000), np.float32)], np.zeros((1, 2)))
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_orig"])
+def test_keras_weight_order_and_counts(model_type):
+    m, _, _ = M.MODELS[model_type]()
+    names = m.weight_names()
+    c = O.count_params(model_type)
+    assert m.count_params() == c["total"]
+    # nested towers: all trainable arrays before any non-trainable one (keras Container.weights)
+    vis = m.get_layer("vision_model")._weight_names
+    first_nt = min(i for i, n in enumerate(vis) if n.endswith("moving_mean"))
+    assert all(n.endswith(("moving_mean", "moving_variance")) for n in vis[first_nt:])
+    aud = m.get_layer("audio_model")._weight_names
+    k = aud.index("kapre/real_kernels")
+    assert aud[k + 1] == "kapre/imag_kernels" and not any(n.endswith(("kernel", "bias", "gamma", "beta")) for n in aud[k:])
+    # layer-by-layer order on the tower itself starts with the kapre arrays
+    # (notebooks/extract_spectrogram_models_from_avc_models.ipynb:446: get_weights()[3:] strips them for mel models)
+    lw = m.get_layer("audio_model").layerwise_weight_names()
+    assert lw[0] == "kapre/real_kernels" and lw[1] == "kapre/imag_kernels"
+    assert names[-4:] == ["dense_1/kernel", "dense_1/bias", "dense_2/kernel", "dense_2/bias"]
+    kc = weights_io.kapre_constants(model_type)
+    n_dft = 2048 if "melspec" in model_type else 512
+    assert kc["kapre/real_kernels"].shape == (n_dft, 1, 1, n_dft // 2 + 1)
+
+
+def test_save_load_round_trip_and_convert(tmp_path):
+    m, _, _ = M.MODELS["cnn_L3_melspec1"]()
+    w = m.get_weights()
+    w2 = [a + 1.0 if a.ndim == 1 and a.shape[0] == 64 else a for a in w]
+    m.set_weights(w2)
+    p = str(tmp_path / "model_latest.h5")     # the reference's file name (train.py:316); npz container without h5py
+    m.save_weights(p)
+    m2 = M.load_model(p, "cnn_L3_melspec1")
+    assert all(np.array_equal(a, b) for a, b in zip(m.get_weights(), m2.get_weights()))
+    m3 = M.load_model(p, "cnn_L3_melspec1", src_num_gpus=4, tgt_num_gpus=1)
+    assert m3.num_gpus == 0 and all(np.array_equal(a, b) for a, b in zip(m.get_weights(), m3.get_weights()))
+    with pytest.raises(ValueError, match="different model layout"):
+        M.load_model(p, "cnn_L3_orig")
+    with pytest.raises(ValueError, match="expecting"):
+        m.set_weights(w[:-1])
+    bad = list(w)
+    bad[-1] = np.zeros(3, np.float32)
+    with pytest.raises(ValueError, match="not compatible"):
+        m.set_weights(bad)
+
+
+def test_load_embedding_boundary(tmp_path):
+    m, _, _ = M.MODELS["cnn_L3_melspec2"]()
+    p = str(tmp_path / "w.npz")
+    m.save_weights(p)
+    e = M.load_embedding(p, "cnn_L3_melspec2", "audio", "original")
+    assert e.output_dim == 6144
+    e2, x, y = M.load_embedding(p, "cnn_L3_melspec2", "audio", "short", return_io=True)
+    assert e2.output_dim == 512 and x.shape == (None, 1, 48000) and y.shape == (None, 512)
+    assert M.load_embedding(p, "cnn_L3_melspec2", "vision", "original").output_dim == 8192
+    with pytest.raises(ValueError, match='Invalid embedding type: "smell"'):
+        M.load_embedding(p, "cnn_L3_melspec2", "smell", "original")
+    with pytest.raises(KeyError):
+        M.load_embedding(p, "cnn_L3_melspec2", "audio", "tiny")
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m, _, _ = M.MODELS["cnn_L3_orig"]()
+    with pytest.raises(_lib.L3Error, match="no CPU fallback"):
+        m.predict([np.zeros((1, 224, 224, 3), np.float32), np.zeros((1, 1, 48000), np.float32)])
+
+
+def test_replica_slice_follows_get_slice():
+    # training_utils.py:121-133
+    assert [dp.replica_slice(64, r, 4) for r in range(4)] == [slice(0, 16), slice(16, 32), slice(32, 48), slice(48, 64)]
+    assert [dp.replica_slice(10, r, 4) for r in range(4)] == [slice(0, 2), slice(2, 4), slice(4, 6), slice(6, 10)]
+    assert dp.current(0).slice(7) == slice(0, 7)
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        dp.current(2)
+
+
+def _dp_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        par = dp.current(world)
+
+        class FakeEngine:
+            grads = torch.full((1000,), float(rank + 1))
+        eng = FakeEngine()
+        par.allreduce_grads(eng)
+        s = par.sum_scalars(float(rank), 1.0)
+        q.put((rank, par.slice(10), float(eng.grads[0]), float(eng.grads[-1]), s))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_glue_over_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == slice(0, 5) and res[1][1] == slice(5, 10)
+    assert all(r[2] == 3.0 and r[3] == 3.0 for r in res)          # 1 + 2 summed over ranks
+    assert all(r[4] == (1.0, 2.0) for r in res)
