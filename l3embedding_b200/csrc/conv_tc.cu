@@ -1,8 +1,580 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 (5th-gen tensor core) bf16 implicit-GEMM 3x3 convolutions for sm_100a: forward / data-gradient
+// (k_conv3x3_tc) and weight-gradient (k_wgrad3x3_tc).  Replaces what cuDNN ran for the keras Conv2D layers of
+// l3embedding/audio_model.py:376-432 and l3embedding/vision_model.py:130-186 (forward and backward).
+//
+// Layout trick: every convolution input lives in a zero-haloed buffer (B,H+2,W+2,C).  Flattening (b,y,x) to one
+// row index m makes tap (ky,kx) of a 'same' 3x3 convolution a CONSTANT row shift (ky-1)*(W+2)+(kx-1), so the
+// im2col operand of a 128-pixel tile is just a 2-D TMA box [128 rows][64 channels] at row m0+shift -- no gather,
+// no boundary predicates (out-of-range rows are zero-filled by TMA, halo rows hold zeros).  Outputs are computed
+// for halo rows too (1.6 % .. 15 % extra MMA work) and dropped in the epilogue.
+//
+// Forward GEMM  D[m][co] = sum_{tap,ci} A[m+shift(tap)][ci] * Wp[tap][ci][co]      M = pixels, N = Cout, K = 9*Cin
+//   A, B both K-major in shared memory (128-byte swizzle, written by TMA), fp32 accumulators in TMEM (double
+//   buffered so the epilogue of tile i overlaps the MMAs of tile i+1), persistent CTAs, warp-specialised:
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator), warps 2..5 = epilogue (TMEM -> regs -> bf16 -> HBM).
+// Weight gradient  dW[tap][ci][co] = sum_m A[m+shift(tap)][ci] * dZ[m][co]          M = Cin, N = Cout, K = pixels
+//   both operands are "MN-major" (channels contiguous), which UMMA reads directly from the same TMA boxes;
+//   split-K over pixel slices with fp32 atomics into dW.
+#include <cuda.h>
 #include "kernels.h"
+
 namespace l3 {
-int conv_tc_supported() { return 0; }
-int launch_pack_weights_tc(const float*, bf16*, int, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return -1; }
-int launch_conv3x3_tc(const bf16*, const bf16*, const float*, bf16*, int, int, int, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return -1; }
-int launch_wgrad3x3_tc(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return -1; }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_addr(bar);
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_addr(dst)), "l"(tm), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.  Addresses / offsets in 16-byte units.
+//   K-major  operand: rows of 128 B (64 bf16 along K); 8-row groups SBO = 1024 B apart; LBO unused (1)
+//   MN-major operand: rows of 128 B (64 bf16 along M/N) per k; 8-k groups SBO = 1024 B apart; next 64 M/N
+//                     elements LBO bytes away
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  d |= 2ull << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host: TMA descriptors through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+int conv_tc_supported() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    cached = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+        get_encode() != nullptr)
+      cached = 1;
+    cudaGetLastError();
+  }
+  return cached;
+}
+// 2-D bf16 tensor [rows][inner] (inner contiguous), box [box_rows][64], 128-byte swizzle, zero fill out of range
+static int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  L3_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  L3_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld box=%d", (int)r, inner, rows, box_rows);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight pack: fp32 HWIO -> bf16 rows [(tap*KC + kc)*Cout + co][64 ci]  (K-major B operand, one 128-byte row each)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int Cout, int flip) {
+  // output conv has Ci' inputs and Co' outputs: forward (Ci',Co') = (Cin,Cout); dgrad (Ci',Co') = (Cout,Cin)
+  const int Ci = flip ? Cout : Cin, Co = flip ? Cin : Cout;
+  const int KC = Ci / 64;
+  const long long n = 9LL * Ci * Co;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cil = (int)(i & 63);
+    long long r = i >> 6;
+    int co = (int)(r % Co);
+    long long r2 = r / Co;
+    int kc = (int)(r2 % KC);
+    int tap = (int)(r2 / KC);
+    int ci = kc * 64 + cil;
+    float v = flip ? w[((long long)(8 - tap) * Cin + co) * Cout + ci]   // w[8-tap][ci_orig = co'][co_orig = ci']
+                   : w[((long long)tap * Cin + ci) * Cout + co];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int flip_transpose, cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "pack_weights: channels must be multiples of 64");
+  long long n = 9LL * Cin * Cout;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_pack_weights<<<blocks, 256, 0, s>>>(w, packed, Cin, Cout, flip_transpose);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward / dgrad
+// ---------------------------------------------------------------------------------------------------------
+static const int kConvThreads = 192;
+static const int kBM = 128;
+static const int kAStageBytes = kBM * 128;  // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvCfg {
+  static const int kBStageBytes = BN * 128;
+  static const int kStageBytes = kAStageBytes + kBStageBytes;
+  static const int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static const int kSmem = kStages * kStageBytes + 1024;
+  static const int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512: powers of two
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
+             int num_m_tiles, int num_n_tiles) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int KC = Cin >> 6;
+  const int k_iters = 9 * KC;
+  const int Wp = W + 2;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * kBM;
+        const int n0 = (tile % num_n_tiles) * BN;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = (tap / 3 - 1) * Wp + (tap % 3 - 1);
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tmA, &full_bar[stage], sa, kc * 64, m0 + shift);
+            tma_load_2d(&tmB, &full_bar[stage], sa + kAStageBytes, 0, (tap * KC + kc) * Cout + n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_addr(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = make_desc(sa, 16, 1024);
+          const uint64_t b_desc = make_desc(sa + kAStageBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzled row
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global (interior pixels only) =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const long long HWp = (long long)(H + 2) * Wp;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m = (long long)(tile / num_n_tiles) * kBM + q * 32 + lane;
+      const int n0 = (tile % num_n_tiles) * BN;
+      bool valid = m < Mp;
+      bf16* optr = nullptr;
+      if (valid) {
+        const long long b = m / HWp;
+        const int r = (int)(m - b * HWp);
+        const int yp = r / Wp, xp = r - yp * Wp;
+        valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
+        optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + n0 + c0 + j + i) : 0.f);
+            store8(optr + c0 + j, f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_conv_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, bf16* out, int H, int W,
+                          int Cin, int Cout, long long Mp, cudaStream_t s) {
+  using Cfg = ConvCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  int num_m = (int)((Mp + kBM - 1) / kBM), num_n = Cout / BN;
+  long long tiles = (long long)num_m * num_n;
+  int sms = 148;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  k_conv3x3_tc<BN><<<grid, kConvThreads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
+                      int Cout, cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
+  const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  CUtensorMap tmA, tmB;
+  if (make_tmap(&tmA, in, Cin, Mp, kBM)) return -1;
+  if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;
+  if (BN == 256) return launch_conv_bn<256>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+  if (BN == 128) return launch_conv_bn<128>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+  return launch_conv_bn<64>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------------------
+// One CTA = one "unit" (a set of G accumulator blocks of 128 x BN) over one slice of the pixel axis.
+//   Cin >= 128 (PAIR = false): block j = tap (ky*3 + j) for the unit's ky, rows = 128 input channels, BN = 128, G = 3
+//   Cin == 64  (PAIR = true) : block j = taps (2j, 2j+1) stacked in M (2 x 64 channels), BN = 64, G = 5
+// Per 32-pixel chunk the producer loads, for every block, two [32 px][64 ch] boxes of A (at the taps' row shifts) and
+// BN/64 boxes of dZ; both are MN-major UMMA operands.
+static const int kWgThreads = 192;
+static const int kWgChunk = 32;             // pixels (GEMM-K) per pipeline stage
+static const int kWgBox = kWgChunk * 128;   // bytes of one [32 px][64 ch] box
+
+template <bool PAIR>
+struct WgCfg {
+  static const int G = PAIR ? 5 : 3;
+  static const int BN = PAIR ? 64 : 128;
+  static const int kABytes = G * 2 * kWgBox;
+  static const int kBBytes = (BN / 64) * kWgBox;
+  static const int kStageBytes = kABytes + kBBytes;
+  static const int kStages = PAIR ? 4 : 6;
+  static const int kSmem = kStages * kStageBytes + 1024;
+  static const int kTmemCols = 512;
+};
+
+template <bool PAIR>
+__global__ void __launch_bounds__(kWgThreads, 1)
+k_wgrad3x3_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmZ, float* __restrict__ dw,
+              int W, int Cin, int Cout, int total_chunks, int chunks_per_slice) {
+  using Cfg = WgCfg<PAIR>;
+  constexpr int STAGES = Cfg::kStages, G = Cfg::G, BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // ---- unit decode ----
+  const int unit = blockIdx.x;
+  int cob, ci_base, ky;
+  if (PAIR) { cob = unit; ci_base = 0; ky = 0; }
+  else {
+    const int n_cob = Cout / BN;
+    ky = unit % 3;
+    cob = (unit / 3) % n_cob;
+    ci_base = (unit / 3 / n_cob) * 128;
+  }
+  const int co0 = cob * BN;
+  const int Wp = W + 2;
+  const int c_begin = blockIdx.y * chunks_per_slice;
+  const int c_end = min(total_chunks, c_begin + chunks_per_slice);
+  // sub-block (j, h) -> tap and first input channel
+  auto sub_tap = [&](int j, int h) -> int { return PAIR ? min(2 * j + h, 8) : ky * 3 + j; };
+  auto sub_ci = [&](int h) -> int { return PAIR ? 0 : ci_base + h * 64; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int m = c * kWgChunk;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int tap = sub_tap(j, h);
+            const int shift = (tap / 3 - 1) * Wp + (tap % 3 - 1);
+            tma_load_2d(&tmA, &full_bar[stage], sa + (j * 2 + h) * kWgBox, sub_ci(h), m + shift);
+          }
+#pragma unroll
+        for (int nb = 0; nb < BN / 64; ++nb)
+          tma_load_2d(&tmZ, &full_bar[stage], sa + Cfg::kABytes + nb * kWgBox, co0 + nb * 64, m);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_addr(smem + stage * Cfg::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+#pragma unroll
+          for (int ks = 0; ks < kWgChunk / 16; ++ks) {   // 16 pixels per UMMA = two 8-row swizzle atoms (2048 B)
+            const uint64_t a_desc = make_desc(sa + (j * 2) * kWgBox + ks * 2048, kWgBox, 1024);
+            const uint64_t b_desc = make_desc(sa + Cfg::kABytes + ks * 2048, kWgBox, 1024);
+            umma_bf16(tmem_base + j * BN, a_desc, b_desc, idesc, (c > c_begin || ks > 0) ? 1u : 0u);
+          }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar);
+    }
+  } else if (c_end > c_begin) {
+    // ===== epilogue: fp32 accumulators -> atomicAdd into dw[tap][ci][co] =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;   // accumulator row = h*64 + channel
+    const int h = row >> 6;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < G; ++j) {
+      const int tap = sub_tap(j, h);
+      const bool dup = PAIR && (2 * j + h > 8);
+      const int ci = sub_ci(h) + (row & 63);
+      float* dst = dw + ((long long)tap * Cin + ci) * Cout + co0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + c0), v);
+        tmem_ld_wait();
+        if (!dup) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// db[co] += sum over all padded rows of dz (halo rows are zero)
+__global__ void k_bias_grad(const bf16* __restrict__ dz, long long rows, int C, float* __restrict__ db) {
+  extern __shared__ float sh[];
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = 0.f;
+  for (long long r = (long long)blockIdx.x * lanes + lane; r < rows; r += (long long)gridDim.x * lanes) {
+    float v[8];
+    load8(dz + r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&sh[g * 8 + i], s1[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sh[i]);
+}
+
+template <bool PAIR>
+static int launch_wgrad_cfg(const CUtensorMap& tmA, const CUtensorMap& tmZ, float* dw, int W, int Cin, int Cout,
+                            long long Mp, cudaStream_t s) {
+  using Cfg = WgCfg<PAIR>;
+  static bool configured = false;
+  if (!configured) {
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad3x3_tc<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  const int units = PAIR ? Cout / Cfg::BN : (Cin / 128) * (Cout / Cfg::BN) * 3;
+  const int total_chunks = (int)((Mp + kWgChunk - 1) / kWgChunk);
+  // enough slices for ~2 waves of 148 CTAs, but at least 16 chunks of work per slice
+  int slices = (2 * 148 + units - 1) / units;
+  int max_slices = (total_chunks + 15) / 16;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int cps = (total_chunks + slices - 1) / slices;
+  slices = (total_chunks + cps - 1) / cps;
+  dim3 grid(units, slices);
+  k_wgrad3x3_tc<PAIR><<<grid, kWgThreads, Cfg::kSmem, s>>>(tmA, tmZ, dw, W, Cin, Cout, total_chunks, cps);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
+                       cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && (Cin == 64 || Cin % 128 == 0) && (Cin == 64 || Cout % 128 == 0),
+             "wgrad_tc: unsupported channels Cin=%d Cout=%d", Cin, Cout);
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) < 0x7fffffffLL, "wgrad_tc: too many pixels for 32-bit TMA coordinates");
+  CUtensorMap tmA, tmZ;
+  if (make_tmap(&tmA, a, Cin, Mp, kWgChunk)) return -1;
+  if (make_tmap(&tmZ, dz, Cout, Mp, kWgChunk)) return -1;
+  int rc = (Cin == 64) ? launch_wgrad_cfg<true>(tmA, tmZ, dw, W, Cin, Cout, Mp, s)
+                       : launch_wgrad_cfg<false>(tmA, tmZ, dw, W, Cin, Cout, Mp, s);
+  if (rc) return rc;
+  if (db) {
+    L3_REQUIRE(256 % (Cout / 8) == 0, "bias_grad: Cout=%d", Cout);
+    int lanes = 256 / (Cout / 8);
+    long long want = (Mp + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+    int blocks = (int)(want > 148 * 4 ? 148 * 4 : (want < 1 ? 1 : want));
+    k_bias_grad<<<blocks, 256, Cout * sizeof(float), s>>>(dz, Mp, Cout, db);
+    L3_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace l3
