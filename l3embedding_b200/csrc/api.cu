@@ -443,29 +443,34 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
     // weight / bias gradient
     {
-    ProfScope ps(c, PROF_CONV_WGRAD);
-    if (L.tc && c->use_tc) {
-      if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
-    } else {
-      if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
-    }
-    }
-    if (l == 0 && !tw.has_bn0) break;
-    // data gradient: da = conv(dz, flip/transpose(w))
-    {
-    ProfScope ps(c, PROF_CONV_DGRAD);
-    if (L.tc && c->use_tc) {
-      if (launch_pack_weights_tc(L.w, L.wt_pk, L.Cin, L.Cout, 1, s)) return -1;
-      if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
-    } else {
-      if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
-      if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
-    }
+      ProfScope ps(c, PROF_CONV_WGRAD);
+      if (L.tc && c->use_tc) {
+        if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+      } else if (l == 0) {
+        if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+      } else {
+        if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+      }
     }
     if (l == 0) {
-      if (launch_input_bn_bwd_stats<T>(da, tw.x0, rows, tw.C0, tw.bn0, s)) return -1;
-      if (launch_bn_bwd_finalize(tw.bn0, rows, s)) return -1;  // writes d_gamma / d_beta of the input BN
+      if (tw.has_bn0) {
+        // input BN: d_gamma / d_beta need only sum(da), sum(da*xhat) -- computed without storing da
+        ProfScope ps(c, PROF_CONV_DGRAD);
+        if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+        if (launch_bn_bwd_finalize(tw.bn0, rows, s)) return -1;
+      }
       break;
+    }
+    // data gradient: da = conv(dz, flip/transpose(w))
+    {
+      ProfScope ps(c, PROF_CONV_DGRAD);
+      if (L.tc && c->use_tc) {
+        if (launch_pack_weights_tc(L.w, L.wt_pk, L.Cin, L.Cout, 1, s)) return -1;
+        if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+      } else {
+        if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
+        if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+      }
     }
     ConvLayer& Lp = tw.L[l - 1];
     if (launch_act_bwd<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;

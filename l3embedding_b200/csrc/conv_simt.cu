@@ -213,3 +213,146 @@ int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStr
 }
 
 }  // namespace l3
+
+// ==========================================================================================================
+// First-layer backward (Cin = 1 audio / 3 vision, Cout = 64): K = 9 / 27 is far too small for a GEMM tile, and
+// both products are HBM/LSU-bound reductions, so they get dedicated kernels.
+// ==========================================================================================================
+namespace l3 {
+
+// dw[tap][c][co] += sum_px a[px+tap][c] * dz[px][co] ; db[co] += sum_px dz[px][co]
+// block = 64 output channels x 4 pixel lanes; every thread keeps its 9*C0 partial sums in registers; the input
+// taps are warp-broadcast loads (all 32 lanes of a warp read the same address).
+template <typename T, int C0>
+__global__ void __launch_bounds__(256)
+k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
+              int B, int H, int W, int rows_per_block) {
+  constexpr int CO = 64, K = 9 * C0;
+  const int co = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  float acc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  const long long n_rows = (long long)B * H;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(n_rows, r0 + rows_per_block);
+  const int Wp = W + 2;
+  for (long long r = r0; r < r1; ++r) {
+    const long long b = r / H;
+    const int y = (int)(r - b * H);
+    const T* dzrow = dz + pad_off(b, y, 0, H, W, CO) + co;
+    const T* arow = a + pad_off(b, y - 1, -1, H, W, C0);   // top-left tap of pixel x = 0
+    for (int x = lane; x < W; x += 4) {
+      const float g = to_f(dzrow[(long long)x * CO]);
+      bsum += g;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int c = 0; c < C0; ++c)
+            acc[(ky * 3 + kx) * C0 + c] = fmaf(to_f(arow[((long long)ky * Wp + x + kx) * C0 + c]), g, acc[(ky * 3 + kx) * C0 + c]);
+    }
+  }
+  __shared__ float red[4][K + 1][CO];
+#pragma unroll
+  for (int i = 0; i < K; ++i) red[lane][i][co] = acc[i];
+  red[lane][K][co] = bsum;
+  __syncthreads();
+  for (int i = threadIdx.x; i < (K + 1) * CO; i += blockDim.x) {
+    const int k = i / CO, c = i % CO;
+    const float v = red[0][k][c] + red[1][k][c] + red[2][k][c] + red[3][k][c];
+    if (k < K) atomicAdd(&dw[k * CO + c], v);
+    else if (db) atomicAdd(&db[c], v);
+  }
+}
+
+template <typename T>
+int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int C0, int Cout,
+                       cudaStream_t s) {
+  L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_wgrad: C0=%d Cout=%d", C0, Cout);
+  long long n_rows = (long long)B * H;
+  int rpb = (int)((n_rows + 148 * 8 - 1) / (148 * 8));
+  if (rpb < 1) rpb = 1;
+  int blocks = (int)((n_rows + rpb - 1) / rpb);
+  if (C0 == 1) k_first_wgrad<T, 1><<<blocks, 256, 0, s>>>(a, dz, dw, db, B, H, W, rpb);
+  else k_first_wgrad<T, 3><<<blocks, 256, 0, s>>>(a, dz, dw, db, B, H, W, rpb);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_first_wgrad<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t);
+
+// Input-BN backward without materialising the data gradient: one thread per input pixel computes
+//   da[c] = sum_{ky,kx,co} dz[y+1-ky, x+1-kx, co] * w[ky][kx][c][co]
+// and the block accumulates sum(da) and sum(da * xhat) per input channel (xhat from the float front-end / video
+// tensor x0) into bn.sum (double[2*C0]); launch_bn_bwd_finalize then yields d_gamma / d_beta.
+template <typename T, int C0>
+__global__ void __launch_bounds__(128)
+k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ x0, BnRef bn,
+                      int B, int H, int W) {
+  constexpr int CO = 64;
+  __shared__ __align__(16) float ws[9 * C0 * CO];
+  __shared__ float red[2 * C0];
+  for (int i = threadIdx.x; i < 9 * C0 * CO; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 2 * C0) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long npix = (long long)B * H * W;
+  float s1[C0], s2[C0], mean[C0], inv[C0];
+#pragma unroll
+  for (int c = 0; c < C0; ++c) { s1[c] = s2[c] = 0.f; mean[c] = bn.mean[c]; inv[c] = bn.invstd[c]; }
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    float da[C0];
+#pragma unroll
+    for (int c = 0; c < C0; ++c) da[c] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const T* src = dz + pad_off(b, y + 1 - ky, x + 1 - kx, H, W, CO);
+      const float* wt = ws + tap * C0 * CO;
+#pragma unroll
+      for (int g = 0; g < CO; g += 8) {
+        float v[8];
+        load8(src + g, v);
+#pragma unroll
+        for (int c = 0; c < C0; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) da[c] = fmaf(v[i], wt[c * CO + g + i], da[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C0; ++c) {
+      const float xh = (x0[p * C0 + c] - mean[c]) * inv[c];
+      s1[c] += da[c];
+      s2[c] += da[c] * xh;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C0; ++c) {
+    const float a1 = warp_sum(s1[c]), a2 = warp_sum(s2[c]);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[c], a1); atomicAdd(&red[C0 + c], a2); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C0) atomicAdd(&bn.sum[threadIdx.x], (double)red[threadIdx.x]);
+}
+
+template <typename T>
+int launch_first_dgrad_bnstats(const T* dz, const float* w, const float* x0, const BnRef& bn, int B, int H, int W, int C0,
+                               int Cout, cudaStream_t s) {
+  L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_dgrad: C0=%d Cout=%d", C0, Cout);
+  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C0, s));
+  long long npix = (long long)B * H * W;
+  long long want = (npix + 127) / 128;
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+  if (C0 == 1) k_first_dgrad_bnstats<T, 1><<<blocks, 128, 0, s>>>(dz, w, x0, bn, B, H, W);
+  else k_first_dgrad_bnstats<T, 3><<<blocks, 128, 0, s>>>(dz, w, x0, bn, B, H, W);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_first_dgrad_bnstats<float>(const float*, const float*, const float*, const BnRef&, int, int, int, int, int, cudaStream_t);
+template int launch_first_dgrad_bnstats<bf16>(const bf16*, const float*, const float*, const BnRef&, int, int, int, int, int, cudaStream_t);
+
+}  // namespace l3

