@@ -438,14 +438,20 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
   for (int l = 7; l >= 0; --l) {
     ConvLayer& L = tw.L[l];
     long long rows = (long long)B * L.H * L.W;
-    // dz currently holds dy (grad wrt the BN output, or wrt BN input side for relu_first) + bn.sum holds the sums
-    if (launch_bn_bwd_finalize(L.bn, rows, s)) return -1;
-    if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
+    if (l == 7) {
+      // dz holds the scattered dy of the global max-pool and bn.sum its sums: finish BN backward in place
+      if (launch_bn_bwd_finalize(L.bn, rows, s)) return -1;
+      if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
+    }
     // weight / bias gradient
     {
       ProfScope ps(c, PROF_CONV_WGRAD);
       if (L.tc && c->use_tc) {
-        if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+        // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
+        // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
+        if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
+                               L.Cout, s))
+          return -1;
       } else if (l == 0) {
         if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
       } else {
@@ -472,8 +478,12 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
         if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
       }
     }
+    // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz (padded, full resolution)
     ConvLayer& Lp = tw.L[l - 1];
-    if (launch_act_bwd<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+    long long rows_p = (long long)B * Lp.H * Lp.W;
+    if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+    if (launch_bn_bwd_finalize(Lp.bn, rows_p, s)) return -1;
+    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
   }
   return 0;
 }

@@ -16,6 +16,7 @@
 //   both operands are "MN-major" (channels contiguous), which UMMA reads directly from the same TMA boxes;
 //   split-K over pixel slices with fp32 atomics into dW.
 #include <cuda.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace l3 {
@@ -346,12 +347,233 @@ static int launch_conv_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// forward / dgrad, version 2: shared-halo A regions
+// ---------------------------------------------------------------------------------------------------------
+// The three kx taps of one filter row read the SAME pixels shifted by one row of the flattened index, so one
+// shared-memory region of (MT*128 + 2) rows serves all three: the UMMA descriptor of tap kx simply starts kx rows
+// (kx*128 B) into the region (the 128-byte swizzle is a function of the absolute shared-memory address, so a
+// row-granular start is legal).  One CTA tile covers MT consecutive 128-row M tiles that share every weight tile.
+// Per (ky, 64-channel chunk) the CTA ingests (MT*128+8)*128 B of activations + 3*BN*128 B of weights for
+// 12*MT MMAs, instead of 3*(MT*16 KB + BN*128 B) -- 2-3x less L2->SMEM traffic per FLOP and 3*MT x fewer barrier
+// round trips per MMA than version 1, which is what the small-N layers (Cout 64/128) were bound by.
+template <int BN, int MT>
+struct Conv2Cfg {
+  static const int kARows = MT * kBM + 8;                 // region rows (multiple of 8 -> 1024-byte multiple)
+  static const int kABoxes = (MT == 4) ? 5 : (MT == 2 ? 3 : 1);
+  static const int kABoxRows = kARows / kABoxes;          // 104 / 88 / 136: multiples of 8
+  static const int kAStage = kARows * 128;
+  static const int kAStages = (MT == 4) ? 2 : (MT == 2 ? 3 : 4);
+  static const int kBStage = BN * 128;
+  static const int kBStages = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
+  static const int kSmem = kAStages * kAStage + kBStages * kBStage + 1024;
+  static const int kTmemCols = 2 * MT * BN;               // 512 for (64,4), (128,2), (256,1)
+};
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
+              int num_m_tiles, int num_n_tiles, int base_offset_mode) {
+  using Cfg = Conv2Cfg<BN, MT>;
+  constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + AST * Cfg::kAStage;
+  __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int KC = Cin >> 6;
+  const int Wp = W + 2;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * (MT * kBM);
+        const int n0 = (tile % num_n_tiles) * BN;
+        for (int kc = 0; kc < KC; ++kc)
+          for (int ky = 0; ky < 3; ++ky) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            uint8_t* sa = smem + as * Cfg::kAStage;
+            mbar_expect_tx(&a_full[as], Cfg::kAStage);
+            const int row0 = m0 + (ky - 1) * Wp - 1;
+#pragma unroll
+            for (int bx = 0; bx < Cfg::kABoxes; ++bx)
+              tma_load_2d(&tmA, &a_full[as], sa + bx * Cfg::kABoxRows * 128, kc * 64, row0 + bx * Cfg::kABoxRows);
+            if (++as == AST) { as = 0; aph ^= 1; }
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_expect_tx(&b_full[bs], Cfg::kBStage);
+              tma_load_2d(&tmB, &b_full[bs], smem_b + bs * Cfg::kBStage, 0, ((ky * 3 + kx) * KC + kc) * Cout + n0);
+              if (++bs == BST) { bs = 0; bph ^= 1; }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        uint32_t first = 1;
+        for (int it = 0; it < 3 * KC; ++it) {
+          mbar_wait(&a_full[as], aph);
+          const uint32_t sa = smem_addr(smem + as * Cfg::kAStage);
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint64_t b_desc = make_desc(smem_addr(smem_b + bs * Cfg::kBStage), 16, 1024);
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+              const uint32_t a_addr = sa + (uint32_t)(t * kBM + kx) * 128u;
+              uint64_t a_desc = make_desc(a_addr, 16, 1024);
+              if (base_offset_mode) a_desc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem + t * BN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            umma_commit(&b_empty[bs]);
+            if (++bs == BST) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == AST) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const long long HWp = (long long)(H + 2) * Wp;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long mbase = (long long)(tile / num_n_tiles) * (MT * kBM) + q * 32 + lane;
+      const int n0 = (tile % num_n_tiles) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < MT; ++t) {
+        const long long m = mbase + t * kBM;
+        bool valid = m < Mp;
+        bf16* optr = nullptr;
+        if (valid) {
+          const long long b = m / HWp;
+          const int r = (int)(m - b * HWp);
+          const int yp = r / Wp, xp = r - yp * Wp;
+          valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
+          optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + n0 + c0 + j + i) : 0.f);
+              store8(optr + c0 + j, f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+template <int BN, int MT>
+static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
+                        int Cout, long long Mp, int base_offset_mode, cudaStream_t s) {
+  using Cfg = Conv2Cfg<BN, MT>;
+  static bool configured = false;
+  if (!configured) {
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tmap(&tmA, in, Cin, Mp, Cfg::kABoxRows)) return -1;
+  if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;
+  int num_m = (int)((Mp + MT * kBM - 1) / (MT * kBM)), num_n = Cout / BN;
+  long long tiles = (long long)num_m * num_n;
+  int grid = (int)(tiles < 148 ? tiles : 148);
+  k_conv3x3_tc2<BN, MT><<<grid, kConvThreads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n,
+                                                             base_offset_mode);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions (default), 3 = version 2 with the
+// descriptor base-offset field set (kept for A/B checks of the descriptor semantics)
+static int conv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_CONV_TC_VARIANT");
+    v = e ? atoi(e) : 2;
+    if (v < 1 || v > 3) v = 2;
+  }
+  return v;
+}
+
 int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
                       int Cout, cudaStream_t s) {
   L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
-  L3_REQUIRE(Mp + 4LL * (W + 2) < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
+  L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  const int variant = conv_variant();
+  if (variant >= 2) {
+    const int bo = variant == 3 ? 1 : 0;
+    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
+    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
+    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
+  }
   CUtensorMap tmA, tmB;
   if (make_tmap(&tmA, in, Cin, Mp, kBM)) return -1;
   if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;

@@ -368,15 +368,18 @@ template int launch_gmaxpool_bwd<float>(const float*, int, const int*, const flo
 template int launch_gmaxpool_bwd<bf16>(const float*, int, const int*, const bf16*, bf16*, const BnRef&, int, int, int, int, cudaStream_t);
 
 // --------------------------------------------------------------------------------------------
-// activation backward: da (pooled res) -> dy (grad wrt BN output, full res) + sum(dy), sum(dy*xhat)
+// activation + BatchNorm backward, two passes over (da, z) with no intermediate tensor:
 //   normal     : a = pool(relu(bn(z)))      dy = unpool(da) * [bn(z) > 0]      xhat from z
 //   relu_first : a = pool(bn(relu(z)))      dy = unpool(da)                    xhat from relu(z)
-// max-pool routes to the first maximum in window order (0,0),(0,1),(1,0),(1,1); rows/cols dropped by
-// 'valid' pooling of odd sizes receive zero gradient.
+//   pass 1 (k_bwd_stats): sum(dy), sum(dy*xhat) per channel                     -> bn.sum
+//   pass 2 (k_bwd_apply): dz = scale*(dy - c1 - xhat*c2) [*(z>0) if relu_first] -> zero-haloed padded buffer
+// max-pool routes to the first maximum in window order (0,0),(0,1),(1,0),(1,1); pixels dropped by 'valid' pooling of
+// odd sizes have dy = 0 (they still receive the BN mean terms).  da: unpadded (B,OH,OW,C); z: unpadded (B,H,W,C).
 // --------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_act_bwd(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dy, int H, int W, int C,
-                          int OH, int OW, long long npix, BnRef bn, int pool, int relu_first) {
+__global__ void __launch_bounds__(256)
+k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int C, int OH, int OW, long long npix,
+            BnRef bn, int pool, int relu_first) {
   extern __shared__ float sh[];  // 2*C
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
@@ -389,63 +392,39 @@ __global__ void k_act_bwd(const T* __restrict__ da, const T* __restrict__ z, T* 
   load8(bn.invstd + g * 8, inv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-    float g8[8];
+    float g8[8], zs[8], m[8];
     load8(da + p * C + g * 8, g8);
-    const int ox = (int)(p % OW);
-    const int oy = (int)((p / OW) % OH);
-    const long long b = p / ((long long)OW * OH);
     if (!pool) {
-      float v[8], y[8], o[8];
-      load8(z + p * C + g * 8, v);
-      act8(v, sc, sf, relu_first, y);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float d = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
-        d = to_f(from_f<T>(d));
-        float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
-        o[i] = d;
-        s1[i] += d;
-        s2[i] += d * ((xin - mean[i]) * inv[i]);
-      }
-      store8(dy + pad_off(b, oy, ox, H, W, C) + g * 8, o);
+      load8(z + p * C + g * 8, zs);
+      act8(zs, sc, sf, relu_first, m);
     } else {
-      float v[4][8], y[4][8];
+      const int ox = (int)(p % OW);
+      const int oy = (int)((p / OW) % OH);
+      const long long b = p / ((long long)OW * OH);
+      const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+      float v1[8], v2[8], v3[8], y[8];
+      load8(z00, zs);
+      load8(z00 + C, v1);
+      load8(z00 + (long long)W * C, v2);
+      load8(z00 + (long long)W * C + C, v3);
+      act8(zs, sc, sf, relu_first, m);
+      act8(v1, sc, sf, relu_first, y);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        load8(z + ((b * H + 2 * oy + (k >> 1)) * W + 2 * ox + (k & 1)) * C + g * 8, v[k]);
-        act8(v[k], sc, sf, relu_first, y[k]);
-      }
-      float o[4][8];
+      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; zs[i] = v1[i]; }
+      act8(v2, sc, sf, relu_first, y);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int arg = 0;
-        float m = y[0][i];
+      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; zs[i] = v2[i]; }
+      act8(v3, sc, sf, relu_first, y);
 #pragma unroll
-        for (int k = 1; k < 4; ++k)
-          if (y[k][i] > m) { m = y[k][i]; arg = k; }
-        float d = relu_first ? g8[i] : (m > 0.f ? g8[i] : 0.f);
-        d = to_f(from_f<T>(d));
+      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; zs[i] = v3[i]; }
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k][i] = (k == arg) ? d : 0.f;
-        float zin = arg == 0 ? v[0][i] : arg == 1 ? v[1][i] : arg == 2 ? v[2][i] : v[3][i];
-        float xin = relu_first ? fmaxf(zin, 0.f) : zin;
-        s1[i] += d;
-        s2[i] += d * ((xin - mean[i]) * inv[i]);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) store8(dy + pad_off(b, 2 * oy + (k >> 1), 2 * ox + (k & 1), H, W, C) + g * 8, o[k]);
-      // rows / columns dropped by valid pooling of odd sizes get zero gradient
-      if ((W & 1) && ox == OW - 1) {
-        store8(dy + pad_off(b, 2 * oy, W - 1, H, W, C) + g * 8, zero8);
-        store8(dy + pad_off(b, 2 * oy + 1, W - 1, H, W, C) + g * 8, zero8);
-      }
-      if ((H & 1) && oy == OH - 1) {
-        store8(dy + pad_off(b, H - 1, 2 * ox, H, W, C) + g * 8, zero8);
-        store8(dy + pad_off(b, H - 1, 2 * ox + 1, H, W, C) + g * 8, zero8);
-        if ((W & 1) && ox == OW - 1) store8(dy + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, zero8);
-      }
+    for (int i = 0; i < 8; ++i) {
+      float d = relu_first ? g8[i] : (m[i] > 0.f ? g8[i] : 0.f);
+      float xin = relu_first ? fmaxf(zs[i], 0.f) : zs[i];
+      s1[i] += d;
+      s2[i] += d * ((xin - mean[i]) * inv[i]);
     }
   }
 #pragma unroll
@@ -456,24 +435,133 @@ __global__ void k_act_bwd(const T* __restrict__ da, const T* __restrict__ z, T* 
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn.sum[i], (double)sh[i]);
 }
-// da: unpadded (B,OH,OW,C); z: unpadded (B,H,W,C); dy: zero-haloed padded (B,H+2,W+2,C) (halo zeroed here)
 template <typename T>
-int launch_act_bwd(const T* da, const T* z, T* dy, int B, int H, int W, int C, const BnRef& bn, int pool,
-                   int relu_first, cudaStream_t s) {
-  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "act_bwd: C=%d", C);
+int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const BnRef& bn, int pool, int relu_first,
+                     cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "bwd_stats: C=%d", C);
   L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
-  if (launch_zero_halo<T>(dy, B, H, W, C, s)) return -1;
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
   int lanes = kThreads / (C / 8);
-  long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
-  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
-  k_act_bwd<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, dy, H, W, C, OH, OW, npix, bn, pool, relu_first);
+  long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  k_bwd_stats<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, pool, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_act_bwd<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
-template int launch_act_bwd<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_bwd_stats<float>(const float*, const float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_bwd_stats<bf16>(const bf16*, const bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+
+struct BnBwdCoef {
+  float sc[8], mean[8], inv[8], c1[8], c2[8];
+};
+template <typename T>
+__device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8], const float (&d)[8], const BnBwdCoef& k,
+                                         int relu_first) {
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
+    float xh = (xin - k.mean[i]) * k.inv[i];
+    float r = k.sc[i] * (d[i] - k.c1[i] - xh * k.c2[i]);
+    if (relu_first && !(v[i] > 0.f)) r = 0.f;
+    o[i] = r;
+  }
+  store8(dst, o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
+            long long total, BnRef bn, int pool, int relu_first) {
+  const int groups = C >> 3;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long p = idx / groups;
+  const int ox = (int)(p % OW);
+  const int oy = (int)((p / OW) % OH);
+  const long long b = p / ((long long)OW * OH);
+  float sf[8], g8[8];
+  BnBwdCoef k;
+  load8(bn.scale + g * 8, k.sc);
+  load8(bn.shift + g * 8, sf);
+  load8(bn.mean + g * 8, k.mean);
+  load8(bn.invstd + g * 8, k.inv);
+  load8(bn.c1 + g * 8, k.c1);
+  load8(bn.c2 + g * 8, k.c2);
+  load8(da + p * C + g * 8, g8);
+  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!pool) {
+    float v[8], y[8], d[8];
+    load8(z + p * C + g * 8, v);
+    act8(v, k.sc, sf, relu_first, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
+    bwd_emit<T>(dz + pad_off(b, oy, ox, H, W, C) + g * 8, v, d, k, relu_first);
+    return;
+  }
+  float v[4][8], m[8];
+  int arg[8];
+  {
+    const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+    load8(z00, v[0]);
+    load8(z00 + C, v[1]);
+    load8(z00 + (long long)W * C, v[2]);
+    load8(z00 + (long long)W * C + C, v[3]);
+    float y[8];
+    act8(v[0], k.sc, sf, relu_first, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) arg[i] = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      act8(v[q], k.sc, sf, relu_first, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = (arg[i] == q && (relu_first || m[i] > 0.f)) ? g8[i] : 0.f;
+    bwd_emit<T>(dz + pad_off(b, 2 * oy + (q >> 1), 2 * ox + (q & 1), H, W, C) + g * 8, v[q], d, k, relu_first);
+  }
+  // rows / columns dropped by valid pooling of odd sizes: dy = 0
+  const bool last_x = (W & 1) && ox == OW - 1, last_y = (H & 1) && oy == OH - 1;
+  if (last_x) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      load8(z + ((b * H + 2 * oy + r) * W + W - 1) * C + g * 8, v[0]);
+      bwd_emit<T>(dz + pad_off(b, 2 * oy + r, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+    }
+  }
+  if (last_y) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      load8(z + ((b * H + H - 1) * W + 2 * ox + r) * C + g * 8, v[0]);
+      bwd_emit<T>(dz + pad_off(b, H - 1, 2 * ox + r, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+    }
+    if (last_x) {
+      load8(z + ((b * H + H - 1) * W + W - 1) * C + g * 8, v[0]);
+      bwd_emit<T>(dz + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+    }
+  }
+}
+// dz: zero-haloed padded (B,H+2,W+2,C); the halo is (re)zeroed here because the buffer is shared between layers
+template <typename T>
+int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
+                     int relu_first, cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0, "bwd_apply: C=%d", C);
+  if (launch_zero_halo<T>(dz, B, H, W, C, s)) return -1;
+  int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
+  long long total = (long long)B * OH * OW * (C / 8);
+  k_bwd_apply<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, total, bn, pool, relu_first);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_bwd_apply<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_bwd_apply<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
 
 // BN backward finalize: dgamma, dbeta, c1 = mean(dy), c2 = mean(dy*xhat)
 __global__ void k_bn_bwd_finalize(BnRef bn, double count) {

@@ -51,9 +51,13 @@ int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, co
 template <typename T>
 int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax, const T* z, T* dy, const BnRef& bn,
                         int B, int H, int W, int C, cudaStream_t s);   // dy: padded
+// activation + BN backward in two passes over (da, z): pass 1 -> bn.sum = {sum dy, sum dy*xhat}; pass 2 -> dz (padded)
 template <typename T>
-int launch_act_bwd(const T* da, const T* z, T* dy, int B, int H, int W, int C, const BnRef& bn, int pool,
-                   int relu_first, cudaStream_t s);
+int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const BnRef& bn, int pool, int relu_first,
+                     cudaStream_t s);
+template <typename T>
+int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
+                     int relu_first, cudaStream_t s);
 int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s);
 template <typename T>
 int launch_bn_bwd_apply(T* dy_inout, const T* z, int B, int H, int W, int C, const BnRef& bn, int relu_first,
