@@ -371,6 +371,8 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B) {
     if (launch_pack_weights_tc(L.w, L.w_pk, L.Cin, L.Cout, 0, c->stream)) return -1;
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
   }
+  if (L.Cin <= 3 && L.Cout == 64)
+    return launch_first_conv<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
   return launch_conv3x3_simt<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
 }
 

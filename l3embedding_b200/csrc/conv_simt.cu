@@ -215,14 +215,99 @@ int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStr
 }  // namespace l3
 
 // ==========================================================================================================
-// First-layer backward (Cin = 1 audio / 3 vision, Cout = 64): K = 9 / 27 is far too small for a GEMM tile, and
-// both products are HBM/LSU-bound reductions, so they get dedicated kernels.
+// First-layer kernels (Cin = 1 audio / 3 vision, Cout = 64): K = 9 / 27 is far too small for a GEMM tile; all three
+// products are HBM/LSU-bound, so they get dedicated direct kernels with a sliding 3x3 input window in registers.
 // ==========================================================================================================
 namespace l3 {
 
+static const int kFirstSeg = 16;   // x-segments per image row = pixel lanes per block
+
+// forward: out[b,y,x,co] = bias[co] + sum_{ky,kx,c} in[b,y+ky,x+kx,c] (padded coords) * w[ky][kx][c][co]
+// block = 16 channel groups (4 output channels each, weights in registers) x 16 pixel lanes (contiguous x segments)
+template <typename T, int C0>
+__global__ void __launch_bounds__(256)
+k_first_conv(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+             int B, int H, int W, int rows_per_block) {
+  constexpr int CO = 64, K = 9 * C0;
+  const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  float wr[K][4], b4[4];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(w + k * CO + cg * 4);
+    wr[k][0] = t.x; wr[k][1] = t.y; wr[k][2] = t.z; wr[k][3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b4[i] = bias ? bias[cg * 4 + i] : 0.f;
+  const int seg = (W + kFirstSeg - 1) / kFirstSeg;
+  const int x0 = pl * seg, x1 = min(W, x0 + seg);
+  const int Wp = W + 2;
+  const long long n_rows = (long long)B * H;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  for (long long r = r0; r < r1; ++r) {
+    if (x0 >= x1) break;
+    const long long b = r / H;
+    const int y = (int)(r - b * H);
+    const T* arow = in + pad_off(b, y - 1, -1, H, W, C0);   // padded row y (top tap), padded column 0
+    float win[3][3][C0];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 1; kx < 3; ++kx)
+#pragma unroll
+        for (int c = 0; c < C0; ++c) win[ky][kx][c] = to_f(arow[((long long)ky * Wp + x0 + kx - 1) * C0 + c]);
+    T* orow = out + ((b * H + y) * (long long)W) * CO + cg * 4;
+    for (int x = x0; x < x1; ++x) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int c = 0; c < C0; ++c) {
+          win[ky][0][c] = win[ky][1][c];
+          win[ky][1][c] = win[ky][2][c];
+          win[ky][2][c] = to_f(arow[((long long)ky * Wp + x + 2) * C0 + c]);
+        }
+      float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int c = 0; c < C0; ++c) {
+            const float v = win[ky][kx][c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(v, wr[(ky * 3 + kx) * C0 + c][i], acc[i]);
+          }
+      T* o = orow + (long long)x * CO;
+      if (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+        uint2 u;
+        u.x = pack_bf16x2(acc[0], acc[1]);
+        u.y = pack_bf16x2(acc[2], acc[3]);
+        *reinterpret_cast<uint2*>(o) = u;
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch_first_conv(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int C0, int Cout,
+                      cudaStream_t s) {
+  L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_conv: C0=%d Cout=%d", C0, Cout);
+  long long n_rows = (long long)B * H;
+  int rpb = (int)((n_rows + 148 * 16 - 1) / (148 * 16));
+  if (rpb < 1) rpb = 1;
+  int blocks = (int)((n_rows + rpb - 1) / rpb);
+  if (C0 == 1) k_first_conv<T, 1><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb);
+  else k_first_conv<T, 3><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+template int launch_first_conv<float>(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_first_conv<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
+
 // dw[tap][c][co] += sum_px a[px+tap][c] * dz[px][co] ; db[co] += sum_px dz[px][co]
-// block = 64 output channels x 4 pixel lanes; every thread keeps its 9*C0 partial sums in registers; the input
-// taps are warp-broadcast loads (all 32 lanes of a warp read the same address).
+// block = 64 output channels x 4 pixel lanes (contiguous x segments, sliding input window: 3*C0 new taps per pixel,
+// all warp-broadcast loads); every thread keeps its 9*C0 partial sums in registers.
 template <typename T, int C0>
 __global__ void __launch_bounds__(256)
 k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
@@ -237,12 +322,30 @@ k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restri
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(n_rows, r0 + rows_per_block);
   const int Wp = W + 2;
+  const int seg = (W + 3) / 4;
+  const int x0 = lane * seg, x1 = min(W, x0 + seg);
   for (long long r = r0; r < r1; ++r) {
+    if (x0 >= x1) break;
     const long long b = r / H;
     const int y = (int)(r - b * H);
     const T* dzrow = dz + pad_off(b, y, 0, H, W, CO) + co;
     const T* arow = a + pad_off(b, y - 1, -1, H, W, C0);   // top-left tap of pixel x = 0
-    for (int x = lane; x < W; x += 4) {
+    float win[3][3][C0];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 1; kx < 3; ++kx)
+#pragma unroll
+        for (int c = 0; c < C0; ++c) win[ky][kx][c] = to_f(arow[((long long)ky * Wp + x0 + kx - 1) * C0 + c]);
+    for (int x = x0; x < x1; ++x) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int c = 0; c < C0; ++c) {
+          win[ky][0][c] = win[ky][1][c];
+          win[ky][1][c] = win[ky][2][c];
+          win[ky][2][c] = to_f(arow[((long long)ky * Wp + x + 2) * C0 + c]);
+        }
       const float g = to_f(dzrow[(long long)x * CO]);
       bsum += g;
 #pragma unroll
@@ -251,7 +354,7 @@ k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restri
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int c = 0; c < C0; ++c)
-            acc[(ky * 3 + kx) * C0 + c] = fmaf(to_f(arow[((long long)ky * Wp + x + kx) * C0 + c]), g, acc[(ky * 3 + kx) * C0 + c]);
+            acc[(ky * 3 + kx) * C0 + c] = fmaf(win[ky][kx][c], g, acc[(ky * 3 + kx) * C0 + c]);
     }
   }
   __shared__ float red[4][K + 1][CO];
@@ -283,12 +386,14 @@ int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int
 template int launch_first_wgrad<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t);
 
-// Input-BN backward without materialising the data gradient: one thread per input pixel computes
+// Input-BN backward without materialising the data gradient.  8 threads per input pixel (8 of the 64 dz channels
+// each, so a warp reads 4 pixels x 128 B fully coalesced) compute
 //   da[c] = sum_{ky,kx,co} dz[y+1-ky, x+1-kx, co] * w[ky][kx][c][co]
-// and the block accumulates sum(da) and sum(da * xhat) per input channel (xhat from the float front-end / video
-// tensor x0) into bn.sum (double[2*C0]); launch_bn_bwd_finalize then yields d_gamma / d_beta.
+// reduce over the 8 lanes by shuffles, and the block accumulates sum(da) and sum(da * xhat) per input channel (xhat
+// from the float front-end / video tensor x0) into bn.sum (double[2*C0]); k_bn_bwd_finalize then yields d_gamma /
+// d_beta.
 template <typename T, int C0>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ x0, BnRef bn,
                       int B, int H, int W) {
   constexpr int CO = 64;
@@ -297,37 +402,47 @@ k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, con
   for (int i = threadIdx.x; i < 9 * C0 * CO; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 2 * C0) red[threadIdx.x] = 0.f;
   __syncthreads();
+  const int g = threadIdx.x & 7;
   const long long npix = (long long)B * H * W;
   float s1[C0], s2[C0], mean[C0], inv[C0];
 #pragma unroll
   for (int c = 0; c < C0; ++c) { s1[c] = s2[c] = 0.f; mean[c] = bn.mean[c]; inv[c] = bn.invstd[c]; }
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
-    const long long b = p / ((long long)W * H);
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  const long long p_end = (npix + stride - 1) / stride * stride;   // all lanes of a warp iterate together (shuffles)
+  for (long long p = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); p < p_end; p += stride) {
+    const bool live = p < npix;
     float da[C0];
 #pragma unroll
     for (int c = 0; c < C0; ++c) da[c] = 0.f;
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ky = tap / 3, kx = tap % 3;
-      const T* src = dz + pad_off(b, y + 1 - ky, x + 1 - kx, H, W, CO);
-      const float* wt = ws + tap * C0 * CO;
+    if (live) {
+      const int x = (int)(p % W);
+      const int y = (int)((p / W) % H);
+      const long long b = p / ((long long)W * H);
 #pragma unroll
-      for (int g = 0; g < CO; g += 8) {
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
         float v[8];
-        load8(src + g, v);
+        load8(dz + pad_off(b, y + 1 - ky, x + 1 - kx, H, W, CO) + g * 8, v);
 #pragma unroll
-        for (int c = 0; c < C0; ++c)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) da[c] = fmaf(v[i], wt[c * CO + g + i], da[c]);
+        for (int c = 0; c < C0; ++c) {
+          const float* wt = ws + (tap * C0 + c) * CO + g * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wt), w1 = *reinterpret_cast<const float4*>(wt + 4);
+          da[c] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, da[c]))));
+          da[c] = fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, da[c]))));
+        }
       }
     }
 #pragma unroll
     for (int c = 0; c < C0; ++c) {
-      const float xh = (x0[p * C0 + c] - mean[c]) * inv[c];
-      s1[c] += da[c];
-      s2[c] += da[c] * xh;
+      float t = da[c];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      if (live && g == 0) {
+        const float xh = (x0[p * C0 + c] - mean[c]) * inv[c];
+        s1[c] += t;
+        s2[c] += t * xh;
+      }
     }
   }
 #pragma unroll
@@ -345,10 +460,10 @@ int launch_first_dgrad_bnstats(const T* dz, const float* w, const float* x0, con
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_dgrad: C0=%d Cout=%d", C0, Cout);
   L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C0, s));
   long long npix = (long long)B * H * W;
-  long long want = (npix + 127) / 128;
+  long long want = (npix + 31) / 32;
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
-  if (C0 == 1) k_first_dgrad_bnstats<T, 1><<<blocks, 128, 0, s>>>(dz, w, x0, bn, B, H, W);
-  else k_first_dgrad_bnstats<T, 3><<<blocks, 128, 0, s>>>(dz, w, x0, bn, B, H, W);
+  if (C0 == 1) k_first_dgrad_bnstats<T, 1><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W);
+  else k_first_dgrad_bnstats<T, 3><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W);
   L3_CHECK_LAUNCH();
   return 0;
 }

@@ -231,45 +231,54 @@ __device__ __forceinline__ void act8(const float (&z)[8], const float (&sc)[8], 
 }
 
 template <typename T>
-__global__ void k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int OH, int OW,
-                          long long total, const float* __restrict__ scale, const float* __restrict__ shift, int pool,
-                          int relu_first) {
+__global__ void __launch_bounds__(256)
+k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int OH, int OW, long long npix,
+          const float* __restrict__ scale, const float* __restrict__ shift, int pool, int relu_first) {
   const int groups = C >> 3;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int g = (int)(idx % groups);
-  long long p = idx / groups;
-  int ox = (int)(p % OW);
-  int oy = (int)((p / OW) % OH);
-  long long b = p / ((long long)OW * OH);
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   float sc[8], sh[8];
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sh);
-  float y[8];
-  if (!pool) {
-    float v[8];
-    load8(z + ((b * H + oy) * W + ox) * C + g * 8, v);
-    act8(v, sc, sh, relu_first, y);
-  } else {
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+    const int ox = (int)(p % OW);
+    const int oy = (int)((p / OW) % OH);
+    const long long b = p / ((long long)OW * OH);
+    float y[8];
+    if (!pool) {
+      float v[8];
+      load8(z + p * C + g * 8, v);
+      act8(v, sc, sh, relu_first, y);
+    } else {
+      const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+      float v0[8], v1[8], v2[8], v3[8], t[8];
+      load8(z00, v0);
+      load8(z00 + C, v1);
+      load8(z00 + (long long)W * C, v2);
+      load8(z00 + (long long)W * C + C, v3);
+      act8(v0, sc, sh, relu_first, y);
+      act8(v1, sc, sh, relu_first, t);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float v[8], t[8];
-      load8(z + ((b * H + 2 * oy + (k >> 1)) * W + 2 * ox + (k & 1)) * C + g * 8, v);
-      act8(v, sc, sh, relu_first, t);
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
+      act8(v2, sc, sh, relu_first, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = k == 0 ? t[i] : fmaxf(y[i], t[i]);
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
+      act8(v3, sc, sh, relu_first, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
     }
+    store8(a + pad_off(b, oy, ox, OH, OW, C) + g * 8, y);
   }
-  store8(a + pad_off(b, oy, ox, OH, OW, C) + g * 8, y);
 }
 template <typename T>
 int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
                    int relu_first, cudaStream_t s) {
-  L3_REQUIRE(C % 8 == 0, "act_fwd: C%%8");
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "act_fwd: C=%d", C);
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
-  long long total = (long long)B * OH * OW * (C / 8);
-  k_act_fwd<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(z, a, H, W, C, OH, OW, total, scale, shift, pool,
-                                                               relu_first);
+  long long npix = (long long)B * OH * OW;
+  int lanes = kThreads / (C / 8);
+  long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  k_act_fwd<T><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, pool, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -452,8 +461,10 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
 template int launch_bwd_stats<float>(const float*, const float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
 template int launch_bwd_stats<bf16>(const bf16*, const bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
 
+// folded BN-backward coefficients (written by k_bn_bwd_finalize into bn.c1 / bn.c2):
+//   dz = scale*(dy - mean(dy) - xhat*mean(dy*xhat)) = scale*dy + c1*xin + c2,   xin = z (or relu(z) if relu_first)
 struct BnBwdCoef {
-  float sc[8], mean[8], inv[8], c1[8], c2[8];
+  float sc[8], cb[8], cc[8];
 };
 template <typename T>
 __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8], const float (&d)[8], const BnBwdCoef& k,
@@ -462,89 +473,86 @@ __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
-    float xh = (xin - k.mean[i]) * k.inv[i];
-    float r = k.sc[i] * (d[i] - k.c1[i] - xh * k.c2[i]);
+    float r = fmaf(k.sc[i], d[i], fmaf(k.cb[i], xin, k.cc[i]));
     if (relu_first && !(v[i] > 0.f)) r = 0.f;
     o[i] = r;
   }
   store8(dst, o);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256, 2)
 k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
-            long long total, BnRef bn, int pool, int relu_first) {
+            long long npix, BnRef bn, int relu_first) {
   const int groups = C >> 3;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = (int)(idx % groups);
-  const long long p = idx / groups;
-  const int ox = (int)(p % OW);
-  const int oy = (int)((p / OW) % OH);
-  const long long b = p / ((long long)OW * OH);
-  float sf[8], g8[8];
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  float sf[8];
   BnBwdCoef k;
   load8(bn.scale + g * 8, k.sc);
   load8(bn.shift + g * 8, sf);
-  load8(bn.mean + g * 8, k.mean);
-  load8(bn.invstd + g * 8, k.inv);
-  load8(bn.c1 + g * 8, k.c1);
-  load8(bn.c2 + g * 8, k.c2);
-  load8(da + p * C + g * 8, g8);
+  load8(bn.c1 + g * 8, k.cb);
+  load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (!pool) {
-    float v[8], y[8], d[8];
-    load8(z + p * C + g * 8, v);
-    act8(v, k.sc, sf, relu_first, y);
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
+    const int ox = (int)(p % OW);
+    const int oy = (int)((p / OW) % OH);
+    const long long b = p / ((long long)OW * OH);
+    float g8[8];
+    load8(da + p * C + g * 8, g8);
+    if (!POOL) {
+      float v[8], y[8], d[8];
+      load8(z + p * C + g * 8, v);
+      act8(v, k.sc, sf, relu_first, y);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
-    bwd_emit<T>(dz + pad_off(b, oy, ox, H, W, C) + g * 8, v, d, k, relu_first);
-    return;
-  }
-  float v[4][8], m[8];
-  int arg[8];
-  {
-    const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
-    load8(z00, v[0]);
-    load8(z00 + C, v[1]);
-    load8(z00 + (long long)W * C, v[2]);
-    load8(z00 + (long long)W * C + C, v[3]);
-    float y[8];
-    act8(v[0], k.sc, sf, relu_first, m);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) arg[i] = 0;
-#pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      act8(v[q], k.sc, sf, relu_first, y);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+      for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
+      bwd_emit<T>(dz + pad_off(b, oy, ox, H, W, C) + g * 8, v, d, k, relu_first);
+      continue;
     }
-  }
+    float v[4][8], m[8];
+    int arg[8];
+    {
+      const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+      load8(z00, v[0]);
+      load8(z00 + C, v[1]);
+      load8(z00 + (long long)W * C, v[2]);
+      load8(z00 + (long long)W * C + C, v[3]);
+      float y[8];
+      act8(v[0], k.sc, sf, relu_first, m);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float d[8];
+      for (int i = 0; i < 8; ++i) arg[i] = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = (arg[i] == q && (relu_first || m[i] > 0.f)) ? g8[i] : 0.f;
-    bwd_emit<T>(dz + pad_off(b, 2 * oy + (q >> 1), 2 * ox + (q & 1), H, W, C) + g * 8, v[q], d, k, relu_first);
-  }
-  // rows / columns dropped by valid pooling of odd sizes: dy = 0
-  const bool last_x = (W & 1) && ox == OW - 1, last_y = (H & 1) && oy == OH - 1;
-  if (last_x) {
+      for (int q = 1; q < 4; ++q) {
+        act8(v[q], k.sc, sf, relu_first, y);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      load8(z + ((b * H + 2 * oy + r) * W + W - 1) * C + g * 8, v[0]);
-      bwd_emit<T>(dz + pad_off(b, 2 * oy + r, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+        for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+      }
     }
-  }
-  if (last_y) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      load8(z + ((b * H + H - 1) * W + 2 * ox + r) * C + g * 8, v[0]);
-      bwd_emit<T>(dz + pad_off(b, H - 1, 2 * ox + r, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+    for (int q = 0; q < 4; ++q) {
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = (arg[i] == q && (relu_first || m[i] > 0.f)) ? g8[i] : 0.f;
+      bwd_emit<T>(dz + pad_off(b, 2 * oy + (q >> 1), 2 * ox + (q & 1), H, W, C) + g * 8, v[q], d, k, relu_first);
     }
+    // rows / columns dropped by valid pooling of odd sizes: dy = 0
+    const bool last_x = (W & 1) && ox == OW - 1, last_y = (H & 1) && oy == OH - 1;
     if (last_x) {
-      load8(z + ((b * H + H - 1) * W + W - 1) * C + g * 8, v[0]);
-      bwd_emit<T>(dz + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        load8(z + ((b * H + 2 * oy + r) * W + W - 1) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, 2 * oy + r, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+      }
+    }
+    if (last_y) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        load8(z + ((b * H + H - 1) * W + 2 * ox + r) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, H - 1, 2 * ox + r, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+      }
+      if (last_x) {
+        load8(z + ((b * H + H - 1) * W + W - 1) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
+      }
     }
   }
 }
@@ -552,26 +560,33 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
                      int relu_first, cudaStream_t s) {
-  L3_REQUIRE(C % 8 == 0, "bwd_apply: C=%d", C);
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "bwd_apply: C=%d", C);
   if (launch_zero_halo<T>(dz, B, H, W, C, s)) return -1;
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
-  long long total = (long long)B * OH * OW * (C / 8);
-  k_bwd_apply<T><<<ceil_div(total, kThreads), kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, total, bn, pool, relu_first);
+  long long npix = (long long)B * OH * OW;
+  int lanes = kThreads / (C / 8);
+  long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  if (pool) k_bwd_apply<T, true><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
 template int launch_bwd_apply<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
 template int launch_bwd_apply<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
 
-// BN backward finalize: dgamma, dbeta, c1 = mean(dy), c2 = mean(dy*xhat)
+// BN backward finalize: dgamma, dbeta and the folded coefficients of dz = scale*dy + c1*xin + c2
+//   c1 = -scale*invstd*mean(dy*xhat) ; c2 = -scale*mean(dy) - c1*mean
 __global__ void k_bn_bwd_finalize(BnRef bn, double count) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= bn.C) return;
   double s1 = bn.sum[c], s2 = bn.sum[bn.C + c];
   bn.d_beta[c] = (float)s1;
   bn.d_gamma[c] = (float)s2;
-  bn.c1[c] = (float)(s1 / count);
-  bn.c2[c] = (float)(s2 / count);
+  const double sc = (double)bn.scale[c];
+  const double cb = -sc * (double)bn.invstd[c] * (s2 / count);
+  bn.c1[c] = (float)cb;
+  bn.c2[c] = (float)(-sc * (s1 / count) - cb * (double)bn.mean[c]);
 }
 int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s) {
   k_bn_bwd_finalize<<<ceil_div(bn.C, 128), 128, 0, s>>>(bn, (double)count);
@@ -580,7 +595,7 @@ int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s) {
 }
 
 // BN backward apply (in place on the padded dy buffer; z unpadded):
-//   dz = scale*(dy - c1 - xhat*c2)  [ * (z>0) and xhat from relu(z) when relu_first ]
+//   dz = scale*dy + c1*xin + c2 (folded coefficients)  [ * (z>0) and xin = relu(z) when relu_first ]
 template <typename T>
 __global__ void k_bn_bwd_apply(T* __restrict__ dy, const T* __restrict__ z, long long total, int H, int W, int C,
                                BnRef bn, int relu_first) {
@@ -593,19 +608,16 @@ __global__ void k_bn_bwd_apply(T* __restrict__ dy, const T* __restrict__ z, long
   const int yy = (int)((p / W) % H);
   const long long b = p / ((long long)W * H);
   T* dptr = dy + pad_off(b, yy, xx, H, W, C) + g * 8;
-  float sc[8], mean[8], inv[8], c1[8], c2[8], d[8], v[8], o[8];
+  float sc[8], cb[8], cc[8], d[8], v[8], o[8];
   load8(bn.scale + g * 8, sc);
-  load8(bn.mean + g * 8, mean);
-  load8(bn.invstd + g * 8, inv);
-  load8(bn.c1 + g * 8, c1);
-  load8(bn.c2 + g * 8, c2);
+  load8(bn.c1 + g * 8, cb);
+  load8(bn.c2 + g * 8, cc);
   load8(dptr, d);
   load8(z + p * C + g * 8, v);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float xin = relu_first ? fmaxf(v[i], 0.f) : v[i];
-    float xh = (xin - mean[i]) * inv[i];
-    float r = sc[i] * (d[i] - c1[i] - xh * c2[i]);
+    float r = fmaf(sc[i], d[i], fmaf(cb[i], xin, cc[i]));
     if (relu_first && !(v[i] > 0.f)) r = 0.f;
     o[i] = r;
   }

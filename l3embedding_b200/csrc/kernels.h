@@ -86,6 +86,9 @@ int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, i
 // first-layer (Cin = 1|3, Cout = 64) backward: weight/bias gradient, and the input-BN backward sums computed
 // straight from dz without materialising the data gradient (bn.sum <- sum(da), sum(da*xhat))
 template <typename T>
+int launch_first_conv(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int C0, int Cout,
+                      cudaStream_t s);
+template <typename T>
 int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int C0, int Cout,
                        cudaStream_t s);
 template <typename T>
