@@ -165,6 +165,7 @@ struct Tower {
   void* xin;    // padded T
   ConvLayer L[8];
   int* argmax;  // (B,512)
+  float* d1;    // 9*64 floats + 1 int flag: first-layer "ones" weight gradient for the input-BN backward
   int concat_off;
 };
 
@@ -307,6 +308,7 @@ static long long carve(l3_ctx* c) {
       H = OH; W = OW;
     }
     tw.argmax = (int*)bp.take(4 * B * 512);
+    tw.d1 = (float*)bp.take(4 * (9 * 64 + 4));
   }
   c->g0 = training ? bp.take(es * g0_max) : nullptr;
   c->g1 = training ? bp.take(es * g1_max) : nullptr;
@@ -364,12 +366,17 @@ static void bind_params(l3_ctx* c) {
 static const float kBnMomentum = 0.99f, kBnEps = 1e-3f;  // keras BatchNormalization defaults
 static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm feeds the Bessel-corrected variance
 
+// want_stats: training-mode BN statistics of the output; *stats_done tells the caller they were fused
 template <typename T>
-static int conv_forward(l3_ctx* c, ConvLayer& L, int B) {
+static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done) {
   ProfScope ps(c, PROF_CONV_FWD);
+  *stats_done = false;
   if (L.tc && c->use_tc) {
     if (launch_pack_weights_tc(L.w, L.w_pk, L.Cin, L.Cout, 0, c->stream)) return -1;
-    return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
+    const bool fuse = want_stats && conv_tc_fuses_stats();
+    *stats_done = fuse;
+    return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
+                             fuse ? L.bn.sum : nullptr, L.relu_first, c->stream);
   }
   if (L.Cin <= 3 && L.Cout == 64)
     return launch_first_conv<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
@@ -408,10 +415,11 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
   cudaStream_t s = c->stream;
   for (int l = 0; l < 8; ++l) {
     ConvLayer& L = tw.L[l];
-    if (conv_forward<T>(c, L, B)) return -1;
+    bool stats_done = false;
+    if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done)) return -1;
     if (l == 7 && embed_only) return 0;  // raw conv4b output incl. bias, before BN/ReLU (audio_model.py:482)
     long long rows = (long long)B * L.H * L.W;
-    if (training && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
+    if (training && !stats_done && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
     if (launch_bn_finalize(L.bn, rows, training, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
     if (l < 7) {
       if (launch_act_fwd<T>((const T*)L.z, (T*)L.a, B, L.H, L.W, L.Cout, L.bn.scale, L.bn.shift, L.pool, L.relu_first, s))
@@ -455,7 +463,9 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
                                L.Cout, s))
           return -1;
       } else if (l == 0) {
-        if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+        if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
+                                  L.Cin, L.Cout, s))
+          return -1;
       } else {
         if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
       }
@@ -464,7 +474,9 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       if (tw.has_bn0) {
         // input BN: d_gamma / d_beta need only sum(da), sum(da*xhat) -- computed without storing da
         ProfScope ps(c, PROF_CONV_DGRAD);
-        if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+        int* fallback = reinterpret_cast<int*>(tw.d1 + 9 * 64);
+        if (launch_bn0_from_dw(L.w, L.dw, tw.d1, tw.bn0, L.Cin, fallback, s)) return -1;
+        if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, fallback, s)) return -1;
         if (launch_bn_bwd_finalize(tw.bn0, rows, s)) return -1;
       }
       break;
@@ -474,7 +486,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       ProfScope ps(c, PROF_CONV_DGRAD);
       if (L.tc && c->use_tc) {
         if (launch_pack_weights_tc(L.w, L.wt_pk, L.Cin, L.Cout, 1, s)) return -1;
-        if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+        if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
       } else {
         if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
         if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
@@ -857,7 +869,7 @@ int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out,
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0 && scratch, "tc conv: bf16, C%%64, scratch");
     L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
     if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 0, s)) return -1;
-    return launch_conv3x3_tc((const bf16*)in, (const bf16*)scratch, bias, (bf16*)out, B, H, W, Cin, Cout, s);
+    return launch_conv3x3_tc((const bf16*)in, (const bf16*)scratch, bias, (bf16*)out, B, H, W, Cin, Cout, nullptr, 0, s);
   }
   if (dtype == L3_DTYPE_BF16) return launch_conv3x3_simt<bf16>((const bf16*)in, w, bias, (bf16*)out, B, H, W, Cin, Cout, s);
   return launch_conv3x3_simt<float>((const float*)in, w, bias, (float*)out, B, H, W, Cin, Cout, s);
@@ -870,7 +882,7 @@ int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0, "tc dgrad: bf16, C%%64");
     L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
     if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 1, s)) return -1;
-    return launch_conv3x3_tc((const bf16*)dz, (const bf16*)scratch, nullptr, (bf16*)da, B, H, W, Cout, Cin, s);
+    return launch_conv3x3_tc((const bf16*)dz, (const bf16*)scratch, nullptr, (bf16*)da, B, H, W, Cout, Cin, nullptr, 0, s);
   }
   if (launch_flip_transpose(w, (float*)scratch, Cin, Cout, s)) return -1;
   if (dtype == L3_DTYPE_BF16)

@@ -306,17 +306,21 @@ template int launch_first_conv<float>(const float*, const float*, const float*, 
 template int launch_first_conv<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
 
 // dw[tap][c][co] += sum_px a[px+tap][c] * dz[px][co] ; db[co] += sum_px dz[px][co]
-// block = 64 output channels x 4 pixel lanes (contiguous x segments, sliding input window: 3*C0 new taps per pixel,
-// all warp-broadcast loads); every thread keeps its 9*C0 partial sums in registers.
+// d1[tap][co]    += sum_px inside(px+tap) * dz[px][co]      (weight gradient w.r.t. an all-ones input plane; used by
+//                                                            k_bn0_from_dw for the input-BN gradients)
+// block = 64 output channels x 4 pixel lanes (contiguous x segments); 4 pixels per iteration with all loads issued
+// first (input taps are warp-broadcast loads); every thread keeps its 9*C0 (+9) partial sums in registers.
 template <typename T, int C0>
 __global__ void __launch_bounds__(256)
 k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
-              int B, int H, int W, int rows_per_block) {
+              float* __restrict__ d1, int B, int H, int W, int rows_per_block) {
   constexpr int CO = 64, K = 9 * C0;
   const int co = threadIdx.x & 63, lane = threadIdx.x >> 6;
-  float acc[K];
+  float acc[K], ones[9];
 #pragma unroll
   for (int i = 0; i < K; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) ones[i] = 0.f;
   float bsum = 0.f;
   const long long n_rows = (long long)B * H;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -325,66 +329,118 @@ k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restri
   const int seg = (W + 3) / 4;
   const int x0 = lane * seg, x1 = min(W, x0 + seg);
   for (long long r = r0; r < r1; ++r) {
-    if (x0 >= x1) break;
     const long long b = r / H;
     const int y = (int)(r - b * H);
     const T* dzrow = dz + pad_off(b, y, 0, H, W, CO) + co;
-    const T* arow = a + pad_off(b, y - 1, -1, H, W, C0);   // top-left tap of pixel x = 0
-    float win[3][3][C0];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 1; kx < 3; ++kx)
-#pragma unroll
-        for (int c = 0; c < C0; ++c) win[ky][kx][c] = to_f(arow[((long long)ky * Wp + x0 + kx - 1) * C0 + c]);
-    for (int x = x0; x < x1; ++x) {
+    const T* arow = a + pad_off(b, y - 1, -1, H, W, C0);   // padded row y (top tap), padded column 0
+    const float fy0 = y > 0 ? 1.f : 0.f, fy2 = y < H - 1 ? 1.f : 0.f;
+    for (int x = x0; x < x1; x += 4) {
+      float cols[3][6][C0], g[4];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int c = 0; c < C0; ++c) {
-          win[ky][0][c] = win[ky][1][c];
-          win[ky][1][c] = win[ky][2][c];
-          win[ky][2][c] = to_f(arow[((long long)ky * Wp + x + 2) * C0 + c]);
+        for (int j = 0; j < 6; ++j) {
+          const int xc = min(x + j, W + 1);
+#pragma unroll
+          for (int c = 0; c < C0; ++c) cols[ky][j][c] = to_f(arow[((long long)ky * Wp + xc) * C0 + c]);
         }
-      const float g = to_f(dzrow[(long long)x * CO]);
-      bsum += g;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int i = 0; i < 4; ++i) g[i] = (x + i < x1) ? to_f(dzrow[(long long)(x + i) * CO]) : 0.f;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
+      for (int i = 0; i < 4; ++i) {
+        bsum += g[i];
+        const float gx0 = (x + i > 0) ? g[i] : 0.f, gx2 = (x + i < W - 1) ? g[i] : 0.f;
+        ones[0] = fmaf(fy0, gx0, ones[0]); ones[1] = fmaf(fy0, g[i], ones[1]); ones[2] = fmaf(fy0, gx2, ones[2]);
+        ones[3] += gx0;                    ones[4] += g[i];                    ones[5] += gx2;
+        ones[6] = fmaf(fy2, gx0, ones[6]); ones[7] = fmaf(fy2, g[i], ones[7]); ones[8] = fmaf(fy2, gx2, ones[8]);
 #pragma unroll
-          for (int c = 0; c < C0; ++c)
-            acc[(ky * 3 + kx) * C0 + c] = fmaf(win[ky][kx][c], g, acc[(ky * 3 + kx) * C0 + c]);
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < C0; ++c)
+              acc[(ky * 3 + kx) * C0 + c] = fmaf(cols[ky][i + kx][c], g[i], acc[(ky * 3 + kx) * C0 + c]);
+      }
     }
   }
-  __shared__ float red[4][K + 1][CO];
+  __shared__ float red[4][K + 10][CO];
 #pragma unroll
   for (int i = 0; i < K; ++i) red[lane][i][co] = acc[i];
-  red[lane][K][co] = bsum;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) red[lane][K + i][co] = ones[i];
+  red[lane][K + 9][co] = bsum;
   __syncthreads();
-  for (int i = threadIdx.x; i < (K + 1) * CO; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (K + 10) * CO; i += blockDim.x) {
     const int k = i / CO, c = i % CO;
     const float v = red[0][k][c] + red[1][k][c] + red[2][k][c] + red[3][k][c];
     if (k < K) atomicAdd(&dw[k * CO + c], v);
+    else if (k < K + 9) { if (d1) atomicAdd(&d1[(k - K) * CO + c], v); }
     else if (db) atomicAdd(&db[c], v);
   }
 }
 
 template <typename T>
-int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int C0, int Cout,
+int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0, int Cout,
                        cudaStream_t s) {
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_wgrad: C0=%d Cout=%d", C0, Cout);
+  if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
   long long n_rows = (long long)B * H;
   int rpb = (int)((n_rows + 148 * 8 - 1) / (148 * 8));
   if (rpb < 1) rpb = 1;
   int blocks = (int)((n_rows + rpb - 1) / rpb);
-  if (C0 == 1) k_first_wgrad<T, 1><<<blocks, 256, 0, s>>>(a, dz, dw, db, B, H, W, rpb);
-  else k_first_wgrad<T, 3><<<blocks, 256, 0, s>>>(a, dz, dw, db, B, H, W, rpb);
+  if (C0 == 1) k_first_wgrad<T, 1><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
+  else k_first_wgrad<T, 3><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_first_wgrad<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_first_wgrad<float>(const float*, const float*, float*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, float*, int, int, int, int, int, cudaStream_t);
+
+// Input-BN gradients from the first layer's weight gradient (no pass over the image at all).  With
+// da = dgrad(dz) and xin = gamma*xhat + beta the zero-padded conv input:
+//   sum_p da[p,c]          = sum_{tap,co} w[tap][c][co] * d1[tap][co]          (d1 = weight gradient of an all-ones plane)
+//   sum_p da[p,c]*xin[p,c] = sum_{tap,co} w[tap][c][co] * dw[tap][c][co]
+//   sum_p da*xhat          = (sum da*xin - beta * sum da) / gamma
+// Writes bn.sum = {sum da, sum da*xhat}.  A channel with |gamma| ~ 0 cannot be recovered this way: *fallback is set
+// and k_first_dgrad_bnstats (which computes the sums directly) runs instead.
+__global__ void k_bn0_from_dw(const float* __restrict__ w, const float* __restrict__ dw, const float* __restrict__ d1,
+                              BnRef bn, int C0, int* __restrict__ fallback) {
+  __shared__ float r1[3][128], r2[3][128];
+  const int t = threadIdx.x;  // 128 threads
+  for (int c = 0; c < C0; ++c) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = t; i < 9 * 64; i += 128) {
+      const int tap = i >> 6, co = i & 63;
+      const float wv = w[(tap * C0 + c) * 64 + co];
+      s1 = fmaf(wv, d1[i], s1);
+      s2 = fmaf(wv, dw[(tap * C0 + c) * 64 + co], s2);
+    }
+    r1[c][t] = s1;
+    r2[c][t] = s2;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int fb = 0;
+    for (int c = 0; c < C0; ++c) {
+      double s1 = 0, s2 = 0;
+      for (int i = 0; i < 128; ++i) { s1 += r1[c][i]; s2 += r2[c][i]; }
+      const double gm = bn.gamma[c];
+      if (fabs(gm) < 1e-12) fb = 1;
+      bn.sum[c] = s1;
+      bn.sum[C0 + c] = fabs(gm) < 1e-12 ? 0.0 : (s2 - (double)bn.beta[c] * s1) / gm;
+    }
+    if (fb)
+      for (int c = 0; c < 2 * C0; ++c) bn.sum[c] = 0.0;   // the fallback kernel accumulates from zero
+    *fallback = fb;
+  }
+}
+int launch_bn0_from_dw(const float* w, const float* dw, const float* d1, const BnRef& bn, int C0, int* fallback,
+                       cudaStream_t s) {
+  L3_REQUIRE(C0 >= 1 && C0 <= 3, "bn0_from_dw: C0=%d", C0);
+  k_bn0_from_dw<<<1, 128, 0, s>>>(w, dw, d1, bn, C0, fallback);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
 
 // Input-BN backward without materialising the data gradient.  8 threads per input pixel (8 of the 64 dz channels
 // each, so a warp reads 4 pixels x 128 B fully coalesced) compute
@@ -395,8 +451,9 @@ template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, 
 template <typename T, int C0>
 __global__ void __launch_bounds__(256)
 k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ x0, BnRef bn,
-                      int B, int H, int W) {
+                      int B, int H, int W, const int* __restrict__ only_if) {
   constexpr int CO = 64;
+  if (only_if != nullptr && *only_if == 0) return;   // the algebraic path (k_bn0_from_dw) already produced bn.sum
   __shared__ __align__(16) float ws[9 * C0 * CO];
   __shared__ float red[2 * C0];
   for (int i = threadIdx.x; i < 9 * C0 * CO; i += blockDim.x) ws[i] = w[i];
@@ -456,18 +513,18 @@ k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, con
 
 template <typename T>
 int launch_first_dgrad_bnstats(const T* dz, const float* w, const float* x0, const BnRef& bn, int B, int H, int W, int C0,
-                               int Cout, cudaStream_t s) {
+                               int Cout, const int* only_if, cudaStream_t s) {
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_dgrad: C0=%d Cout=%d", C0, Cout);
-  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C0, s));
+  if (!only_if) L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C0, s));
   long long npix = (long long)B * H * W;
   long long want = (npix + 31) / 32;
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
-  if (C0 == 1) k_first_dgrad_bnstats<T, 1><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W);
-  else k_first_dgrad_bnstats<T, 3><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W);
+  if (C0 == 1) k_first_dgrad_bnstats<T, 1><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W, only_if);
+  else k_first_dgrad_bnstats<T, 3><<<blocks, 256, 0, s>>>(dz, w, x0, bn, B, H, W, only_if);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_first_dgrad_bnstats<float>(const float*, const float*, const float*, const BnRef&, int, int, int, int, int, cudaStream_t);
-template int launch_first_dgrad_bnstats<bf16>(const bf16*, const float*, const float*, const BnRef&, int, int, int, int, int, cudaStream_t);
+template int launch_first_dgrad_bnstats<float>(const float*, const float*, const float*, const BnRef&, int, int, int, int, int, const int*, cudaStream_t);
+template int launch_first_dgrad_bnstats<bf16>(const bf16*, const float*, const float*, const BnRef&, int, int, int, int, int, const int*, cudaStream_t);
 
 }  // namespace l3

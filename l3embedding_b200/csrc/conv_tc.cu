@@ -374,7 +374,7 @@ template <int BN, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-              int num_m_tiles, int num_n_tiles, int base_offset_mode) {
+              int num_m_tiles, int num_n_tiles, int base_offset_mode, double* __restrict__ stats, int relu_stats) {
   using Cfg = Conv2Cfg<BN, MT>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -474,14 +474,30 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue: TMEM -> regs -> (+bias) -> bf16 -> HBM, plus per-channel sum / sum-of-squares of the stored
+    // values (BatchNorm batch statistics) reduced across the 32 rows of a warp by a transposing butterfly =====
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     const long long HWp = (long long)(H + 2) * Wp;
+    float st_sum[BN / 32], st_sq[BN / 32];   // lane i owns column c0 + i of every 32-column chunk
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
+    int st_n0 = -1;
+    auto flush_stats = [&]() {
+      if (stats != nullptr && st_n0 >= 0) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          atomicAdd(&stats[st_n0 + i * 32 + lane], (double)st_sum[i]);
+          atomicAdd(&stats[Cout + st_n0 + i * 32 + lane], (double)st_sq[i]);
+          st_sum[i] = st_sq[i] = 0.f;
+        }
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long mbase = (long long)(tile / num_n_tiles) * (MT * kBM) + q * 32 + lane;
       const int n0 = (tile % num_n_tiles) * BN;
+      if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -497,19 +513,53 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int c0 = ch * 32;
           uint32_t v[32];
           tmem_ld32(t_row + c0, v);
           tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float f0 = __uint_as_float(v[2 * j]) + (bias ? __ldg(bias + n0 + c0 + 2 * j) : 0.f);
+            const float f1 = __uint_as_float(v[2 * j + 1]) + (bias ? __ldg(bias + n0 + c0 + 2 * j + 1) : 0.f);
+            pk[j] = pack_bf16x2(f0, f1);
+          }
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float f[8];
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (stats != nullptr) {
+            // statistics of the values as stored (bf16-rounded), zero for halo / out-of-range rows
+            float a[32], b2[32];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + n0 + c0 + j + i) : 0.f);
-              store8(optr + c0 + j, f);
+            for (int j = 0; j < 16; ++j) {
+              float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+              float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+              if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              a[2 * j] = x0; a[2 * j + 1] = x1;
+              b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
             }
+            // transposing butterfly: after the 5 steps lane i holds the sum over the warp's 32 rows of column i
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+              const int half = 16 >> step;              // values kept per lane after this step
+              const bool upper = (lane >> (4 - step)) & 1;
+#pragma unroll
+              for (int j = 0; j < half; ++j) {
+                // lanes with the bit set keep the upper half of the columns and send the lower half (and vice versa)
+                const float send_a = upper ? a[j] : a[j + half];
+                const float keep_a = upper ? a[j + half] : a[j];
+                const float send_b = upper ? b2[j] : b2[j + half];
+                const float keep_b = upper ? b2[j + half] : b2[j];
+                a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
+                b2[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
+              }
+            }
+            st_sum[ch] += a[0];
+            st_sq[ch] += b2[0];
           }
         }
       }
@@ -519,6 +569,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -530,7 +581,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 template <int BN, int MT>
 static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
-                        int Cout, long long Mp, int base_offset_mode, cudaStream_t s) {
+                        int Cout, long long Mp, int base_offset_mode, double* stats, int relu_stats, cudaStream_t s) {
   using Cfg = Conv2Cfg<BN, MT>;
   static bool configured = false;
   if (!configured) {
@@ -543,8 +594,9 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
   int num_m = (int)((Mp + MT * kBM - 1) / (MT * kBM)), num_n = Cout / BN;
   long long tiles = (long long)num_m * num_n;
   int grid = (int)(tiles < 148 ? tiles : 148);
+  if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
   k_conv3x3_tc2<BN, MT><<<grid, kConvThreads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n,
-                                                             base_offset_mode);
+                                                             base_offset_mode, stats, relu_stats);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -561,8 +613,10 @@ static int conv_variant() {
   return v;
 }
 
+int conv_tc_fuses_stats() { return conv_variant() >= 2; }
+
 int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
-                      int Cout, cudaStream_t s) {
+                      int Cout, double* stats, int relu_stats, cudaStream_t s) {
   L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
@@ -570,10 +624,11 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const int variant = conv_variant();
   if (variant >= 2) {
     const int bo = variant == 3 ? 1 : 0;
-    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
-    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
-    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, s);
+    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
+    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
+    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
   }
+  L3_REQUIRE(stats == nullptr, "conv_tc variant 1 has no fused statistics");
   CUtensorMap tmA, tmB;
   if (make_tmap(&tmA, in, Cin, Mp, kBM)) return -1;
   if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;

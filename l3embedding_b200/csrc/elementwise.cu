@@ -385,10 +385,10 @@ template int launch_gmaxpool_bwd<bf16>(const float*, int, const int*, const bf16
 // max-pool routes to the first maximum in window order (0,0),(0,1),(1,0),(1,1); pixels dropped by 'valid' pooling of
 // odd sizes have dy = 0 (they still receive the BN mean terms).  da: unpadded (B,OH,OW,C); z: unpadded (B,H,W,C).
 // --------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256, 2)
 k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int C, int OH, int OW, long long npix,
-            BnRef bn, int pool, int relu_first) {
+            BnRef bn, int relu_first) {
   extern __shared__ float sh[];  // 2*C
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
@@ -404,7 +404,7 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
     float g8[8], zs[8], m[8];
     load8(da + p * C + g * 8, g8);
-    if (!pool) {
+    if (!POOL) {
       load8(z + p * C + g * 8, zs);
       act8(zs, sc, sf, relu_first, m);
     } else {
@@ -454,7 +454,8 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
   int lanes = kThreads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  k_bwd_stats<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, pool, relu_first);
+  if (pool) k_bwd_stats<T, true><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
+  else k_bwd_stats<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }

@@ -88,12 +88,17 @@ int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, i
 template <typename T>
 int launch_first_conv(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int C0, int Cout,
                       cudaStream_t s);
+// d1 (optional, 9*64 floats): weight gradient w.r.t. an all-ones input plane, consumed by launch_bn0_from_dw
 template <typename T>
-int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int C0, int Cout,
+int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0, int Cout,
                        cudaStream_t s);
+// input-BN gradients (bn.sum = {sum da, sum da*xhat}) from dw and d1 alone; *fallback = 1 if some |gamma| ~ 0
+int launch_bn0_from_dw(const float* w, const float* dw, const float* d1, const BnRef& bn, int C0, int* fallback,
+                       cudaStream_t s);
+// direct computation of the same sums from dz; with only_if != null the kernel is a no-op unless *only_if != 0
 template <typename T>
 int launch_first_dgrad_bnstats(const T* dz, const float* w, const float* x0, const BnRef& bn, int B, int H, int W, int C0,
-                               int Cout, cudaStream_t s);
+                               int Cout, const int* only_if, cudaStream_t s);
 // w_t[(ky*3+kx)*Cout*Cin + co*Cin + ci] = w[((2-ky)*3+(2-kx))*Cin*Cout + ci*Cout + co]  (for dgrad-as-conv)
 int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStream_t s);
 
@@ -116,14 +121,17 @@ int launch_head_bwd(const HeadRef& h, int B, cudaStream_t s);
 // ---- tcgen05 bf16 implicit-GEMM convolutions (conv_tc.cu) ---------------------------------------
 // 1 when the running device is sm_100 and the driver exposes cuTensorMapEncodeTiled.
 int conv_tc_supported();
+int conv_tc_fuses_stats();   // the active forward variant computes BN statistics in its epilogue
 // Weight pre-pack: fp32 HWIO (3,3,Cin,Cout) -> bf16 K-major rows [(tap*Cin/64 + kc)*Cout + co][64 ci] (one TMA box
 // row = 128 B).  flip_transpose=1 packs the dgrad operand: taps flipped and Cin/Cout swapped, i.e. the result is the
 // forward pack of a conv with Cin' = Cout, Cout' = Cin.
 int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int flip_transpose, cudaStream_t s);
 // Forward / dgrad conv on tensor cores. in: zero-haloed padded bf16 (B,H+2,W+2,Cin), Cin%64==0, Cout%64==0;
-// out: unpadded bf16 (B,H,W,Cout); bias may be null.
+// out: unpadded bf16 (B,H,W,Cout); bias may be null.  stats (optional): double[2*Cout] receives the per-channel sum and
+// sum of squares of the stored output (of relu(output) if relu_stats) -- the BatchNorm batch statistics, fused into
+// the epilogue so the tensor is not read again.
 int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
-                      int Cout, cudaStream_t s);
+                      int Cout, double* stats, int relu_stats, cudaStream_t s);
 // Weight gradient on tensor cores: a padded (B,H+2,W+2,Cin), dz padded (B,H+2,W+2,Cout) with zero halos;
 // dw (3,3,Cin,Cout) fp32 and db (Cout) are accumulated into (pre-zeroed by the caller).
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,

@@ -191,6 +191,25 @@ def test_training_step_gradients_f32(model_type):
         assert np.abs(w_after[name] - w_ref[name].numpy()).max() <= 2e-6, name
 
 
+def test_input_bn_gradient_fallback_when_gamma_is_zero():
+    """The input-BN gradients normally come from the first layer's weight gradient divided by gamma; a zero gamma
+    must take the direct path and still match the oracle."""
+    mt, B = "cnn_L3_kapredbinputbn", 2
+    w_np = O.init_weights(mt, seed=9, randomize_bn=True)
+    w_np["audio/bn0/gamma"][:] = 0.0
+    w_np["vision/bn0/gamma"][1] = 0.0
+    video, audio, label = O.synthetic_batch(B, seed=404)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
+    grads, _, _ = O.compute_grads(vf, af, torch.from_numpy(label), w, mt, F64)
+    eng = _engine(mt, B, "f32", training=True, weights=w_np)
+    eng.forward_backward(video, audio, label)
+    got = eng.get_grads()
+    for name in ("audio/bn0/gamma", "audio/bn0/beta", "vision/bn0/gamma", "vision/bn0/beta"):
+        ref = grads[name].numpy()
+        assert rel_l2(got[name], ref) <= 1e-2 or np.abs(got[name] - ref).max() <= 1e-4, (name, got[name], ref)
+
+
 def test_train_steps_from_host_decrease_loss():
     """BASELINE config 1 on the device path: cnn_L3_orig, batch 4, 8 steps from host buffers."""
     mt = "cnn_L3_orig"
