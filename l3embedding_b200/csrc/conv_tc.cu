@@ -62,6 +62,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// descriptor passed as (lo, hi) 32-bit halves: only `lo` (start address | LBO) changes between MMAs, `hi` is constant
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %6, 0;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// high half of a 128B-swizzle descriptor: SBO | version 1 | SWIZZLE_128B ; low half: start address | LBO
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+// one lane of the (converged) warp, the same one every time
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
@@ -370,11 +390,13 @@ struct Conv2Cfg {
   static const int kTmemCols = 2 * MT * BN;               // 512 for (64,4), (128,2), (256,1)
 };
 
+static const int kConv2Threads = 64 + 256;   // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+
 template <int BN, int MT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConv2Threads, 1)
 k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-              int num_m_tiles, int num_n_tiles, int base_offset_mode, double* __restrict__ stats, int relu_stats) {
+              int num_m_tiles, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
   using Cfg = Conv2Cfg<BN, MT>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -387,7 +409,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -433,63 +455,75 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-        uint32_t first = 1;
-        for (int it = 0; it < 3 * KC; ++it) {
-          mbar_wait(&a_full[as], aph);
-          const uint32_t sa = smem_addr(smem + as * Cfg::kAStage);
-          for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint64_t b_desc = make_desc(smem_addr(smem_b + bs * Cfg::kBStage), 16, 1024);
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so descriptors live in uniform
+    // registers; one elected lane issues tcgen05.mma / tcgen05.commit =====
+    constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
+    constexpr uint32_t hi = desc_hi(1024);
+    const bool leader = elect_one();
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t sa_base = smem_addr(smem), sb_base = smem_addr(smem_b);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+      uint32_t first = 1;
+      for (int it = 0; it < 3 * KC; ++it) {
+        mbar_wait(&a_full[as], aph);
+        const uint32_t a_lo0 = desc_lo(sa_base + as * Cfg::kAStage, 16);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint32_t b_lo0 = desc_lo(sb_base + bs * Cfg::kBStage, 16);
+          if (leader) {
 #pragma unroll
             for (int t = 0; t < MT; ++t) {
-              const uint32_t a_addr = sa + (uint32_t)(t * kBM + kx) * 128u;
-              uint64_t a_desc = make_desc(a_addr, 16, 1024);
-              if (base_offset_mode) a_desc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem + t * BN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) {
+                // A rows start (t*128 + kx) rows = (t*128+kx)*8 sixteen-byte units into the region; k-step = 32 B = 2 units
+                const uint32_t a_lo = a_lo0 + (uint32_t)((t * kBM + kx) * 8 + k * 2);
+                umma_bf16_lh(d_tmem + t * BN, a_lo, hi, b_lo0 + (uint32_t)(k * 2), hi, idesc,
+                             (first && kx == 0 && k == 0) ? 0u : 1u);   // first MMA of each accumulator overwrites
+              }
             }
-            first = 0;
             umma_commit(&b_empty[bs]);
-            if (++bs == BST) { bs = 0; bph ^= 1; }
           }
-          umma_commit(&a_empty[as]);
-          if (++as == AST) { as = 0; aph ^= 1; }
+          __syncwarp();
+          if (++bs == BST) { bs = 0; bph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        first = 0;
+        if (leader) umma_commit(&a_empty[as]);
+        __syncwarp();
+        if (++as == AST) { as = 0; aph ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===== epilogue: TMEM -> regs -> (+bias) -> bf16 -> HBM, plus per-channel sum / sum-of-squares of the stored
     // values (BatchNorm batch statistics) reduced across the 32 rows of a warp by a transposing butterfly =====
-    const int q = warp & 3;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the (m-tile, 32-column chunk) items
+    constexpr int NCH = BN / 32, NITEMS = MT * NCH, NST = NCH / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const long long HWp = (long long)(H + 2) * Wp;
-    float st_sum[BN / 32], st_sq[BN / 32];   // lane i owns column c0 + i of every 32-column chunk
+    float st_sum[NST], st_sq[NST];   // lane i owns column c0 + i of this warp's chunks (ch = half, half+2, ...)
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
+    for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
     int st_n0 = -1;
     auto flush_stats = [&]() {
       if (stats != nullptr && st_n0 >= 0) {
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {
-          atomicAdd(&stats[st_n0 + i * 32 + lane], (double)st_sum[i]);
-          atomicAdd(&stats[Cout + st_n0 + i * 32 + lane], (double)st_sq[i]);
+        for (int i = 0; i < NST; ++i) {
+          const int col = st_n0 + (2 * i + half) * 32 + lane;
+          atomicAdd(&stats[col], (double)st_sum[i]);
+          atomicAdd(&stats[Cout + col], (double)st_sq[i]);
           st_sum[i] = st_sq[i] = 0.f;
         }
       }
@@ -500,8 +534,11 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < MT; ++t) {
+#pragma unroll
+      for (int it = 0; it < NITEMS / 2; ++it) {
+        // item = 2*it + half  ->  m-tile t = it / NST, chunk ch = 2*(it % NST) + half (NCH is even)
+        const int t = it / NST, chh = it % NST;
+        const int ch = 2 * chh + half;
         const long long m = mbase + t * kBM;
         bool valid = m < Mp;
         bf16* optr = nullptr;
@@ -513,8 +550,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
-#pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        {
           const int c0 = ch * 32;
           uint32_t v[32];
           tmem_ld32(t_row + c0, v);
@@ -545,21 +581,20 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // transposing butterfly: after the 5 steps lane i holds the sum over the warp's 32 rows of column i
 #pragma unroll
             for (int step = 0; step < 5; ++step) {
-              const int half = 16 >> step;              // values kept per lane after this step
+              const int hv = 16 >> step;              // values kept per lane after this step
               const bool upper = (lane >> (4 - step)) & 1;
 #pragma unroll
-              for (int j = 0; j < half; ++j) {
-                // lanes with the bit set keep the upper half of the columns and send the lower half (and vice versa)
-                const float send_a = upper ? a[j] : a[j + half];
-                const float keep_a = upper ? a[j + half] : a[j];
-                const float send_b = upper ? b2[j] : b2[j + half];
-                const float keep_b = upper ? b2[j + half] : b2[j];
+              for (int j = 0; j < hv; ++j) {
+                const float send_a = upper ? a[j] : a[j + hv];
+                const float keep_a = upper ? a[j + hv] : a[j];
+                const float send_b = upper ? b2[j] : b2[j + hv];
+                const float keep_b = upper ? b2[j + hv] : b2[j];
                 a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
                 b2[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
               }
             }
-            st_sum[ch] += a[0];
-            st_sq[ch] += b2[0];
+            st_sum[chh] += a[0];
+            st_sq[chh] += b2[0];
           }
         }
       }
@@ -581,7 +616,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 template <int BN, int MT>
 static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
-                        int Cout, long long Mp, int base_offset_mode, double* stats, int relu_stats, cudaStream_t s) {
+                        int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s) {
   using Cfg = Conv2Cfg<BN, MT>;
   static bool configured = false;
   if (!configured) {
@@ -595,20 +630,21 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
   long long tiles = (long long)num_m * num_n;
   int grid = (int)(tiles < 148 ? tiles : 148);
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
-  k_conv3x3_tc2<BN, MT><<<grid, kConvThreads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n,
-                                                             base_offset_mode, stats, relu_stats);
+  k_conv3x3_tc2<BN, MT><<<grid, kConv2Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n,
+                                                              stats, relu_stats);
   L3_CHECK_LAUNCH();
   return 0;
 }
 
-// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions (default), 3 = version 2 with the
-// descriptor base-offset field set (kept for A/B checks of the descriptor semantics)
+// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions (default).  (Measured on B200: the
+// descriptor "base offset" field must stay 0 for row-shifted starts -- the swizzle is applied to absolute
+// shared-memory address bits; setting the field to (addr >> 7) & 7 produces wrong results.)
 static int conv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("L3_CONV_TC_VARIANT");
     v = e ? atoi(e) : 2;
-    if (v < 1 || v > 3) v = 2;
+    if (v < 1 || v > 2) v = 2;
   }
   return v;
 }
@@ -623,10 +659,9 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   const int variant = conv_variant();
   if (variant >= 2) {
-    const int bo = variant == 3 ? 1 : 0;
-    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
-    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
-    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, bo, stats, relu_stats, s);
+    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
   }
   L3_REQUIRE(stats == nullptr, "conv_tc variant 1 has no fused statistics");
   CUtensorMap tmA, tmB;
@@ -876,37 +911,38 @@ k_wgrad3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_addr(smem + stage * Cfg::kStageBytes);
+    // whole warp runs the loop (uniform registers), one elected lane issues
+    constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+    constexpr uint32_t hi = desc_hi(1024);
+    const bool leader = elect_one();
+    const uint32_t s_base = smem_addr(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = s_base + stage * Cfg::kStageBytes;
+      if (leader) {
+        const uint32_t b_lo0 = desc_lo(sa + Cfg::kABytes, kWg2ZB);
+        const uint32_t accum = (c > c_begin) ? 1u : 0u;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-          uint32_t a0, lbo;
-          if (PAIR) {
-            const int t0 = 2 * j, t1 = (2 * j + 1 > 8) ? 8 : 2 * j + 1;
-            a0 = sa + (t0 / 3) * kWg2RB + (t0 % 3) * 128;
-            lbo = (sa + (t1 / 3) * kWg2RB + (t1 % 3) * 128) - a0;
-          } else {
-            a0 = sa + j * 128;
-            lbo = kWg2RB;
-          }
+          // compile-time byte offset of the block's first tap inside the stage and its leading-dimension offset
+          const int t0 = 2 * j, t1 = (2 * j + 1 > 8) ? 8 : 2 * j + 1;
+          const int off0 = PAIR ? (t0 / 3) * kWg2RB + (t0 % 3) * 128 : j * 128;
+          const int lbo = PAIR ? ((t1 / 3) * kWg2RB + (t1 % 3) * 128) - off0 : kWg2RB;
+          const uint32_t a_lo0 = desc_lo(sa + off0, (uint32_t)lbo);
 #pragma unroll
-          for (int ks = 0; ks < kWg2Chunk / 16; ++ks) {
-            const uint64_t a_desc = make_desc(a0 + ks * 2048, lbo, 1024);
-            const uint64_t b_desc = make_desc(sa + Cfg::kABytes + ks * 2048, kWg2ZB, 1024);
-            umma_bf16(tmem_base + j * BN, a_desc, b_desc, idesc, (c > c_begin || ks > 0) ? 1u : 0u);
-          }
+          for (int ks = 0; ks < kWg2Chunk / 16; ++ks)   // 16 pixels = 2048 B = 128 sixteen-byte units
+            umma_bf16_lh(tmem_base + j * BN, a_lo0 + ks * 128, hi, b_lo0 + ks * 128, hi, idesc, (ks > 0) ? 1u : accum);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (leader) umma_commit(&tfull_bar);
+    __syncwarp();
   } else if (c_end > c_begin) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -953,7 +989,7 @@ static int launch_wgrad2_cfg(const bf16* a, const bf16* dz, float* dw, int W, in
   if (make_tmap(&tmZ, dz, Cout, Mp, kWg2Chunk)) return -1;
   const int units = PAIR ? Cout / Cfg::BN : (Cin / 128) * (Cout / Cfg::BN) * 3;
   const int total_chunks = (int)((Mp + kWg2Chunk - 1) / kWg2Chunk);
-  int slices = (2 * 148 + units - 1) / units;
+  int slices = (2 * 148) / units;   // units*slices <= 296: exactly two waves of one CTA per SM, never a third
   int max_slices = (total_chunks + 7) / 8;
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;

@@ -436,10 +436,20 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
       s2[i] += d * ((xin - mean[i]) * inv[i]);
     }
   }
+  // lanes of a warp that share a channel group (tid % groups) are `groups` apart: fold them first
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    atomicAdd(&sh[g * 8 + i], s1[i]);
-    atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    for (int off = 16; off >= groups; off >>= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+    }
+  }
+  if ((threadIdx.x & 31) < groups || groups >= 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[g * 8 + i], s1[i]);
+      atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn.sum[i], (double)sh[i]);
@@ -452,8 +462,8 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
   int lanes = kThreads / (C / 8);
-  long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
-  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
+  int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
   if (pool) k_bwd_stats<T, true><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   else k_bwd_stats<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();

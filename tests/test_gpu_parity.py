@@ -196,7 +196,8 @@ def test_input_bn_gradient_fallback_when_gamma_is_zero():
     must take the direct path and still match the oracle."""
     mt, B = "cnn_L3_kapredbinputbn", 2
     w_np = O.init_weights(mt, seed=9, randomize_bn=True)
-    w_np["audio/bn0/gamma"][:] = 0.0
+    # only one of the three vision channels: zeroing the single audio channel would make the whole audio tower's
+    # input constant and every later BatchNorm amplify pure round-off (an ill-conditioned comparison)
     w_np["vision/bn0/gamma"][1] = 0.0
     video, audio, label = O.synthetic_batch(B, seed=404)
     vf, af = _oracle_inputs(video, audio)
