@@ -12,6 +12,7 @@
 // replica as under the reference's multi_gpu_model (l3embedding/training_utils.py:141-162).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string>
 #include <vector>
@@ -434,6 +435,15 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
   return 0;
 }
 
+static bool first_wgrad_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_FIRST_WGRAD_TC");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 template <typename T>
 static int tower_backward(l3_ctx* c, Tower& tw, int B) {
   cudaStream_t s = c->stream;
@@ -461,6 +471,10 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
         // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
         if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
                                L.Cout, s))
+          return -1;
+      } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64 && first_wgrad_tc_enabled()) {
+        if (launch_first_wgrad_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
+                                  L.Cin, L.Cout, s))
           return -1;
       } else if (l == 0) {
         if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
@@ -894,6 +908,11 @@ int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B,
   cudaStream_t s = (cudaStream_t)stream;
   L3_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * Cin * Cout, s));
   if (db) L3_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
+  if (use_tc && (Cin == 1 || Cin == 3)) {
+    L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cout == 64, "tc first-layer wgrad: bf16, Cout 64");
+    L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+    return launch_first_wgrad_tc((const bf16*)a, (const bf16*)dz, dw, db, nullptr, B, H, W, Cin, Cout, s);
+  }
   if (use_tc) {
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0, "tc wgrad: bf16, C%%64");
     L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");

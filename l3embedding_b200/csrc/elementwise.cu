@@ -401,13 +401,40 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   load8(bn.invstd + g * 8, inv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-    float g8[8], zs[8], m[8];
-    load8(da + p * C + g * 8, g8);
-    if (!POOL) {
-      load8(z + p * C + g * 8, zs);
-      act8(zs, sc, sf, relu_first, m);
-    } else {
+  const long long stride = (long long)gridDim.x * lanes;
+  if (!POOL) {
+    // 4 pixels per iteration, all 8 loads issued before any use (the kernel is latency-bound otherwise)
+    constexpr int U = 4;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+      float g8[U][8], zs[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * stride;
+        if (p < npix) {
+          load8(da + p * C + g * 8, g8[u]);
+          load8(z + p * C + g * 8, zs[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { g8[u][i] = 0.f; zs[u][i] = 0.f; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float m[8];
+        act8(zs[u], sc, sf, relu_first, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = relu_first ? g8[u][i] : (m[i] > 0.f ? g8[u][i] : 0.f);
+          float xin = relu_first ? fmaxf(zs[u][i], 0.f) : zs[u][i];
+          s1[i] += d;
+          s2[i] += d * ((xin - mean[i]) * inv[i]);
+        }
+      }
+    }
+  } else {
+    for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += stride) {
+      float g8[8], zs[8], m[8];
+      load8(da + p * C + g * 8, g8);
       const int ox = (int)(p % OW);
       const int oy = (int)((p / OW) % OH);
       const long long b = p / ((long long)OW * OH);
@@ -427,13 +454,13 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
       act8(v3, sc, sf, relu_first, y);
 #pragma unroll
       for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; zs[i] = v3[i]; }
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float d = relu_first ? g8[i] : (m[i] > 0.f ? g8[i] : 0.f);
-      float xin = relu_first ? fmaxf(zs[i], 0.f) : zs[i];
-      s1[i] += d;
-      s2[i] += d * ((xin - mean[i]) * inv[i]);
+      for (int i = 0; i < 8; ++i) {
+        float d = relu_first ? g8[i] : (m[i] > 0.f ? g8[i] : 0.f);
+        float xin = relu_first ? fmaxf(zs[i], 0.f) : zs[i];
+        s1[i] += d;
+        s2[i] += d * ((xin - mean[i]) * inv[i]);
+      }
     }
   }
   // lanes of a warp that share a channel group (tid % groups) are `groups` apart: fold them first

@@ -136,5 +136,9 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
 // dw (3,3,Cin,Cout) fp32 and db (Cout) are accumulated into (pre-zeroed by the caller).
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                        cudaStream_t s);
+// First-layer (Cin = 1|3, Cout = 64) weight gradient on tensor cores: xin padded (B,H+2,W+2,C0), dz padded
+// (B,H+2,W+2,64); accumulates dw (9*C0*64), db (64) and d1 (9*64, optional; zeroed here) -- see launch_first_wgrad.
+int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0,
+                          int Cout, cudaStream_t s);
 
 }  // namespace l3

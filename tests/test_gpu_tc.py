@@ -100,6 +100,12 @@ def test_tc_wgrad(lib, shape):
     assert (db.cpu() - ref_db).abs().max().item() <= 2e-3 * max(1.0, ref_db.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 13, 3, 64), (2, 9, 20, 1, 64), (1, 33, 31, 3, 64), (3, 40, 37, 1, 64)])
+def test_tc_first_layer_wgrad(lib, shape):
+    """Cin = 1 / 3: the im2col operand is built in shared memory by the kernel itself."""
+    test_tc_wgrad(lib, shape)
+
+
 def test_tc_path_is_active_in_bf16_engine():
     from l3embedding_b200.engine import Engine
     eng = Engine("cnn_L3_melspec2", 2, "bf16", training=True)
