@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
                 self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1 if self._nvml else 0.5)
+            self._stop_evt.wait(0.02 if self._nvml else 0.5)
 
     def finish(self):
         self._stop_evt.set()
@@ -270,7 +270,8 @@ def main_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (224 * 224 * 3 + 48000 * 2 + 8),
                     "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps,
-                    "api": "Engine.train_step_host -> l3_train_step_host (pinned host buffers)"},
+                    "api": ("Engine.train_step_host -> l3_train_step_host (pinned host buffers)" if world == 1 else
+                            "pinned host batch -> H2D -> Engine.forward_backward -> NCCL all-reduce -> metrics D2H -> adam")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,

@@ -373,14 +373,16 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* s
   ProfScope ps(c, PROF_CONV_FWD);
   *stats_done = false;
   if (L.tc && c->use_tc) {
-    if (launch_pack_weights_tc(L.w, L.w_pk, L.Cin, L.Cout, 0, c->stream)) return -1;
     const bool fuse = want_stats && conv_tc_fuses_stats();
     *stats_done = fuse;
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
                              fuse ? L.bn.sum : nullptr, L.relu_first, c->stream);
   }
-  if (L.Cin <= 3 && L.Cout == 64)
-    return launch_first_conv<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
+  if (L.Cin <= 3 && L.Cout == 64) {
+    *stats_done = want_stats;
+    return launch_first_conv<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout,
+                                want_stats ? L.bn.sum : nullptr, c->stream);
+  }
   return launch_conv3x3_simt<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
 }
 
@@ -499,7 +501,6 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     {
       ProfScope ps(c, PROF_CONV_DGRAD);
       if (L.tc && c->use_tc) {
-        if (launch_pack_weights_tc(L.w, L.wt_pk, L.Cin, L.Cout, 1, s)) return -1;
         if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
       } else {
         if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
@@ -516,9 +517,28 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
   return 0;
 }
 
+// bf16 tensor-core operand packs of every layer (forward, and dgrad when training), one launch
+static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad) {
+  if (!c->use_tc) return 0;
+  PackBatch pb;
+  pb.n = 0;
+  for (int t = 0; t < 2; ++t) {
+    Tower& tw = t == 0 ? c->vision : c->audio;
+    if (!tw.present || !(t == 0 ? vision : audio)) continue;
+    for (int l = 0; l < 8; ++l) {
+      ConvLayer& L = tw.L[l];
+      if (!L.tc) continue;
+      pb.job[pb.n++] = PackJob{L.w, L.w_pk, L.Cin, L.Cout, 0};
+      if (with_dgrad && L.wt_pk) pb.job[pb.n++] = PackJob{L.w, L.wt_pk, L.Cin, L.Cout, 1};
+    }
+  }
+  return launch_pack_weights_batch(pb, c->stream);
+}
+
 template <typename T>
 static int forward_all(l3_ctx* c, const void* video, int vfmt, const void* audio, int afmt, const float* labels, int B,
                        bool training, float grad_scale) {
+  if (pack_all_weights(c, true, true, training)) return -1;
   if (tower_input<T>(c, c->vision, false, video, vfmt, B, training)) return -1;
   if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
   if (tower_input<T>(c, c->audio, true, audio, afmt, B, training)) return -1;
@@ -843,6 +863,7 @@ int l3_embed_audio(l3_ctx* c, const void* audio, int audio_fmt, int n, int pooli
   Tower& tw = c->audio;
   const int ph = c->spec.embed_pool[pooling][0], pw = c->spec.embed_pool[pooling][1];
   ConvLayer& L = tw.L[7];
+  if (pack_all_weights(c, false, true, false)) return -1;
   if (c->dtype == L3_DTYPE_BF16) {
     if (tower_input<bf16>(c, tw, true, audio, audio_fmt, n, false)) return -1;
     if (tower_forward<bf16>(c, tw, n, false, true)) return -1;
@@ -859,6 +880,7 @@ int l3_embed_vision(l3_ctx* c, const void* video, int video_fmt, int n, float* o
   L3_REQUIRE(video && out, "null argument");
   Tower& tw = c->vision;
   ConvLayer& L = tw.L[7];
+  if (pack_all_weights(c, true, false, false)) return -1;
   if (c->dtype == L3_DTYPE_BF16) {
     if (tower_input<bf16>(c, tw, false, video, video_fmt, n, false)) return -1;
     if (tower_forward<bf16>(c, tw, n, false, true)) return -1;

@@ -227,8 +227,9 @@ static const int kFirstSeg = 16;   // x-segments per image row = pixel lanes per
 template <typename T, int C0>
 __global__ void __launch_bounds__(256)
 k_first_conv(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-             int B, int H, int W, int rows_per_block) {
+             int B, int H, int W, int rows_per_block, double* __restrict__ stats) {
   constexpr int CO = 64, K = 9 * C0;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};   // BN statistics of the stored values
   const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;
   float wr[K][4], b4[4];
 #pragma unroll
@@ -284,26 +285,45 @@ k_first_conv(const T* __restrict__ in, const float* __restrict__ w, const float*
         u.x = pack_bf16x2(acc[0], acc[1]);
         u.y = pack_bf16x2(acc[2], acc[3]);
         *reinterpret_cast<uint2*>(o) = u;
+        acc[0] = __uint_as_float(u.x << 16); acc[1] = __uint_as_float(u.x & 0xffff0000u);
+        acc[2] = __uint_as_float(u.y << 16); acc[3] = __uint_as_float(u.y & 0xffff0000u);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ssum[i] += acc[i]; ssq[i] = fmaf(acc[i], acc[i], ssq[i]); }
     }
+  }
+  if (stats != nullptr) {
+    __shared__ float red[2][CO];
+    if (threadIdx.x < 2 * CO) (&red[0][0])[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // lanes l and l+16 of a warp hold the same channel group (cg = tid & 15)
+      float a = ssum[i] + __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+      float b2 = ssq[i] + __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+      if ((threadIdx.x & 31) < 16) { atomicAdd(&red[0][cg * 4 + i], a); atomicAdd(&red[1][cg * 4 + i], b2); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * CO) atomicAdd(&stats[threadIdx.x], (double)(&red[0][0])[threadIdx.x]);
   }
 }
 
 template <typename T>
 int launch_first_conv(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int C0, int Cout,
-                      cudaStream_t s) {
+                      double* stats, cudaStream_t s) {
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_conv: C0=%d Cout=%d", C0, Cout);
+  if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
   long long n_rows = (long long)B * H;
   int rpb = (int)((n_rows + 148 * 16 - 1) / (148 * 16));
   if (rpb < 1) rpb = 1;
   int blocks = (int)((n_rows + rpb - 1) / rpb);
-  if (C0 == 1) k_first_conv<T, 1><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb);
-  else k_first_conv<T, 3><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb);
+  if (C0 == 1) k_first_conv<T, 1><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb, stats);
+  else k_first_conv<T, 3><<<blocks, 256, 0, s>>>(in, w, bias, out, B, H, W, rpb, stats);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_first_conv<float>(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
-template int launch_first_conv<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, cudaStream_t);
+template int launch_first_conv<float>(const float*, const float*, const float*, float*, int, int, int, int, int, double*, cudaStream_t);
+template int launch_first_conv<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, double*, cudaStream_t);
 
 // dw[tap][c][co] += sum_px a[px+tap][c] * dz[px][co] ; db[co] += sum_px dz[px][co]
 // d1[tap][co]    += sum_px inside(px+tap) * dz[px][co]      (weight gradient w.r.t. an all-ones input plane; used by

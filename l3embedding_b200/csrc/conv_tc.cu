@@ -188,6 +188,34 @@ __global__ void k_pack_weights(const float* __restrict__ w, bf16* __restrict__ o
     out[i] = __float2bfloat16_rn(v);
   }
 }
+// all layers of a step in one launch: blockIdx.y = job
+__global__ void k_pack_weights_batch(PackBatch pb) {
+  const PackJob j = pb.job[blockIdx.y];
+  const int Cin = j.Cin, Cout = j.Cout, flip = j.flip;
+  const int Ci = flip ? Cout : Cin, Co = flip ? Cin : Cout;
+  const int KC = Ci / 64;
+  const long long n = 9LL * Ci * Co;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int cil = (int)(i & 63);
+    long long r = i >> 6;
+    int co = (int)(r % Co);
+    long long r2 = r / Co;
+    int kc = (int)(r2 % KC);
+    int tap = (int)(r2 / KC);
+    int ci = kc * 64 + cil;
+    float v = flip ? j.w[((long long)(8 - tap) * Cin + co) * Cout + ci] : j.w[((long long)tap * Cin + ci) * Cout + co];
+    j.out[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weights_batch(const PackBatch& pb, cudaStream_t s) {
+  if (pb.n == 0) return 0;
+  L3_REQUIRE(pb.n <= kMaxPackJobs, "pack batch too large");
+  dim3 grid(148, pb.n);
+  k_pack_weights_batch<<<grid, 256, 0, s>>>(pb);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int flip_transpose, cudaStream_t s) {
   L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "pack_weights: channels must be multiples of 64");
   long long n = 9LL * Cin * Cout;

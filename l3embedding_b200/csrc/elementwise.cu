@@ -340,36 +340,33 @@ int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, co
 template int launch_gmaxpool_fwd<float>(const float*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
 template int launch_gmaxpool_fwd<bf16>(const bf16*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
 
-// global max-pool backward: dy = scatter(dpool) masked by relu; BN-backward sums (deterministic, one thread / channel)
+// global max-pool backward: dy = scatter(dpool) masked by relu, plus the BN-backward sums.  One thread per
+// (sample, channel); the per-channel sums go through double atomics (B values per channel).
 template <typename T>
 __global__ void k_gmaxpool_bwd(const float* __restrict__ dpool, int dpool_stride, const int* __restrict__ argmax,
                                const T* __restrict__ z, T* __restrict__ dy, BnRef bn, int B, int H, int W, int C) {
   const int HW = H * W;
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sc = bn.scale[c], sh = bn.shift[c], mean = bn.mean[c], inv = bn.invstd[c];
-  double s1 = 0, s2 = 0;
-  for (int b = 0; b < B; ++b) {
-    int p = argmax[b * C + c];
-    long long off = ((long long)b * HW + p) * C + c;
-    float zz = to_f(z[off]);
-    float g = dpool[(long long)b * dpool_stride + c];
-    if (zz * sc + sh > 0.f) {
-      T gt = from_f<T>(g);
-      dy[pad_off(b, p / W, p % W, H, W, C) + c] = gt;
-      float gq = to_f(gt);
-      s1 += gq;
-      s2 += gq * ((zz - mean) * inv);
-    }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int c = idx % C, b = idx / C;
+  const float sc = bn.scale[c], sh = bn.shift[c], mean = bn.mean[c], inv = bn.invstd[c];
+  const int p = argmax[b * C + c];
+  const float zz = to_f(z[((long long)b * HW + p) * C + c]);
+  const float g = dpool[(long long)b * dpool_stride + c];
+  if (zz * sc + sh > 0.f) {
+    const T gt = from_f<T>(g);
+    dy[pad_off(b, p / W, p % W, H, W, C) + c] = gt;
+    const float gq = to_f(gt);
+    atomicAdd(&bn.sum[c], (double)gq);
+    atomicAdd(&bn.sum[C + c], (double)(gq * ((zz - mean) * inv)));
   }
-  bn.sum[c] = s1;
-  bn.sum[C + c] = s2;
 }
 template <typename T>
 int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax, const T* z, T* dy, const BnRef& bn,
                         int B, int H, int W, int C, cudaStream_t s) {
   L3_CHECK_CUDA(cudaMemsetAsync(dy, 0, sizeof(T) * (size_t)B * (H + 2) * (W + 2) * C, s));
-  k_gmaxpool_bwd<T><<<ceil_div(C, 32), 32, 0, s>>>(dpool, dpool_stride, argmax, z, dy, bn, B, H, W, C);
+  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
+  k_gmaxpool_bwd<T><<<ceil_div((long long)B * C, 256), 256, 0, s>>>(dpool, dpool_stride, argmax, z, dy, bn, B, H, W, C);
   L3_CHECK_LAUNCH();
   return 0;
 }

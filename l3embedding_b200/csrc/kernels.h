@@ -85,9 +85,10 @@ int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, i
                          cudaStream_t s);
 // first-layer (Cin = 1|3, Cout = 64) backward: weight/bias gradient, and the input-BN backward sums computed
 // straight from dz without materialising the data gradient (bn.sum <- sum(da), sum(da*xhat))
+// stats (optional): double[2*64] per-channel sum / sum of squares of the stored output (BN batch statistics)
 template <typename T>
 int launch_first_conv(const T* in, const float* w, const float* bias, T* out, int B, int H, int W, int C0, int Cout,
-                      cudaStream_t s);
+                      double* stats, cudaStream_t s);
 // d1 (optional, 9*64 floats): weight gradient w.r.t. an all-ones input plane, consumed by launch_bn0_from_dw
 template <typename T>
 int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0, int Cout,
@@ -126,6 +127,18 @@ int conv_tc_fuses_stats();   // the active forward variant computes BN statistic
 // row = 128 B).  flip_transpose=1 packs the dgrad operand: taps flipped and Cin/Cout swapped, i.e. the result is the
 // forward pack of a conv with Cin' = Cout, Cout' = Cin.
 int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int flip_transpose, cudaStream_t s);
+// the same for every tensor-core layer of a step in ONE launch (weights change once per step, in k_adam)
+static const int kMaxPackJobs = 32;
+struct PackJob {
+  const float* w;
+  bf16* out;
+  int Cin, Cout, flip;
+};
+struct PackBatch {
+  PackJob job[kMaxPackJobs];
+  int n;
+};
+int launch_pack_weights_batch(const PackBatch& pb, cudaStream_t s);
 // Forward / dgrad conv on tensor cores. in: zero-haloed padded bf16 (B,H+2,W+2,Cin), Cin%64==0, Cout%64==0;
 // out: unpadded bf16 (B,H,W,Cout); bias may be null.  stats (optional): double[2*Cout] receives the per-channel sum and
 // sum of squares of the stored output (of relu(output) if relu_stats) -- the BatchNorm batch statistics, fused into
