@@ -462,7 +462,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     long long rows = (long long)B * L.H * L.W;
     if (l == 7) {
       // dz holds the scattered dy of the global max-pool and bn.sum its sums: finish BN backward in place
-      if (launch_bn_bwd_finalize(L.bn, rows, s)) return -1;
+      if (launch_bn_bwd_finalize(L.bn, rows, 0, s)) return -1;
       if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
     }
     // weight / bias gradient
@@ -493,7 +493,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
         int* fallback = reinterpret_cast<int*>(tw.d1 + 9 * 64);
         if (launch_bn0_from_dw(L.w, L.dw, tw.d1, tw.bn0, L.Cin, fallback, s)) return -1;
         if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, fallback, s)) return -1;
-        if (launch_bn_bwd_finalize(tw.bn0, rows, s)) return -1;
+        if (launch_bn_bwd_finalize(tw.bn0, rows, 0, s)) return -1;
       }
       break;
     }
@@ -511,7 +511,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     ConvLayer& Lp = tw.L[l - 1];
     long long rows_p = (long long)B * Lp.H * Lp.W;
     if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
-    if (launch_bn_bwd_finalize(Lp.bn, rows_p, s)) return -1;
+    if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
     if (launch_bwd_apply<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
   }
   return 0;

@@ -382,8 +382,11 @@ template int launch_gmaxpool_bwd<bf16>(const float*, int, const int*, const bf16
 // max-pool routes to the first maximum in window order (0,0),(0,1),(1,0),(1,1); pixels dropped by 'valid' pooling of
 // odd sizes have dy = 0 (they still receive the BN mean terms).  da: unpadded (B,OH,OW,C); z: unpadded (B,H,W,C).
 // --------------------------------------------------------------------------------------------
+// Accumulates the RAW sums S1 = sum(dy) and S2 = sum(dy * xin) (xin = z, or relu(z) when relu_first); the
+// normalised sum the BN backward needs is sum(dy*xhat) = invstd * (S2 - mean * S1), formed in double precision by
+// k_bn_bwd_finalize.  (Fewer instructions per element: these kernels are issue-bound, not HBM-bound.)
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, POOL ? 2 : 3)
 k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int C, int OH, int OW, long long npix,
             BnRef bn, int relu_first) {
   extern __shared__ float sh[];  // 2*C
@@ -391,17 +394,20 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  float sc[8], sf[8], mean[8], inv[8], s1[8], s2[8];
+  // fp32 (parity) mode subtracts the batch mean before accumulating (no cancellation in S2 - mean*S1: the
+  // near-zero input-BN beta gradient is sensitive to it); bf16 mode keeps the raw products.
+  constexpr bool kCentre = sizeof(T) == 4;
+  float sc[8], sf[8], mu[8], s1[8], s2[8];
   load8(bn.scale + g * 8, sc);
   load8(bn.shift + g * 8, sf);
-  load8(bn.mean + g * 8, mean);
-  load8(bn.invstd + g * 8, inv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mu[i] = 0.f;
+  if (kCentre) load8(bn.mean + g * 8, mu);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   const long long stride = (long long)gridDim.x * lanes;
   if (!POOL) {
-    // 4 pixels per iteration, all 8 loads issued before any use (the kernel is latency-bound otherwise)
-    constexpr int U = 4;
+    constexpr int U = 2;
     for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
       float g8[U][8], zs[U][8];
 #pragma unroll
@@ -416,17 +422,17 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float m[8];
-        act8(zs[u], sc, sf, relu_first, m);
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float d = relu_first ? g8[u][i] : (m[i] > 0.f ? g8[u][i] : 0.f);
-          float xin = relu_first ? fmaxf(zs[u][i], 0.f) : zs[u][i];
+          const float zz = zs[u][i];
+          // normal: dy = da where bn(z) > 0, xin = z ; relu_first: dy = da, xin = relu(z)
+          const float d = relu_first ? g8[u][i] : (fmaf(zz, sc[i], sf[i]) > 0.f ? g8[u][i] : 0.f);
+          float xin = relu_first ? fmaxf(zz, 0.f) : zz;
+          if (kCentre) xin -= mu[i];
           s1[i] += d;
-          s2[i] += d * ((xin - mean[i]) * inv[i]);
+          s2[i] = fmaf(d, xin, s2[i]);
         }
-      }
     }
   } else {
     for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += stride) {
@@ -453,10 +459,11 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
       for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; zs[i] = v3[i]; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float d = relu_first ? g8[i] : (m[i] > 0.f ? g8[i] : 0.f);
+        const float d = relu_first ? g8[i] : (m[i] > 0.f ? g8[i] : 0.f);
         float xin = relu_first ? fmaxf(zs[i], 0.f) : zs[i];
+        if (kCentre) xin -= mu[i];
         s1[i] += d;
-        s2[i] += d * ((xin - mean[i]) * inv[i]);
+        s2[i] = fmaf(d, xin, s2[i]);
       }
     }
   }
@@ -612,10 +619,13 @@ template int launch_bwd_apply<bf16>(const bf16*, const bf16*, bf16*, int, int, i
 
 // BN backward finalize: dgamma, dbeta and the folded coefficients of dz = scale*dy + c1*xin + c2
 //   c1 = -scale*invstd*mean(dy*xhat) ; c2 = -scale*mean(dy) - c1*mean
-__global__ void k_bn_bwd_finalize(BnRef bn, double count) {
+__global__ void k_bn_bwd_finalize(BnRef bn, double count, int raw) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= bn.C) return;
   double s1 = bn.sum[c], s2 = bn.sum[bn.C + c];
+  // raw 1: sum(dy*xin) ; raw 2: sum(dy*(xin-mean))   ->  sum(dy*xhat)
+  if (raw == 1) s2 = (double)bn.invstd[c] * (s2 - (double)bn.mean[c] * s1);
+  else if (raw == 2) s2 = (double)bn.invstd[c] * s2;
   bn.d_beta[c] = (float)s1;
   bn.d_gamma[c] = (float)s2;
   const double sc = (double)bn.scale[c];
@@ -623,8 +633,8 @@ __global__ void k_bn_bwd_finalize(BnRef bn, double count) {
   bn.c1[c] = (float)cb;
   bn.c2[c] = (float)(-sc * (s1 / count) - cb * (double)bn.mean[c]);
 }
-int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s) {
-  k_bn_bwd_finalize<<<ceil_div(bn.C, 128), 128, 0, s>>>(bn, (double)count);
+int launch_bn_bwd_finalize(const BnRef& bn, long long count, int raw_sums, cudaStream_t s) {
+  k_bn_bwd_finalize<<<ceil_div(bn.C, 128), 128, 0, s>>>(bn, (double)count, raw_sums);
   L3_CHECK_LAUNCH();
   return 0;
 }

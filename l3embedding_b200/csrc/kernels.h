@@ -58,7 +58,8 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
                      int relu_first, cudaStream_t s);
-int launch_bn_bwd_finalize(const BnRef& bn, long long count, cudaStream_t s);
+// raw_sums: bn.sum[C..2C) holds 0: sum(dy*xhat); 1: sum(dy*xin) (launch_bwd_stats<bf16>); 2: sum(dy*(xin-mean)) (<float>)
+int launch_bn_bwd_finalize(const BnRef& bn, long long count, int raw_sums, cudaStream_t s);
 template <typename T>
 int launch_bn_bwd_apply(T* dy_inout, const T* z, int B, int H, int W, int C, const BnRef& bn, int relu_first,
                         cudaStream_t s);   // dy: padded, z: unpadded
