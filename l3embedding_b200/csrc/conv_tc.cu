@@ -664,15 +664,305 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
   return 0;
 }
 
-// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions (default).  (Measured on B200: the
+// ---------------------------------------------------------------------------------------------------------
+// forward / dgrad, version 3: CTA pairs (tcgen05 cta_group::2), N = 256
+// ---------------------------------------------------------------------------------------------------------
+// Version 2 with N = 256 is bound by shared-memory bandwidth: every 128x256x16 MMA re-reads an 8 KB weight slice
+// for only 128 output rows (4 + 8 KB per 128 cycles) while TMA writes the next stages into the same memory.  A CTA
+// pair (two SMs of one TPC) issues ONE 256x256x16 MMA: each CTA stages its own 128 pixel rows (A) and HALF of the
+// weight tile (128 of the 256 output channels); the tensor cores of both SMs read both halves, so per SM the
+// operand traffic per FLOP halves.  The leader CTA (cluster rank 0) issues the MMAs; both CTAs run TMA (their
+// transaction bytes land on the leader's mbarriers), and tcgen05.commit multicasts "stage free" / "accumulator
+// ready" to both.
+static const int kConv3Threads = 64 + 256;
+struct Conv3Cfg {
+  static const int BN = 256;
+  static const int kARows = kBM + 8;
+  static const int kAStage = kARows * 128;       // 17408 B
+  static const int kAStages = 4;
+  static const int kBStage = (BN / 2) * 128;     // this CTA's half of the weight tile: 16384 B
+  static const int kBStages = 8;
+  static const int kSmem = kAStages * kAStage + kBStages * kBStage + 1024;
+  static const int kTmemCols = 512;              // two 256-column accumulators
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose transaction bytes are credited to the mbarrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_addr(dst)), "l"(tm), "r"(smem_addr(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lh_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %6, 0;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_addr(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(
+          smem_addr(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
+k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
+              int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
+  using Cfg = Conv3Cfg;
+  constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages, BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + AST * Cfg::kAStage;
+  __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }   // 8 warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int KC = Cin >> 6;
+  const int Wp = W + 2;
+  const int num_tiles = num_m_pairs * num_n_tiles;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own 128 pixel rows + own half of the weight tile =====
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / num_n_tiles) * (2 * kBM) + (int)rank * kBM;
+        const int n0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kc = 0; kc < KC; ++kc)
+          for (int ky = 0; ky < 3; ++ky) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (rank == 0) mbar_expect_tx(&a_full[as], 2 * Cfg::kAStage);
+            tma_load_2d_pair(&tmA, &a_full[as], smem + as * Cfg::kAStage, kc * 64, m0 + (ky - 1) * Wp - 1);
+            if (++as == AST) { as = 0; aph ^= 1; }
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * Cfg::kBStage);
+              tma_load_2d_pair(&tmB, &b_full[bs], smem_b + bs * Cfg::kBStage, 0, ((ky * 3 + kx) * KC + kc) * Cout + n0);
+              if (++bs == BST) { bs = 0; bph ^= 1; }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = make_idesc(2 * kBM, BN, 0, 0);
+      constexpr uint32_t hi = desc_hi(1024);
+      const bool leader = elect_one();
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t sa_base = smem_addr(smem), sb_base = smem_addr(smem_b);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t first = 1;
+        for (int it = 0; it < 3 * KC; ++it) {
+          mbar_wait(&a_full[as], aph);
+          const uint32_t a_lo0 = desc_lo(sa_base + as * Cfg::kAStage, 16);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_lo0 = desc_lo(sb_base + bs * Cfg::kBStage, 16);
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lh_pair(d_tmem, a_lo0 + (uint32_t)(kx * 8 + k * 2), hi, b_lo0 + (uint32_t)(k * 2), hi, idesc,
+                                  (first && kx == 0 && k == 0) ? 0u : 1u);
+              umma_commit_pair(&b_empty[bs]);
+            }
+            __syncwarp();
+            if (++bs == BST) { bs = 0; bph ^= 1; }
+          }
+          first = 0;
+          if (leader) umma_commit_pair(&a_empty[as]);
+          __syncwarp();
+          if (++as == AST) { as = 0; aph ^= 1; }
+        }
+        if (leader) umma_commit_pair(&tfull_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, own 128 rows): as in version 2 =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = BN / 32, NST = NCH / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const long long HWp = (long long)(H + 2) * Wp;
+    float st_sum[NST], st_sq[NST];
+#pragma unroll
+    for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
+    int st_n0 = -1;
+    auto flush_stats = [&]() {
+      if (stats != nullptr && st_n0 >= 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) {
+          const int col = st_n0 + (2 * i + half) * 32 + lane;
+          atomicAdd(&stats[col], (double)st_sum[i]);
+          atomicAdd(&stats[Cout + col], (double)st_sq[i]);
+          st_sum[i] = st_sq[i] = 0.f;
+        }
+      }
+    };
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const long long m = (long long)(tile / num_n_tiles) * (2 * kBM) + (long long)rank * kBM + q * 32 + lane;
+      const int n0 = (tile % num_n_tiles) * BN;
+      if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
+      bool valid = m < Mp;
+      bf16* optr = nullptr;
+      if (valid) {
+        const long long b = m / HWp;
+        const int r = (int)(m - b * HWp);
+        const int yp = r / Wp, xp = r - yp * Wp;
+        valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
+        optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+      for (int chh = 0; chh < NST; ++chh) {
+        const int c0 = (2 * chh + half) * 32;
+        uint32_t v[32];
+        tmem_ld32(t_row + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float f0 = __uint_as_float(v[2 * j]) + (bias ? __ldg(bias + n0 + c0 + 2 * j) : 0.f);
+          const float f1 = __uint_as_float(v[2 * j + 1]) + (bias ? __ldg(bias + n0 + c0 + 2 * j + 1) : 0.f);
+          pk[j] = pack_bf16x2(f0, f1);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (stats != nullptr) {
+          float a[32], b2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+            float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+            if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            a[2 * j] = x0; a[2 * j + 1] = x1;
+            b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
+          }
+#pragma unroll
+          for (int step = 0; step < 5; ++step) {
+            const int hv = 16 >> step;
+            const bool upper = (lane >> (4 - step)) & 1;
+#pragma unroll
+            for (int j = 0; j < hv; ++j) {
+              const float send_a = upper ? a[j] : a[j + hv];
+              const float keep_a = upper ? a[j + hv] : a[j];
+              const float send_b = upper ? b2[j] : b2[j + hv];
+              const float keep_b = upper ? b2[j + hv] : b2[j];
+              a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
+              b2[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
+            }
+          }
+          st_sum[chh] += a[0];
+          st_sq[chh] += b2[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the leader's MMA warp owns the accumulator hand-off
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    flush_stats();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // nobody leaves while the peer may still signal its barriers / read its operands
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
+                        long long Mp, double* stats, int relu_stats, cudaStream_t s) {
+  using Cfg = Conv3Cfg;
+  static bool configured = false;
+  if (!configured) {
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tmap(&tmA, in, Cin, Mp, Cfg::kARows)) return -1;
+  if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, Cfg::BN / 2)) return -1;
+  const int num_mp = (int)((Mp + 2 * kBM - 1) / (2 * kBM)), num_n = Cout / Cfg::BN;
+  long long tiles = (long long)num_mp * num_n;
+  int pairs = (int)(tiles < 74 ? tiles : 74);
+  if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
+  k_conv3x3_tc3<<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n, stats,
+                                                            relu_stats);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions, 3 = version 2 + CTA pairs
+// (cta_group::2) for the N = 256 layers (default).  (Measured on B200: the
 // descriptor "base offset" field must stay 0 for row-shifted starts -- the swizzle is applied to absolute
 // shared-memory address bits; setting the field to (addr >> 7) & 7 produces wrong results.)
 static int conv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("L3_CONV_TC_VARIANT");
-    v = e ? atoi(e) : 2;
-    if (v < 1 || v > 2) v = 2;
+    v = e ? atoi(e) : 3;
+    if (v < 1 || v > 3) v = 3;
   }
   return v;
 }
@@ -687,6 +977,7 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   const int variant = conv_variant();
   if (variant >= 2) {
+    if (BN == 256 && variant == 3) return launch_conv3(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
