@@ -87,6 +87,10 @@ class OracleConfig:
     adam_beta2: float = 0.999
     adam_eps: float = 1e-8                # keras 2.0.9 K.epsilon()=1e-7? -> see note below
     dtype: torch.dtype = torch.float32
+    # Emulate the bf16 throughput mode of the CUDA path: round to bfloat16 exactly where the device stores bf16
+    # (conv inputs, conv outputs z, conv weights of the tensor-core layers, and in backward dz / da); all arithmetic
+    # stays in `dtype`.  With this on, the oracle differs from the device only by accumulation order.
+    emulate_bf16: bool = False
 
 
 # Note on adam_eps: keras 2.0.9 Adam(epsilon=1e-8) is the constructor default; the update is
@@ -276,6 +280,23 @@ def frontend(audio: torch.Tensor, model_type: str, cfg: OracleConfig = OracleCon
 # Towers, head, loss
 # --------------------------------------------------------------------------------------
 
+def _q(x):
+    """round to bf16 in forward, straight-through gradient"""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+class _RoundGrad(torch.autograd.Function):
+    """identity in forward; rounds the incoming gradient to bf16 in backward (the device stores dz / da as bf16)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
 def _bn(x, w, prefix, training, cfg, stats):
     """x NCHW.  Keras BatchNormalization(axis=-1 in NHWC): batch mean / biased var when training."""
     g, b = w[prefix + "/gamma"], w[prefix + "/beta"]
@@ -290,8 +311,15 @@ def _bn(x, w, prefix, training, cfg, stats):
     return (x - mean[None, :, None, None]) * (inv * g)[None, :, None, None] + b[None, :, None, None]
 
 
-def _conv(x, w, prefix):
+def _conv(x, w, prefix, cfg=None):
     k = w[prefix + "/kernel"].permute(3, 2, 0, 1)     # HWIO -> OIHW
+    if cfg is not None and cfg.emulate_bf16:
+        # device: bf16 conv input (gradient da stored as bf16), bf16 packed weights on the tcgen05 layers (Cin >= 64;
+        # the first layer runs SIMT with fp32 weights), fp32 accumulate, output z and its gradient dz stored as bf16
+        x = _RoundGrad.apply(_q(x))
+        if k.shape[1] >= 64:
+            k = _q(k)
+        return _RoundGrad.apply(_q(F.conv2d(x, k, w[prefix + "/bias"], padding=1)))
     return F.conv2d(x, k, w[prefix + "/bias"], padding=1)
 
 
@@ -318,7 +346,7 @@ def tower_forward(x_nhwc: torch.Tensor, w: Dict[str, torch.Tensor], tower: str, 
         x = _bn(x, w, f"{tower}/bn0", training, cfg, stats)
     same_pool = tower == "vision"
     for i, nm in enumerate(CONV_NAMES):
-        z = _conv(x, w, f"{tower}/{nm}")
+        z = _conv(x, w, f"{tower}/{nm}", cfg)
         if nm == "conv4b" and return_embedding_map:
             return z.permute(0, 2, 3, 1)
         bnn = f"{tower}/bn{nm[4:]}"
