@@ -87,6 +87,11 @@ int l3_predict(l3_ctx* ctx, const void* video, int video_fmt, const void* audio,
 /* load_embedding(...,'audio', pooling) + model.predict (model.py:131-181, features.py:304):
  * audio (n,1,48000) device -> out (n, 6144|512) device floats, n <= max_batch per call.                      */
 int l3_embed_audio(l3_ctx* ctx, const void* audio, int audio_fmt, int n, int pooling, float* out);
+/* get_l3_frames_uniform (data/usc/features.py:256-306) without materialising the framed copy: `signal` is ONE device
+ * array of n_samples; frame i is the 1 s window starting at i*hop (hop in samples; hop*sizeof(sample) must be a
+ * multiple of 16).  out (n_frames, 6144|512).  Runs in chunks of the context's max_batch. */
+int l3_embed_audio_frames(l3_ctx* ctx, const void* signal, int audio_fmt, int64_t n_samples, int hop, int n_frames,
+                          int pooling, float* out);
 /* load_embedding(...,'vision',...) (vision_model.py:198-218): video (n,224,224,3) -> (n, 8192) */
 int l3_embed_vision(l3_ctx* ctx, const void* video, int video_fmt, int n, float* out);
 

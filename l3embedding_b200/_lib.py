@@ -46,6 +46,7 @@ SIGNATURES = {
     "l3_train_step_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _f, _fp]),
     "l3_predict": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "l3_embed_audio": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "l3_embed_audio_frames": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "l3_embed_vision": (_i, [_vp, _vp, _i, _i, _vp]),
     "l3_frontend_fwd": (_i, [_vp, _vp, _i, _i, _vp]),
     "l3_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

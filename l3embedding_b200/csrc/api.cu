@@ -695,7 +695,7 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   audio_geometry(c->spec, &n_out, &n_frames, &left);
   FrontendPlan& fe = c->fe;
   fe.n_dft = c->spec.n_dft; fe.n_hop = kHop; fe.n_frames = n_frames; fe.left_pad = left; fe.n_out = n_out;
-  fe.mel = c->spec.mel; fe.decibel = c->spec.decibel; fe.n_samples = kSR;
+  fe.mel = c->spec.mel; fe.decibel = c->spec.decibel; fe.n_samples = kSR; fe.clip_stride = kSR;
   if (frontend_build_tables(&fe, kSR, c->spec.n_mels, c->fe_tables, c->stream)) {
     delete c;
     return nullptr;
@@ -872,6 +872,28 @@ int l3_embed_audio(l3_ctx* c, const void* audio, int audio_fmt, int n, int pooli
   if (tower_input<float>(c, tw, true, audio, audio_fmt, n, false)) return -1;
   if (tower_forward<float>(c, tw, n, false, true)) return -1;
   return launch_embed_pool<float>((const float*)L.z, n, L.H, L.W, L.Cout, ph, pw, out, c->stream);
+}
+
+int l3_embed_audio_frames(l3_ctx* c, const void* signal, int audio_fmt, int64_t n_samples, int hop, int n_frames,
+                          int pooling, float* out) {
+  L3_REQUIRE(c != nullptr && signal && out, "null argument");
+  L3_REQUIRE(hop >= 1 && n_frames >= 1, "bad hop %d / n_frames %d", hop, n_frames);
+  L3_REQUIRE((int64_t)(n_frames - 1) * hop + kSR <= n_samples, "signal of %lld samples is too short for %d frames at hop %d",
+             (long long)n_samples, n_frames, hop);
+  const int es = audio_fmt == L3_AUDIO_I16 ? 2 : 4;
+  L3_REQUIRE(((int64_t)hop * es) % 16 == 0, "hop %d breaks the 16-byte alignment of the frame starts (frame on the host)", hop);
+  L3_REQUIRE(pooling == L3_POOL_ORIGINAL || pooling == L3_POOL_SHORT, "bad pooling %d", pooling);
+  int eh, ew;
+  l3_embedding_map_shape(c->model_type, &eh, &ew);
+  const int dim = (eh / c->spec.embed_pool[pooling][0]) * (ew / c->spec.embed_pool[pooling][1]) * 512;
+  int rc = 0;
+  c->fe.clip_stride = hop;   // overlapping 1 s windows read straight from the signal: no 10x framed copy
+  for (int f0 = 0; f0 < n_frames && !rc; f0 += c->max_batch) {
+    const int nb = n_frames - f0 < c->max_batch ? n_frames - f0 : c->max_batch;
+    rc = l3_embed_audio(c, (const char*)signal + (int64_t)f0 * hop * es, audio_fmt, nb, pooling, out + (int64_t)f0 * dim);
+  }
+  c->fe.clip_stride = kSR;
+  return rc;
 }
 
 int l3_embed_vision(l3_ctx* c, const void* video, int video_fmt, int n, float* out) {

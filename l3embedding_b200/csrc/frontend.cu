@@ -155,7 +155,7 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   const int a_lo = c_lo & ~(16 / ES - 1);
   const int a_hi = min((c_hi + 16 / ES - 1) & ~(16 / ES - 1), p.n_samples);  // n_samples*ES is a multiple of 16
   const uint32_t bytes = (uint32_t)(a_hi - a_lo) * ES;
-  const unsigned char* src = reinterpret_cast<const unsigned char*>(audio) + ((size_t)b * p.n_samples + a_lo) * ES;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(audio) + ((size_t)b * p.clip_stride + a_lo) * ES;
 
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -302,6 +302,7 @@ static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out
 int launch_frontend(const FrontendPlan& p, const void* audio, int is_i16, int B, float* out, int* clip_max,
                     cudaStream_t s) {
   L3_REQUIRE(p.n_dft == 512 || p.n_dft == 2048, "frontend: n_dft %d", p.n_dft);
+  L3_REQUIRE((p.clip_stride * (is_i16 ? 2 : 4)) % 16 == 0, "frontend: clip stride %lld breaks 16-byte alignment", p.clip_stride);
   if (p.decibel) {
     k_frontend_init_max<<<ceil_div(B, 128), 128, 0, s>>>(clip_max, B);
     L3_CHECK_LAUNCH();

@@ -14,6 +14,7 @@ struct FrontendPlan {
   int mel;          // 1 -> mel filterbank
   int decibel;      // 1 -> 10*log10, per-clip max, clip -80 ; 0 -> log(max(x,1e-12))/5
   int n_samples;    // 48000
+  long long clip_stride;  // samples between the starts of consecutive clips (n_samples; the hop when framing on device)
   // device constants (built once per ctx by frontend_build_tables)
   const float2* twiddle;    // n_dft/2 entries exp(-2 pi i j / n_dft)
   const float* window;      // n_dft periodic hann

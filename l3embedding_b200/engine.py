@@ -218,6 +218,29 @@ class Engine:
             self._keep = (a,)
             return out
 
+    def embedding_dim(self, pooling: str) -> int:
+        eh, ew = self.embedding_map_shape
+        ph, pw = {"cnn_L3_melspec1": {"original": (4, 8), "short": (16, 24)}}.get(
+            self.model_type, {"original": (8, 8), "short": (32, 24)})[pooling]
+        return (eh // ph) * (ew // pw) * 512
+
+    def embed_audio_frames(self, signal, hop: int, pooling: str = "original") -> torch.Tensor:
+        """Embeddings of every 1 s window of a 1-D signal at `hop` samples (get_l3_frames_uniform,
+        data/usc/features.py:279-304) -- the overlapping windows are read in place on the device."""
+        with torch.cuda.device(self.device):
+            sig = _as_device(signal, self.device, (torch.int16, torch.float32)).reshape(-1)
+            n = sig.numel()
+            if n < SR:
+                raise ValueError("signal shorter than one 1 s frame")
+            n_frames = 1 + (n - SR) // hop
+            out = torch.empty(n_frames, self.embedding_dim(pooling), dtype=torch.float32, device=self.device)
+            af = _lib.AUDIO_I16 if sig.dtype == torch.int16 else _lib.AUDIO_F32
+            _lib.check(self.lib.l3_embed_audio_frames(self.ctx, self._p(sig), af, n, int(hop), n_frames,
+                                                      _lib.POOL_ORIGINAL if pooling == "original" else _lib.POOL_SHORT,
+                                                      self._p(out)), "l3_embed_audio_frames")
+            self._keep = (sig,)
+            return out
+
     def embed_vision(self, video) -> torch.Tensor:
         with torch.cuda.device(self.device):
             v, vf, _, _, _, n = self._inputs(video, None)

@@ -380,6 +380,21 @@ class EmbeddingModel:
                                   towers=(self.embedding_type,), weights=self.parent._weights_dict(), host_staging=False)
         return self._engine
 
+    def predict_frames(self, signal, hop_length, batch_size=256):
+        """Embeddings of all 1 s windows of a 1-D signal at `hop_length` samples, framed on the device."""
+        if self.embedding_type != "audio":
+            raise ValueError("predict_frames is an audio-embedding call")
+        sig = np.ascontiguousarray(signal).reshape(-1)
+        es = 2 if sig.dtype == np.int16 else 4
+        if sig.dtype not in (np.int16, np.float32):
+            sig = sig.astype(np.float32)
+        n_frames = 1 + (len(sig) - 48000) // hop_length
+        if (hop_length * es) % 16 != 0:      # unaligned frame starts: frame on the host as the reference does
+            idx = np.arange(48000)[None, :] + hop_length * np.arange(n_frames)[:, None]
+            return self.predict(sig[idx].reshape(n_frames, 1, 48000), batch_size=batch_size)
+        eng = self._get_engine(min(batch_size, max(n_frames, 1)))
+        return eng.embed_audio_frames(sig, hop_length, self.pooling_type).cpu().numpy()
+
     def predict(self, x, batch_size=32, verbose=0):
         x = np.asarray(x) if not hasattr(x, "shape") else x
         n = len(x)

@@ -137,6 +137,99 @@ def test_load_embedding_boundary(tmp_path):
         M.load_embedding(p, "cnn_L3_melspec2", "audio", "tiny")
 
 
+def test_framing_rule_matches_reference_quirk():
+    """data/usc/features.py:279-298: short clips are padded symmetrically to one frame; longer clips are NEVER padded
+    (operator-precedence quirk) and the trailing partial hop is dropped."""
+    from l3embedding_b200.features import frame_signal
+
+    class Rec:
+        def predict(self, x):
+            self.x = x
+            return np.zeros((len(x), 4))
+    a, hop, n = frame_signal(np.arange(30000, dtype=np.float32))
+    assert len(a) == 48000 and hop == 4800 and n == 1 and a[9000] == 0.0 and a[9001] == 1.0
+    a, hop, n = frame_signal(np.zeros(48000 * 4 + 1234, np.float32))
+    assert len(a) == 48000 * 4 + 1234 and n == 1 + (3 * 48000 + 1234) // 4800
+    from l3embedding_b200.features import get_l3_frames_uniform, compute_file_features
+    r = Rec()
+    sig = np.arange(48000 + 2 * 4800 + 7, dtype=np.float32)
+    out = get_l3_frames_uniform(sig, r)
+    assert out.shape == (3, 4) and r.x.shape == (3, 1, 48000) and r.x[2, 0, 0] == 9600.0
+    with pytest.raises(ValueError, match="Must provide L3 embedding model"):
+        compute_file_features("x.wav", "l3")
+    with pytest.raises(ValueError, match="Invalid feature type"):
+        compute_file_features("x.wav", "mfcc", l3embedding_model=r)
+
+
+def _write_batches(d, n_files=2, per_file=5, seed=0):
+    from l3embedding_b200.synthetic import synthetic_batch
+    os.makedirs(d, exist_ok=True)
+    for i in range(n_files):
+        v, a, l = synthetic_batch(per_file, seed=seed + i)
+        np.savez(os.path.join(d, "batch_%02d.npz" % i), video=v, audio=a, label=l)
+
+
+def test_data_generator_and_restart_info(tmp_path):
+    """train.py:142-215: batches are cut across file boundaries; start_batch_idx skips without yielding; raw u8/i16 by
+    default, the reference's float scaling on request; get_restart_info reads the last CSV row."""
+    from l3embedding_b200 import train as T
+    d = str(tmp_path / "subset_train")
+    _write_batches(d)
+    g = T.data_generator(d, batch_size=4, random_state=1)
+    b0, b1, b2 = next(g), next(g), next(g)
+    assert b0["video"].shape == (4, 224, 224, 3) and b0["video"].dtype == np.uint8 and b0["audio"].dtype == np.int16
+    assert b1["label"].shape == (4, 2) and b1["label"].dtype == np.float32
+    g2 = T.data_generator(d, batch_size=4, random_state=1, start_batch_idx=1)
+    assert np.array_equal(next(g2)["audio"], b1["audio"])          # resume lands on the same batch
+    gs = T.data_generator(d, batch_size=4, random_state=1, scale_on_host=True)
+    s0 = next(gs)
+    assert s0["video"].dtype == np.float32 and s0["video"].min() >= -1 and s0["video"].max() <= 1
+    assert np.array_equal(s0["audio"], b0["audio"].astype(np.float32) / 32768)
+    x, y = next(T.keras_tuples(T.data_generator(d, batch_size=2), ["video", "audio"], "label"))
+    assert len(x) == 2 and x[0].shape == (2, 224, 224, 3) and y.shape == (2, 2)
+    ev = T.single_epoch_data_generator(d, 2, batch_size=4, random_state=1)
+    e = [next(ev) for _ in range(4)]
+    assert np.array_equal(e[0]["audio"], e[2]["audio"]) and np.array_equal(e[1]["audio"], e[3]["audio"])
+    p = tmp_path / "history_csvlog.csv"
+    p.write_text("epoch,acc,loss,val_acc,val_loss\n0,0.5,0.9,0.55,0.8\n1,0.6,0.7,0.65,0.6\n")
+    assert T.get_restart_info(str(p)) == (1, 0.65, 0.6)
+
+
+def test_training_callbacks(tmp_path):
+    from l3embedding_b200 import train as T
+
+    class Dummy:
+        saved = []
+
+        def save_weights(self, path):
+            self.saved.append(os.path.basename(path))
+    m = Dummy()
+    cbs = [T.ModelCheckpoint(str(tmp_path / "model_latest.h5")),
+           T.ModelCheckpoint(str(tmp_path / "best_acc.h5"), save_best_only=True, monitor="val_acc"),
+           T.ModelCheckpoint(str(tmp_path / "best_loss.h5"), save_best_only=True, monitor="val_loss"),
+           T.ModelCheckpoint(str(tmp_path / "model_checkpoint.{epoch:02d}.h5"), period=2),
+           T.CSVLogger(str(tmp_path / "history_csvlog.csv"), append=True), T.LossHistory(str(tmp_path / "h.pkl")),
+           T.TimeHistory()]
+    for c in cbs:
+        c.set_model(m)
+        if hasattr(c, "on_train_begin"):
+            c.on_train_begin()
+    logs = [dict(loss=1.0, acc=0.5, val_loss=0.9, val_acc=0.5), dict(loss=0.8, acc=0.6, val_loss=1.1, val_acc=0.7),
+            dict(loss=0.7, acc=0.7, val_loss=0.5, val_acc=0.6)]
+    for e, lg in enumerate(logs):
+        for c in cbs:
+            if hasattr(c, "on_epoch_begin"):
+                c.on_epoch_begin(e)
+        for c in cbs:
+            c.on_epoch_end(e, lg)
+    assert m.saved.count("model_latest.h5") == 3
+    assert m.saved.count("best_acc.h5") == 2 and m.saved.count("best_loss.h5") == 2
+    assert "model_checkpoint.02.h5" in m.saved and "model_checkpoint.01.h5" not in m.saved
+    assert T.get_restart_info(str(tmp_path / "history_csvlog.csv")) == (2, 0.6, 0.5)
+    import pickle
+    assert pickle.load(open(tmp_path / "h.pkl", "rb")) == {"loss": [1.0, 0.8, 0.7], "val_loss": [0.9, 1.1, 0.5]}
+
+
 def test_compute_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
