@@ -82,6 +82,10 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic op for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
@@ -675,15 +679,18 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
 // transaction bytes land on the leader's mbarriers), and tcgen05.commit multicasts "stage free" / "accumulator
 // ready" to both.
 static const int kConv3Threads = 64 + 256;
+template <int BN_, int MT_>
 struct Conv3Cfg {
-  static const int BN = 256;
-  static const int kARows = kBM + 8;
-  static const int kAStage = kARows * 128;       // 17408 B
-  static const int kAStages = 4;
-  static const int kBStage = (BN / 2) * 128;     // this CTA's half of the weight tile: 16384 B
+  static const int BN = BN_, MT = MT_;
+  static const int kARows = MT * kBM + 8;          // this CTA's MT m-tiles + halo
+  static const int kABoxes = (MT == 4) ? 5 : (MT == 2 ? 3 : 1);
+  static const int kABoxRows = kARows / kABoxes;   // 104 / 88 / 136
+  static const int kAStage = kARows * 128;
+  static const int kAStages = (MT == 4) ? 2 : (MT == 2 ? 3 : 4);
+  static const int kBStage = (BN / 2) * 128;       // this CTA's half of the weight tile
   static const int kBStages = 8;
   static const int kSmem = kAStages * kAStage + kBStages * kBStage + 1024;
-  static const int kTmemCols = 512;              // two 256-column accumulators
+  static const int kTmemCols = 2 * MT * BN;        // 512 for (256,1), (128,2), (64,4)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -725,12 +732,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
+template <int BN, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
               int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
-  using Cfg = Conv3Cfg;
-  constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages, BN = Cfg::BN;
+  using Cfg = Conv3Cfg<BN, MT>;
+  constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + AST * Cfg::kAStage;
@@ -768,13 +776,17 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile / num_n_tiles) * (2 * kBM) + (int)rank * kBM;
+        const int m0 = (tile / num_n_tiles) * (2 * MT * kBM) + (int)rank * (MT * kBM);
         const int n0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);
         for (int kc = 0; kc < KC; ++kc)
           for (int ky = 0; ky < 3; ++ky) {
             mbar_wait(&a_empty[as], aph ^ 1);
             if (rank == 0) mbar_expect_tx(&a_full[as], 2 * Cfg::kAStage);
-            tma_load_2d_pair(&tmA, &a_full[as], smem + as * Cfg::kAStage, kc * 64, m0 + (ky - 1) * Wp - 1);
+            const int row0 = m0 + (ky - 1) * Wp - 1;
+#pragma unroll
+            for (int bx = 0; bx < Cfg::kABoxes; ++bx)
+              tma_load_2d_pair(&tmA, &a_full[as], smem + as * Cfg::kAStage + bx * Cfg::kABoxRows * 128, kc * 64,
+                               row0 + bx * Cfg::kABoxRows);
             if (++as == AST) { as = 0; aph ^= 1; }
             for (int kx = 0; kx < 3; ++kx) {
               mbar_wait(&b_empty[bs], bph ^ 1);
@@ -799,7 +811,7 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         uint32_t first = 1;
         for (int it = 0; it < 3 * KC; ++it) {
           mbar_wait(&a_full[as], aph);
@@ -811,9 +823,11 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint32_t b_lo0 = desc_lo(sb_base + bs * Cfg::kBStage, 16);
             if (leader) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_lh_pair(d_tmem, a_lo0 + (uint32_t)(kx * 8 + k * 2), hi, b_lo0 + (uint32_t)(k * 2), hi, idesc,
-                                  (first && kx == 0 && k == 0) ? 0u : 1u);
+              for (int t = 0; t < MT; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_lh_pair(d_tmem + t * BN, a_lo0 + (uint32_t)((t * kBM + kx) * 8 + k * 2), hi,
+                                    b_lo0 + (uint32_t)(k * 2), hi, idesc, (first && kx == 0 && k == 0) ? 0u : 1u);
               umma_commit_pair(&b_empty[bs]);
             }
             __syncwarp();
@@ -834,7 +848,7 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // ===== epilogue (both CTAs, own 128 rows): as in version 2 =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int NCH = BN / 32, NST = NCH / 2;
+    constexpr int NCH = BN / 32, NITEMS = MT * NCH, NST = NCH / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const long long HWp = (long long)(H + 2) * Wp;
@@ -854,23 +868,25 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     };
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const long long m = (long long)(tile / num_n_tiles) * (2 * kBM) + (long long)rank * kBM + q * 32 + lane;
+      const long long mbase = (long long)(tile / num_n_tiles) * (2 * MT * kBM) + (long long)rank * (MT * kBM) + q * 32 + lane;
       const int n0 = (tile % num_n_tiles) * BN;
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
-      bool valid = m < Mp;
-      bf16* optr = nullptr;
-      if (valid) {
-        const long long b = m / HWp;
-        const int r = (int)(m - b * HWp);
-        const int yp = r / Wp, xp = r - yp * Wp;
-        valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
-        optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll
-      for (int chh = 0; chh < NST; ++chh) {
+      for (int it = 0; it < NITEMS / 2; ++it) {
+        const int t = it / NST, chh = it % NST;
+        const long long m = mbase + t * kBM;
+        bool valid = m < Mp;
+        bf16* optr = nullptr;
+        if (valid) {
+          const long long b = m / HWp;
+          const int r = (int)(m - b * HWp);
+          const int yp = r / Wp, xp = r - yp * Wp;
+          valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
+          optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
         const int c0 = (2 * chh + half) * 32;
         uint32_t v[32];
         tmem_ld32(t_row + c0, v);
@@ -932,29 +948,30 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+template <int BN, int MT>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
                         long long Mp, double* stats, int relu_stats, cudaStream_t s) {
-  using Cfg = Conv3Cfg;
+  using Cfg = Conv3Cfg<BN, MT>;
   static bool configured = false;
   if (!configured) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured = true;
   }
   CUtensorMap tmA, tmB;
-  if (make_tmap(&tmA, in, Cin, Mp, Cfg::kARows)) return -1;
+  if (make_tmap(&tmA, in, Cin, Mp, Cfg::kABoxRows)) return -1;
   if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, Cfg::BN / 2)) return -1;
-  const int num_mp = (int)((Mp + 2 * kBM - 1) / (2 * kBM)), num_n = Cout / Cfg::BN;
+  const int num_mp = (int)((Mp + 2 * MT * kBM - 1) / (2 * MT * kBM)), num_n = Cout / Cfg::BN;
   long long tiles = (long long)num_mp * num_n;
   int pairs = (int)(tiles < 74 ? tiles : 74);
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
-  k_conv3x3_tc3<<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n, stats,
+  k_conv3x3_tc3<BN, MT><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n, stats,
                                                             relu_stats);
   L3_CHECK_LAUNCH();
   return 0;
 }
 
-// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions, 3 = version 2 + CTA pairs
-// (cta_group::2) for the N = 256 layers (default).  (Measured on B200: the
+// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions, 3 = shared-halo regions on CTA
+// pairs (cta_group::2; default).  (Measured on B200: the
 // descriptor "base offset" field must stay 0 for row-shifted starts -- the swizzle is applied to absolute
 // shared-memory address bits; setting the field to (addr >> 7) & 7 produces wrong results.)
 static int conv_variant() {
@@ -977,7 +994,11 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   const int variant = conv_variant();
   if (variant >= 2) {
-    if (BN == 256 && variant == 3) return launch_conv3(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+    if (variant == 3) {
+      if (BN == 256) return launch_conv3<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+      if (BN == 128) return launch_conv3<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+      return launch_conv3<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+    }
     if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
@@ -1126,7 +1147,9 @@ k_wgrad3x3_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_ld_wait();
         if (!dup) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                       __uint_as_float(v[i + 3]));
         }
       }
     }
@@ -1281,7 +1304,9 @@ k_wgrad3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (!dup) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                       __uint_as_float(v[i + 3]));
         }
       }
     }
@@ -1342,24 +1367,34 @@ static const int kFwStages = 4;
 static const int kFwThreads = 64 + 256;
 static const int kFwTile = 64 * 128;   // bytes: A tile and dz tile
 
-template <int C0>
-__device__ __forceinline__ void fw_build_chunk(uint8_t* __restrict__ tile, int row, int q, const bf16* __restrict__ xin,
-                                               long long m, long long Mp, int yp, int xp, int H, int W) {
+// one 16-byte column chunk Q (columns 8Q .. 8Q+7) of pixel row `row`; Q is a template parameter so tap / channel /
+// address offsets of every column fold to constants.  `safe`: all nine taps of this row lie inside the buffer.
+template <int C0, int Q>
+__device__ __forceinline__ void fw_build_chunk(uint8_t* __restrict__ tile, int row, const bf16* __restrict__ xin,
+                                               long long m, long long Mp, bool safe, int yp, int xp, int H, int W) {
   constexpr int K = 9 * C0;
   const int Wp = W + 2;
+  const bf16* centre = xin + m * C0;
   uint32_t pk[4];
 #pragma unroll
   for (int e = 0; e < 8; e += 2) {
     float v[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int i = q * 8 + e + u;   // column index (q is warp-uniform; the branches below do not diverge)
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int i = Q * 8 + e + u;   // compile-time after unrolling
       float val = 0.f;
       if (m < Mp) {
         if (i < K) {
           const int tap = i / C0, c = i - tap * C0;
-          const long long idx = m + (tap / 3 - 1) * Wp + (tap % 3 - 1);
-          if (idx >= 0 && idx < Mp) val = __bfloat162float(xin[idx * C0 + c]);
+          const int off = ((tap / 3 - 1) * Wp + (tap % 3 - 1)) * C0 + c;
+          if (safe) {
+            val = __bfloat162float(centre[off]);
+          } else {
+            const long long idx = m + (tap / 3 - 1) * Wp + (tap % 3 - 1);
+            if (idx >= 0 && idx < Mp) val = __bfloat162float(centre[off]);
+          }
         } else if (i < K + 9) {
           const int tap = i - K;
           const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
@@ -1372,7 +1407,7 @@ __device__ __forceinline__ void fw_build_chunk(uint8_t* __restrict__ tile, int r
     }
     pk[e >> 1] = pack_bf16x2(v[0], v[1]);
   }
-  *reinterpret_cast<uint4*>(tile + row * 128 + ((q ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((Q ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 template <int C0>
@@ -1460,10 +1495,25 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
         yp = r / Wp;
         xp = r - yp * Wp;
       }
+      const bool safe = (m >= Wp + 1) && (m + Wp + 1 < Mp);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* tile = smem + stage * 2 * kFwTile;
-      if (part < NQ) fw_build_chunk<C0>(tile, row, part, xin, m, Mp, yp, xp, H, W);
-      if (part + 4 < NQ) fw_build_chunk<C0>(tile, row, part + 4, xin, m, Mp, yp, xp, H, W);
+      // `part` is warp-uniform (two builder warps per part): the switch does not diverge
+      switch (part) {
+        case 0:
+          fw_build_chunk<C0, 0>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          if (NQ > 4) fw_build_chunk<C0, 4>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          break;
+        case 1:
+          fw_build_chunk<C0, 1>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          break;
+        case 2:
+          fw_build_chunk<C0, 2>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          break;
+        default:
+          if (NQ > 3) fw_build_chunk<C0, 3>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          break;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
@@ -1484,9 +1534,14 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
         if (r < K) dst = dw + r * 64;
         else if (r < K + 9) dst = d1 ? d1 + (r - K) * 64 : nullptr;
         else if (r == K + 9) dst = db;
-        if (dst) {
+        if (dst && r == K + 9) {   // the bias-gradient vector sits at an arbitrary (4-byte aligned) arena offset
 #pragma unroll
           for (int i = 0; i < 32; ++i) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+        } else if (dst) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                       __uint_as_float(v[i + 3]));
         }
       }
     }
