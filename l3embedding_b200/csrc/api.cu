@@ -166,6 +166,7 @@ struct Tower {
   void* xin;    // padded T
   ConvLayer L[8];
   int* argmax;  // (B,512)
+  unsigned long long* pool_scratch;  // (B,512) packed (value, ~index) keys of the global max-pool
   float* d1;    // 9*64 floats + 1 int flag: first-layer "ones" weight gradient for the input-BN backward
   int concat_off;
 };
@@ -309,6 +310,7 @@ static long long carve(l3_ctx* c) {
       H = OH; W = OW;
     }
     tw.argmax = (int*)bp.take(4 * B * 512);
+    tw.pool_scratch = (unsigned long long*)bp.take(8 * B * 512);
     tw.d1 = (float*)bp.take(4 * (9 * 64 + 4));
   }
   c->g0 = training ? bp.take(es * g0_max) : nullptr;
@@ -430,7 +432,7 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
     } else {
       // MaxPooling2D over the whole final map + Flatten (audio_model.py:436-437, vision_model.py:189-190)
       if (launch_gmaxpool_fwd<T>((const T*)L.z, B, L.H * L.W, L.Cout, L.bn.scale, L.bn.shift,
-                                 c->head.concat + tw.concat_off, 1024, tw.argmax, s))
+                                 c->head.concat + tw.concat_off, 1024, tw.argmax, tw.pool_scratch, s))
         return -1;
     }
   }
@@ -497,7 +499,10 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       }
       break;
     }
-    // data gradient: da = conv(dz, flip/transpose(w))
+    // data gradient: da = conv(dz, flip/transpose(w)).  (Fusing pass 1 of the BN/ReLU backward of the layer below into
+    // this kernel's epilogue was tried and measured SLOWER -- +1.7 ms per step: the extra z loads and the second
+    // transposing reduction make the epilogue, not the MMA pipe, the critical path of every dgrad launch.)
+    ConvLayer& Lp = tw.L[l - 1];
     {
       ProfScope ps(c, PROF_CONV_DGRAD);
       if (L.tc && c->use_tc) {
@@ -508,7 +513,6 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       }
     }
     // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz (padded, full resolution)
-    ConvLayer& Lp = tw.L[l - 1];
     long long rows_p = (long long)B * Lp.H * Lp.W;
     if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
     if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;

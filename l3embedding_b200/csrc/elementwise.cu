@@ -240,9 +240,11 @@ k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int O
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sh);
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-    const int ox = (int)(p % OW);
-    const int oy = (int)((p / OW) % OH);
-    const long long b = p / ((long long)OW * OH);
+    // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
+    const unsigned pr = (unsigned)p / (unsigned)OW;
+    const int ox = (int)((unsigned)p - pr * (unsigned)OW);
+    const long long b = pr / (unsigned)OH;
+    const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
     float y[8];
     if (!pool) {
       float v[8];
@@ -275,6 +277,7 @@ int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* sc
   L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "act_fwd: C=%d", C);
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
+  L3_REQUIRE(npix < 0x7fffffffLL, "act_fwd: too many pixels");
   int lanes = kThreads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
@@ -288,23 +291,24 @@ template int launch_act_fwd<bf16>(const bf16*, bf16*, int, int, int, int, const 
 // --------------------------------------------------------------------------------------------
 // global max-pool forward over relu(bn(z)) -> (B,C) float + argmax pixel (first max in row-major order)
 // --------------------------------------------------------------------------------------------
+// Stage 1: grid (B, slices); every block reduces its pixel slice per channel and merges with a 64-bit atomicMax of
+// (value bits << 32 | ~pixel index): values are relu outputs (>= 0, so their bit patterns order like the floats) and
+// among equal values the smallest pixel index wins (first maximum in row-major order, like keras/TF max-pool).
 template <typename T>
 __global__ void k_gmaxpool_fwd(const T* __restrict__ z, int HW, int C, const float* __restrict__ scale,
-                               const float* __restrict__ shift, float* __restrict__ out, int out_stride,
-                               int* __restrict__ argmax) {
-  extern __shared__ float shm[];  // lanes*C floats + lanes*C ints
+                               const float* __restrict__ shift, unsigned long long* __restrict__ best_out) {
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   const int b = blockIdx.x;
-  float* smax = shm;
-  int* sidx = reinterpret_cast<int*>(shm + lanes * C);
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(HW, p0 + per);
   float sc[8], sh[8], best[8];
   int bi[8];
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sh);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
-  for (int p = lane; p < HW; p += lanes) {
+  for (int i = 0; i < 8; ++i) { best[i] = -1.f; bi[i] = 0; }
+  for (int p = p0 + lane; p < p1; p += lanes) {
     float v[8], y[8];
     load8(z + ((long long)b * HW + p) * C + g * 8, v);
     act8(v, sc, sh, 0, y);
@@ -313,32 +317,38 @@ __global__ void k_gmaxpool_fwd(const T* __restrict__ z, int HW, int C, const flo
       if (y[i] > best[i]) { best[i] = y[i]; bi[i] = p; }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { smax[lane * C + g * 8 + i] = best[i]; sidx[lane * C + g * 8 + i] = bi[i]; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float m = smax[c];
-    int mi = sidx[c];
-    for (int l = 1; l < lanes; ++l) {
-      float v = smax[l * C + c];
-      int vi = sidx[l * C + c];
-      if (v > m || (v == m && vi < mi)) { m = v; mi = vi; }
+  for (int i = 0; i < 8; ++i) {
+    if (best[i] >= 0.f) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(best[i]) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)bi[i]);
+      atomicMax(&best_out[(long long)b * C + g * 8 + i], key);
     }
-    out[(long long)b * out_stride + c] = m;
-    argmax[b * C + c] = mi;
   }
+}
+__global__ void k_gmaxpool_fwd_finish(const unsigned long long* __restrict__ best, int n, int C, float* __restrict__ out,
+                                      int out_stride, int* __restrict__ argmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = best[i];
+  out[(long long)(i / C) * out_stride + (i % C)] = __uint_as_float((unsigned)(key >> 32));
+  argmax[i] = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
 }
 template <typename T>
 int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, const float* shift, float* out,
-                        int out_stride, int* argmax, cudaStream_t s) {
+                        int out_stride, int* argmax, unsigned long long* scratch, cudaStream_t s) {
   L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "gmaxpool: C=%d", C);
-  int lanes = kThreads / (C / 8);
-  size_t sm = (size_t)lanes * C * 8;
-  k_gmaxpool_fwd<T><<<B, kThreads, sm, s>>>(z, HW, C, scale, shift, out, out_stride, argmax);
+  L3_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * (size_t)B * C, s));
+  int slices = (148 * 4 + B - 1) / B;
+  if (slices > 16) slices = 16;
+  if (slices < 1) slices = 1;
+  dim3 grid(B, slices);
+  k_gmaxpool_fwd<T><<<grid, kThreads, 0, s>>>(z, HW, C, scale, shift, scratch);
+  L3_CHECK_LAUNCH();
+  k_gmaxpool_fwd_finish<<<ceil_div((long long)B * C, 256), 256, 0, s>>>(scratch, B * C, C, out, out_stride, argmax);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_gmaxpool_fwd<float>(const float*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
-template int launch_gmaxpool_fwd<bf16>(const bf16*, int, int, int, const float*, const float*, float*, int, int*, cudaStream_t);
+template int launch_gmaxpool_fwd<float>(const float*, int, int, int, const float*, const float*, float*, int, int*, unsigned long long*, cudaStream_t);
+template int launch_gmaxpool_fwd<bf16>(const bf16*, int, int, int, const float*, const float*, float*, int, int*, unsigned long long*, cudaStream_t);
 
 // global max-pool backward: dy = scatter(dpool) masked by relu, plus the BN-backward sums.  One thread per
 // (sample, channel); the per-channel sums go through double atomics (B values per channel).
@@ -438,9 +448,10 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
     for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += stride) {
       float g8[8], zs[8], m[8];
       load8(da + p * C + g * 8, g8);
-      const int ox = (int)(p % OW);
-      const int oy = (int)((p / OW) % OH);
-      const long long b = p / ((long long)OW * OH);
+      const unsigned pr = (unsigned)p / (unsigned)OW;
+      const int ox = (int)((unsigned)p - pr * (unsigned)OW);
+      const long long b = pr / (unsigned)OH;
+      const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
       const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
       float v1[8], v2[8], v3[8], y[8];
       load8(z00, zs);
@@ -536,9 +547,11 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-    const int ox = (int)(p % OW);
-    const int oy = (int)((p / OW) % OH);
-    const long long b = p / ((long long)OW * OH);
+    // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
+    const unsigned pr = (unsigned)p / (unsigned)OW;
+    const int ox = (int)((unsigned)p - pr * (unsigned)OW);
+    const long long b = pr / (unsigned)OH;
+    const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
     float g8[8];
     load8(da + p * C + g * 8, g8);
     if (!POOL) {

@@ -48,7 +48,7 @@ int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* sc
                    int relu_first, cudaStream_t s);
 template <typename T>
 int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, const float* shift, float* out,
-                        int out_stride, int* argmax, cudaStream_t s);
+                        int out_stride, int* argmax, unsigned long long* scratch /* B*C */, cudaStream_t s);
 template <typename T>
 int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax, const T* z, T* dy, const BnRef& bn,
                         int B, int H, int W, int C, cudaStream_t s);   // dy: padded
