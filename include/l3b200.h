@@ -98,6 +98,10 @@ int l3_embed_vision(l3_ctx* ctx, const void* video, int video_fmt, int n, float*
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------- */
 /* kernel launches issued by this library in the calling process since it was loaded */
 uint64_t l3_launch_count(void);
+/* The two towers are independent until the head; by default the audio tower's kernels run on a second internal
+ * stream (forked from / joined to the context stream with events) so HBM-bound kernels of one tower overlap
+ * tensor-core kernels of the other.  0 serialises everything on the context stream (used for per-kernel timing). */
+int l3_ctx_set_two_streams(l3_ctx* ctx, int enable);
 /* optional CUDA-event timing of the convolution / front-end launches on the ctx stream.  l3_ctx_profile_read
  * synchronises and returns the milliseconds and launch counts accumulated since the previous read, per class:
  * [0] conv forward, [1] conv dgrad, [2] conv wgrad, [3] audio front-end. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "l3_conv3x3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "l3_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "l3_launch_count": (C.c_uint64, []),
+    "l3_ctx_set_two_streams": (_i, [_vp, _i]),
     "l3_ctx_profile_enable": (_i, [_vp, _i]),
     "l3_ctx_profile_read": (_i, [_vp, _fp, C.POINTER(_i)]),
     "l3_debug_read": (_i64, [_vp, C.c_char_p, _i, _fp, _i64]),

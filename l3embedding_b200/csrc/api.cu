@@ -169,6 +169,8 @@ struct Tower {
   unsigned long long* pool_scratch;  // (B,512) packed (value, ~index) keys of the global max-pool
   float* d1;    // 9*64 floats + 1 int flag: first-layer "ones" weight gradient for the input-BN backward
   int concat_off;
+  void *g0, *g1;         // backward ping-pong of this tower: padded dz / unpadded da
+  cudaStream_t stream;   // stream this tower's kernels are launched on (set by the caller of tower_*)
 };
 
 }  // namespace l3
@@ -189,7 +191,11 @@ struct l3_ctx {
   Tower vision, audio;
   HeadRef head;
   double* l2_out;
-  void *g0, *g1;  // backward ping-pong: padded dz / unpadded da
+  // the two towers are independent until the head: the audio tower runs on a second stream so its HBM-bound
+  // kernels overlap the vision tower's tensor-core kernels (and vice versa)
+  cudaStream_t stream2;
+  cudaEvent_t ev_fork, ev_join;
+  int two_streams;
   // host staging
   void *st_video, *st_audio;
   float* st_labels;
@@ -211,7 +217,8 @@ enum { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_FRONTEN
 struct ProfScope {
   l3_ctx* c;
   cudaEvent_t stop;
-  ProfScope(l3_ctx* ctx, int cls) : c(ctx), stop(nullptr) {
+  cudaStream_t st;
+  ProfScope(l3_ctx* ctx, int cls, cudaStream_t stream) : c(ctx), stop(nullptr), st(stream) {
     if (!c->prof_on) return;
     if (c->prof_used * 2 + 2 > c->prof_ev.size()) {
       cudaEvent_t a, b;
@@ -222,12 +229,12 @@ struct ProfScope {
       c->prof_cls.push_back(cls);
     }
     c->prof_cls[c->prof_used] = cls;
-    cudaEventRecord(c->prof_ev[c->prof_used * 2], c->stream);
+    cudaEventRecord(c->prof_ev[c->prof_used * 2], st);
     stop = c->prof_ev[c->prof_used * 2 + 1];
     c->prof_used++;
   }
   ~ProfScope() {
-    if (stop) cudaEventRecord(stop, c->stream);
+    if (stop) cudaEventRecord(stop, st);
   }
 };
 
@@ -272,8 +279,8 @@ static long long carve(l3_ctx* c) {
     c->st_video = c->st_audio = nullptr;
     c->st_labels = nullptr;
   }
-  long long g0_max = 0, g1_max = 0;
   for (int t = 0; t < 2; ++t) {
+    long long g0_max = 0, g1_max = 0;
     Tower& tw = t == 0 ? c->vision : c->audio;
     tw.present = (c->flags & (t == 0 ? L3_WS_VISION : L3_WS_AUDIO)) ? 1 : 0;
     tw.C0 = t == 0 ? 3 : 1;
@@ -312,9 +319,9 @@ static long long carve(l3_ctx* c) {
     tw.argmax = (int*)bp.take(4 * B * 512);
     tw.pool_scratch = (unsigned long long*)bp.take(8 * B * 512);
     tw.d1 = (float*)bp.take(4 * (9 * 64 + 4));
+    tw.g0 = training ? bp.take(es * g0_max) : nullptr;
+    tw.g1 = training ? bp.take(es * g1_max) : nullptr;
   }
-  c->g0 = training ? bp.take(es * g0_max) : nullptr;
-  c->g1 = training ? bp.take(es * g1_max) : nullptr;
   HeadRef& h = c->head;
   h.concat = (float*)bp.take(4 * B * 1024);
   h.hidden = (float*)bp.take(4 * B * 128);
@@ -371,29 +378,29 @@ static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm 
 
 // want_stats: training-mode BN statistics of the output; *stats_done tells the caller they were fused
 template <typename T>
-static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done) {
-  ProfScope ps(c, PROF_CONV_FWD);
+static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done, cudaStream_t s) {
+  ProfScope ps(c, PROF_CONV_FWD, s);
   *stats_done = false;
   if (L.tc && c->use_tc) {
     const bool fuse = want_stats && conv_tc_fuses_stats();
     *stats_done = fuse;
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
-                             fuse ? L.bn.sum : nullptr, L.relu_first, c->stream);
+                             fuse ? L.bn.sum : nullptr, L.relu_first, s);
   }
   if (L.Cin <= 3 && L.Cout == 64) {
     *stats_done = want_stats;
     return launch_first_conv<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout,
-                                want_stats ? L.bn.sum : nullptr, c->stream);
+                                want_stats ? L.bn.sum : nullptr, s);
   }
-  return launch_conv3x3_simt<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, c->stream);
+  return launch_conv3x3_simt<T>((const T*)L.in, L.w, L.b, (T*)L.z, B, L.H, L.W, L.Cin, L.Cout, s);
 }
 
 // input: raw (device) video or audio -> x0 -> (input BN) -> xin
 template <typename T>
 static int tower_input(l3_ctx* c, Tower& tw, bool is_audio, const void* src, int fmt, int B, bool training) {
-  cudaStream_t s = c->stream;
+  cudaStream_t s = tw.stream;
   if (is_audio) {
-    ProfScope ps(c, PROF_FRONTEND);
+    ProfScope ps(c, PROF_FRONTEND, s);
     if (launch_frontend(c->fe, src, fmt == L3_AUDIO_I16, B, tw.x0, c->clip_max, s)) return -1;
   } else {
     long long n = (long long)B * 224 * 224 * 3;
@@ -417,11 +424,11 @@ static int tower_input(l3_ctx* c, Tower& tw, bool is_audio, const void* src, int
 // n_layers_act: layers [0, 7) always activate into the next input; the last conv's z is the embedding tap
 template <typename T>
 static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_only) {
-  cudaStream_t s = c->stream;
+  cudaStream_t s = tw.stream;
   for (int l = 0; l < 8; ++l) {
     ConvLayer& L = tw.L[l];
     bool stats_done = false;
-    if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done)) return -1;
+    if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done, s)) return -1;
     if (l == 7 && embed_only) return 0;  // raw conv4b output incl. bias, before BN/ReLU (audio_model.py:482)
     long long rows = (long long)B * L.H * L.W;
     if (training && !stats_done && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
@@ -450,9 +457,9 @@ static bool first_wgrad_tc_enabled() {
 
 template <typename T>
 static int tower_backward(l3_ctx* c, Tower& tw, int B) {
-  cudaStream_t s = c->stream;
-  T* dz = (T*)c->g0;
-  T* da = (T*)c->g1;
+  cudaStream_t s = tw.stream;
+  T* dz = (T*)tw.g0;
+  T* da = (T*)tw.g1;
   {
     ConvLayer& L = tw.L[7];
     if (launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, dz, L.bn, B, L.H, L.W,
@@ -469,7 +476,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     }
     // weight / bias gradient
     {
-      ProfScope ps(c, PROF_CONV_WGRAD);
+      ProfScope ps(c, PROF_CONV_WGRAD, s);
       if (L.tc && c->use_tc) {
         // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
         // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
@@ -491,7 +498,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     if (l == 0) {
       if (tw.has_bn0) {
         // input BN: d_gamma / d_beta need only sum(da), sum(da*xhat) -- computed without storing da
-        ProfScope ps(c, PROF_CONV_DGRAD);
+        ProfScope ps(c, PROF_CONV_DGRAD, s);
         int* fallback = reinterpret_cast<int*>(tw.d1 + 9 * 64);
         if (launch_bn0_from_dw(L.w, L.dw, tw.d1, tw.bn0, L.Cin, fallback, s)) return -1;
         if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, fallback, s)) return -1;
@@ -504,7 +511,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     // transposing reduction make the epilogue, not the MMA pipe, the critical path of every dgrad launch.)
     ConvLayer& Lp = tw.L[l - 1];
     {
-      ProfScope ps(c, PROF_CONV_DGRAD);
+      ProfScope ps(c, PROF_CONV_DGRAD, s);
       if (L.tc && c->use_tc) {
         if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
       } else {
@@ -539,14 +546,33 @@ static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad)
   return launch_pack_weights_batch(pb, c->stream);
 }
 
+// audio tower on stream2 between fork() and join(); everything else on the caller's stream
+static int fork_streams(l3_ctx* c) {
+  c->vision.stream = c->stream;
+  c->audio.stream = c->two_streams ? c->stream2 : c->stream;
+  if (!c->two_streams) return 0;
+  L3_CHECK_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+  L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  return 0;
+}
+static int join_streams(l3_ctx* c) {
+  if (!c->two_streams) return 0;
+  L3_CHECK_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+  L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  return 0;
+}
+
 template <typename T>
 static int forward_all(l3_ctx* c, const void* video, int vfmt, const void* audio, int afmt, const float* labels, int B,
                        bool training, float grad_scale) {
   if (pack_all_weights(c, true, true, training)) return -1;
+  if (fork_streams(c)) return -1;
+  // interleave the two towers' launches so neither stream starves while the host is still enqueuing the other
   if (tower_input<T>(c, c->vision, false, video, vfmt, B, training)) return -1;
-  if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
   if (tower_input<T>(c, c->audio, true, audio, afmt, B, training)) return -1;
+  if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
   if (tower_forward<T>(c, c->audio, B, training, false)) return -1;
+  if (join_streams(c)) return -1;
   return launch_head_fwd(c->head, labels, B, grad_scale, c->stream);
 }
 
@@ -687,6 +713,21 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->last_batch = 0;
   c->prof_on = 0;
   c->prof_used = 0;
+  c->vision.stream = c->audio.stream = c->stream;
+  c->stream2 = nullptr;
+  {
+    const char* e = getenv("L3_TWO_STREAMS");
+    c->two_streams = e ? atoi(e) : 1;
+    if (c->two_streams) {
+      if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("could not create the second stream: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+      }
+    }
+  }
   carve(c);
   bind_params(c);
   // zero the workspace once: the halos of every fixed-geometry padded activation buffer stay zero forever
@@ -710,10 +751,28 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
 void l3_ctx_destroy(l3_ctx* ctx) {
   if (!ctx) return;
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+  if (ctx->stream2) {
+    cudaStreamSynchronize(ctx->stream2);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream2);
+  }
   delete ctx;
 }
 
 uint64_t l3_launch_count(void) { return g_launch_count; }
+
+int l3_ctx_set_two_streams(l3_ctx* c, int enable) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  if (enable && !c->stream2) {
+    L3_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  c->two_streams = enable ? 1 : 0;
+  return 0;
+}
 
 int l3_ctx_profile_enable(l3_ctx* c, int enable) {
   L3_REQUIRE(c != nullptr, "null ctx");
@@ -791,13 +850,17 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
   if (c->dtype == L3_DTYPE_BF16) {
     rc = forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc) rc = fork_streams(c);
     if (!rc) rc = tower_backward<bf16>(c, c->vision, batch);
     if (!rc) rc = tower_backward<bf16>(c, c->audio, batch);
+    if (!rc) rc = join_streams(c);
   } else {
     rc = forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc) rc = fork_streams(c);
     if (!rc) rc = tower_backward<float>(c, c->vision, batch);
     if (!rc) rc = tower_backward<float>(c, c->audio, batch);
+    if (!rc) rc = join_streams(c);
   }
   c->last_batch = batch;
   return rc;
@@ -865,6 +928,7 @@ int l3_embed_audio(l3_ctx* c, const void* audio, int audio_fmt, int n, int pooli
   L3_REQUIRE(pooling == L3_POOL_ORIGINAL || pooling == L3_POOL_SHORT, "bad pooling %d", pooling);
   L3_REQUIRE(audio && out, "null argument");
   Tower& tw = c->audio;
+  tw.stream = c->stream;
   const int ph = c->spec.embed_pool[pooling][0], pw = c->spec.embed_pool[pooling][1];
   ConvLayer& L = tw.L[7];
   if (pack_all_weights(c, false, true, false)) return -1;
@@ -905,6 +969,7 @@ int l3_embed_vision(l3_ctx* c, const void* video, int video_fmt, int n, float* o
   L3_REQUIRE(c->vision.present, "context lacks the vision tower");
   L3_REQUIRE(video && out, "null argument");
   Tower& tw = c->vision;
+  tw.stream = c->stream;
   ConvLayer& L = tw.L[7];
   if (pack_all_weights(c, true, false, false)) return -1;
   if (c->dtype == L3_DTYPE_BF16) {

@@ -499,14 +499,17 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
 template <typename T>
 int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const BnRef& bn, int pool, int relu_first,
                      cudaStream_t s) {
-  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "bwd_stats: C=%d", C);
+  // The 2x2-pool variants need ~128 registers: in 128-thread blocks (16 K registers) they still fit next to a resident
+  // tensor-core CTA (38 K registers) of the other tower's stream; a 256-thread block would not.
+  const int threads = pool ? 128 : kThreads;
+  L3_REQUIRE(C % 8 == 0 && threads % (C / 8) == 0, "bwd_stats: C=%d", C);
   L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
-  int lanes = kThreads / (C / 8);
+  int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
   int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_stats<T, true><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
+  if (pool) k_bwd_stats<T, true><<<blocks, threads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   else k_bwd_stats<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
@@ -615,14 +618,15 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
                      int relu_first, cudaStream_t s) {
-  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "bwd_apply: C=%d", C);
+  const int threads = pool ? 128 : kThreads;   // see launch_bwd_stats
+  L3_REQUIRE(C % 8 == 0 && threads % (C / 8) == 0, "bwd_apply: C=%d", C);
   if (launch_zero_halo<T>(dz, B, H, W, C, s)) return -1;
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
-  int lanes = kThreads / (C / 8);
+  int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_apply<T, true><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;

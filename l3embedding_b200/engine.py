@@ -264,6 +264,10 @@ class Engine:
         _lib.check(int(n), "l3_debug_read(%s)" % which)
         return buf[:n].copy()
 
+    def set_two_streams(self, enable: bool):
+        """Overlap the two towers on two streams (default) or serialise them (per-kernel timing)."""
+        _lib.check(self.lib.l3_ctx_set_two_streams(self.ctx, int(bool(enable))), "l3_ctx_set_two_streams")
+
     def profile(self, enable: bool):
         _lib.check(self.lib.l3_ctx_profile_enable(self.ctx, int(bool(enable))), "l3_ctx_profile_enable")
 
