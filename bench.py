@@ -49,6 +49,11 @@ def conv_class_gflop_per_pair():
     return {"conv_fwd": t, "conv_dgrad": t, "conv_wgrad": t}
 
 
+# DRAM bytes (read + write) per training step at B=64, summed over the launches of each convolution class, from ONE
+# `ncu --set full --clock-control none` capture of a whole step (profiles/r1_ncu_full_conv_step.txt)
+NCU_DRAM_BYTES_PER_STEP_B64 = {"conv_fwd": 4336.0e6, "conv_dgrad": 3753.7e6, "conv_wgrad": 5448.2e6}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU during the timed region (NVML; nvidia-smi fallback)."""
 
@@ -281,7 +286,10 @@ def main_gpu(args):
                             "pinned host batch -> H2D -> Engine.forward_backward -> NCCL all-reduce -> metrics D2H -> adam")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_tf,
+                         "traffic": (NCU_DRAM_BYTES_PER_STEP_B64[dom] if (B == 64 and args.dtype == "bf16") else None),
+                         "traffic_unit": "DRAM bytes per step for the class (ncu, profiles/r1_ncu_full_conv_step.txt)",
+                         "peak_source": peak_src,
                          "whole_step_frac": value * TRAIN_GFLOP / 1e3 / world / peak_tf,
                          "serial_ms_per_step": ms_serial / prof_steps,
                          "note": "kernel classes timed with CUDA events on the library stream in a pass with the two "
