@@ -116,6 +116,11 @@ int l3_frontend_fwd(l3_ctx* ctx, const void* audio, int audio_fmt, int n, float*
  * scratch then holds the packed weights (>= 2*9*Cin*Cout bytes). */
 int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
                    int Cout, int dtype, int use_tc, void* scratch, void* stream);
+/* the tensor-core forward with its fused BatchNorm batch statistics (what the training step runs): as l3_conv3x3_fwd
+ * with dtype bf16 / use_tc 1 (Cin 1|3 with Cout 64, or Cin%64==0 and Cout%64==0), plus stats: device double[2*Cout]
+ * <- per-channel sum and sum of squares of the stored bf16 output (of relu(output) if relu_stats; Cin%64 layers only). */
+int l3_conv3x3_fwd_stats(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                         int Cout, void* scratch, double* stats, int relu_stats, void* stream);
 /* data gradient of the same conv: dz zero-haloed padded (B,H+2,W+2,Cout) -> da unpadded (B,H,W,Cin);
  * scratch >= 9*Cin*Cout floats. */
 int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,

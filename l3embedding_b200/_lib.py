@@ -50,6 +50,7 @@ SIGNATURES = {
     "l3_embed_vision": (_i, [_vp, _vp, _i, _i, _vp]),
     "l3_frontend_fwd": (_i, [_vp, _vp, _i, _i, _vp]),
     "l3_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "l3_conv3x3_fwd_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "l3_conv3x3_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "l3_conv3x3_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "l3_launch_count": (C.c_uint64, []),

@@ -376,6 +376,16 @@ static void bind_params(l3_ctx* c) {
 static const float kBnMomentum = 0.99f, kBnEps = 1e-3f;  // keras BatchNormalization defaults
 static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm feeds the Bessel-corrected variance
 
+// L3_FIRST_CONV_TC=0 keeps the SIMT first-layer forward in bf16 mode (A/B checks)
+static bool first_conv_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_FIRST_CONV_TC");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 // want_stats: training-mode BN statistics of the output; *stats_done tells the caller they were fused
 template <typename T>
 static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done, cudaStream_t s) {
@@ -386,6 +396,11 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* s
     *stats_done = fuse;
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
                              fuse ? L.bn.sum : nullptr, L.relu_first, s);
+  }
+  if (L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16 && first_conv_tc_enabled()) {
+    *stats_done = want_stats;
+    return launch_first_conv_tc((const bf16*)L.in, L.w, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
+                                want_stats ? L.bn.sum : nullptr, s);
   }
   if (L.Cin <= 3 && L.Cout == 64) {
     *stats_done = want_stats;
@@ -992,6 +1007,11 @@ int l3_frontend_fwd(l3_ctx* c, const void* audio, int audio_fmt, int n, float* o
 int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin, int Cout,
                    int dtype, int use_tc, void* scratch, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_tc && (Cin == 1 || Cin == 3)) {
+    L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cout == 64, "tc first-layer conv: bf16, Cout 64");
+    L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+    return launch_first_conv_tc((const bf16*)in, w, bias, (bf16*)out, B, H, W, Cin, Cout, nullptr, s);
+  }
   if (use_tc) {
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0 && scratch, "tc conv: bf16, C%%64, scratch");
     L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
@@ -1000,6 +1020,20 @@ int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out,
   }
   if (dtype == L3_DTYPE_BF16) return launch_conv3x3_simt<bf16>((const bf16*)in, w, bias, (bf16*)out, B, H, W, Cin, Cout, s);
   return launch_conv3x3_simt<float>((const float*)in, w, bias, (float*)out, B, H, W, Cin, Cout, s);
+}
+int l3_conv3x3_fwd_stats(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                         int Cout, void* scratch, double* stats, int relu_stats, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+  L3_REQUIRE(stats != nullptr, "fwd_stats: stats is NULL");
+  if (Cin == 1 || Cin == 3) {
+    L3_REQUIRE(Cout == 64 && !relu_stats, "tc first-layer conv: Cout 64, no relu statistics");
+    return launch_first_conv_tc((const bf16*)in, w, bias, (bf16*)out, B, H, W, Cin, Cout, stats, s);
+  }
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && scratch, "tc conv: C%%64, scratch");
+  L3_REQUIRE(conv_tc_fuses_stats(), "the selected L3_CONV_TC_VARIANT has no fused statistics");
+  if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 0, s)) return -1;
+  return launch_conv3x3_tc((const bf16*)in, (const bf16*)scratch, bias, (bf16*)out, B, H, W, Cin, Cout, stats, relu_stats, s);
 }
 int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
                      int use_tc, void* scratch, void* stream) {

@@ -679,6 +679,7 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
 // transaction bytes land on the leader's mbarriers), and tcgen05.commit multicasts "stage free" / "accumulator
 // ready" to both.
 static const int kConv3Threads = 64 + 256;
+static const int kMaxCoutTc = 512;   // bias staging in shared memory
 template <int BN_, int MT_>
 struct Conv3Cfg {
   static const int BN = BN_, MT = MT_;
@@ -732,6 +733,25 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       : "memory");
 }
 
+// Transposing butterfly over a warp: on entry lane r holds 32 per-column partial values a[0..31] (and b[0..31]); on
+// exit lane i holds in a[0] (b[0]) the sum over all 32 lanes of column i.  31 shuffles per array.
+__device__ __forceinline__ void col_butterfly(float (&a)[32], float (&b)[32], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int hv = 16 >> step;              // values kept per lane after this step
+    const bool upper = (lane >> (4 - step)) & 1;
+#pragma unroll
+    for (int j = 0; j < hv; ++j) {
+      const float send_a = upper ? a[j] : a[j + hv];
+      const float keep_a = upper ? a[j + hv] : a[j];
+      const float send_b = upper ? b[j] : b[j + hv];
+      const float keep_b = upper ? b[j + hv] : b[j];
+      a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
+      b[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
+    }
+  }
+}
+
 template <int BN, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -744,9 +764,12 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* smem_b = smem + AST * Cfg::kAStage;
   __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[kMaxCoutTc];   // whole bias vector, read by the epilogue as float4
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  if (bias != nullptr)
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_bias[i] = __ldg(bias + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -845,19 +868,35 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    // ===== epilogue (both CTAs, own 128 rows): as in version 2 =====
+    // ===== epilogue (both CTAs, own 128 rows): TMEM -> regs -> (+bias from smem) -> bf16 -> HBM, plus the BN batch
+    // statistics of the stored values.  Lane = pixel row, so per-channel sums need a reduction ACROSS lanes (the
+    // 31-shuffle transposing butterfly).  It is the expensive part (the Cin <= 128 layers were epilogue-bound), so
+    // the per-lane partial sums of a chunk's 32 columns are first accumulated in registers over the tile's MT
+    // m-tiles -- and, when a warp owns a single chunk (BN = 64), over ALL tiles of the kernel -- and the butterfly
+    // runs once per (tile, chunk) resp. once per kernel.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int NCH = BN / 32, NITEMS = MT * NCH, NST = NCH / 2;
+    constexpr int NCH = BN / 32, NST = NCH / 2;
+    constexpr bool CARRY = (NST == 1);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const long long HWp = (long long)(H + 2) * Wp;
+    const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
     float st_sum[NST], st_sq[NST];
 #pragma unroll
     for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
+    float ca[32], cb[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
     int st_n0 = -1;
     auto flush_stats = [&]() {
       if (stats != nullptr && st_n0 >= 0) {
+        if (CARRY) {
+          col_butterfly(ca, cb, lane);
+          st_sum[0] = ca[0];
+          st_sq[0] = cb[0];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < NST; ++i) {
           const int col = st_n0 + (2 * i + half) * 32 + lane;
@@ -868,67 +907,80 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     };
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const long long mbase = (long long)(tile / num_n_tiles) * (2 * MT * kBM) + (long long)rank * (MT * kBM) + q * 32 + lane;
+      const unsigned mbase = (unsigned)(tile / num_n_tiles) * (2 * MT * kBM) + rank * (MT * kBM) + q * 32 + lane;
       const int n0 = (tile % num_n_tiles) * BN;
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
+      // output pointer / validity of this lane's row in each m-tile (32-bit index math: Mp < 2^31)
+      bool valid[MT];
+      bf16* optr[MT];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const unsigned m = mbase + t * kBM;
+        const unsigned b = m / HWp;
+        const unsigned r = m - b * HWp;
+        const unsigned yp = r / (unsigned)Wp, xp = r - yp * (unsigned)Wp;
+        valid[t] = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
+        optr[t] = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * (long long)Cout + n0;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll
-      for (int it = 0; it < NITEMS / 2; ++it) {
-        const int t = it / NST, chh = it % NST;
-        const long long m = mbase + t * kBM;
-        bool valid = m < Mp;
-        bf16* optr = nullptr;
-        if (valid) {
-          const long long b = m / HWp;
-          const int r = (int)(m - b * HWp);
-          const int yp = r / Wp, xp = r - yp * Wp;
-          valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
-          optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
-        }
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
+      for (int chh = 0; chh < NST; ++chh) {
         const int c0 = (2 * chh + half) * 32;
-        uint32_t v[32];
-        tmem_ld32(t_row + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        if (!CARRY) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float f0 = __uint_as_float(v[2 * j]) + (bias ? __ldg(bias + n0 + c0 + 2 * j) : 0.f);
-          const float f1 = __uint_as_float(v[2 * j + 1]) + (bias ? __ldg(bias + n0 + c0 + 2 * j + 1) : 0.f);
-          pk[j] = pack_bf16x2(f0, f1);
+          for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
         }
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-        if (stats != nullptr) {
-          float a[32], b2[32];
+        for (int t = 0; t < MT; ++t) {
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
+          uint32_t v[32];
+          __syncwarp();   // reconverge after the per-row `valid` branch: tcgen05.ld is warp-collective
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-            float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
-            if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            a[2 * j] = x0; a[2 * j + 1] = x1;
-            b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + 4 * j]);
+              pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+              pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           }
+          if (valid[t]) {
 #pragma unroll
-          for (int step = 0; step < 5; ++step) {
-            const int hv = 16 >> step;
-            const bool upper = (lane >> (4 - step)) & 1;
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(optr[t] + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            if (stats != nullptr) {
+              // statistics of the values as stored (bf16-rounded); halo / out-of-range rows contribute nothing
+              if (relu_stats) {
 #pragma unroll
-            for (int j = 0; j < hv; ++j) {
-              const float send_a = upper ? a[j] : a[j + hv];
-              const float keep_a = upper ? a[j + hv] : a[j];
-              const float send_b = upper ? b2[j] : b2[j + hv];
-              const float keep_b = upper ? b2[j + hv] : b2[j];
-              a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
-              b2[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
+                for (int j = 0; j < 16; ++j) {
+                  const float x0 = fmaxf(__uint_as_float(pk[j] << 16), 0.f);
+                  const float x1 = fmaxf(__uint_as_float(pk[j] & 0xffff0000u), 0.f);
+                  ca[2 * j] += x0; ca[2 * j + 1] += x1;
+                  cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float x0 = __uint_as_float(pk[j] << 16);
+                  const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
+                  ca[2 * j] += x0; ca[2 * j + 1] += x1;
+                  cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
+                }
+              }
             }
           }
-          st_sum[chh] += a[0];
-          st_sq[chh] += b2[0];
+        }
+        if (!CARRY && stats != nullptr) {
+          __syncwarp();
+          col_butterfly(ca, cb, lane);
+          st_sum[chh] += ca[0];
+          st_sq[chh] += cb[0];
         }
       }
       tc_fence_before();
@@ -952,6 +1004,7 @@ template <int BN, int MT>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
                         long long Mp, double* stats, int relu_stats, cudaStream_t s) {
   using Cfg = Conv3Cfg<BN, MT>;
+  L3_REQUIRE(Cout <= kMaxCoutTc, "conv_tc: Cout=%d exceeds the bias staging buffer", Cout);
   static bool configured = false;
   if (!configured) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -1367,47 +1420,37 @@ static const int kFwStages = 4;
 static const int kFwThreads = 64 + 256;
 static const int kFwTile = 64 * 128;   // bytes: A tile and dz tile
 
-// one 16-byte column chunk Q (columns 8Q .. 8Q+7) of pixel row `row`; Q is a template parameter so tap / channel /
-// address offsets of every column fold to constants.  `safe`: all nine taps of this row lie inside the buffer.
+// one 16-byte column chunk Q (columns 8Q .. 8Q+7) of a pixel row as raw bf16 bits; Q is a template parameter so tap /
+// channel / address offsets of every column fold to constants.  r0/r1/r2 point at the leftmost tap of the three filter
+// rows (clamped into the buffer for halo / out-of-range rows: their dz row is zero, so any finite value will do).
 template <int C0, int Q>
-__device__ __forceinline__ void fw_build_chunk(uint8_t* __restrict__ tile, int row, const bf16* __restrict__ xin,
-                                               long long m, long long Mp, bool safe, int yp, int xp, int H, int W) {
+__device__ __forceinline__ uint4 fw_chunk(const unsigned short* __restrict__ r0, const unsigned short* __restrict__ r1,
+                                          const unsigned short* __restrict__ r2, int yp, int xp, int H, int W) {
   constexpr int K = 9 * C0;
-  const int Wp = W + 2;
-  const bf16* centre = xin + m * C0;
   uint32_t pk[4];
 #pragma unroll
-  for (int e = 0; e < 8; e += 2) {
-    float v[2];
+  for (int e = 0; e < 4; ++e) {
+    uint32_t b2[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int i = Q * 8 + e + u;   // compile-time after unrolling
-      float val = 0.f;
-      if (m < Mp) {
-        if (i < K) {
-          const int tap = i / C0, c = i - tap * C0;
-          const int off = ((tap / 3 - 1) * Wp + (tap % 3 - 1)) * C0 + c;
-          if (safe) {
-            val = __bfloat162float(centre[off]);
-          } else {
-            const long long idx = m + (tap / 3 - 1) * Wp + (tap % 3 - 1);
-            if (idx >= 0 && idx < Mp) val = __bfloat162float(centre[off]);
-          }
-        } else if (i < K + 9) {
-          const int tap = i - K;
-          const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
-          val = (yy >= 1 && yy <= H && xx >= 1 && xx <= W) ? 1.f : 0.f;
-        } else if (i == K + 9) {
-          val = 1.f;
-        }
+      const int i = Q * 8 + 2 * e + u;   // compile-time after unrolling
+      uint32_t bits = 0u;
+      if (i < K) {
+        const int tap = i / C0, c = i - tap * C0, ky = tap / 3, kx = tap % 3;
+        const unsigned short* rp = ky == 0 ? r0 : (ky == 1 ? r1 : r2);
+        bits = (uint32_t)__ldg(rp + kx * C0 + c);
+      } else if (i < K + 9) {
+        const int tap = i - K;
+        const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
+        bits = (yy >= 1 && yy <= H && xx >= 1 && xx <= W) ? 0x3F80u : 0u;   // bf16 1.0
+      } else if (i == K + 9) {
+        bits = 0x3F80u;
       }
-      v[u] = val;
+      b2[u] = bits;
     }
-    pk[e >> 1] = pack_bf16x2(v[0], v[1]);
+    pk[e] = b2[0] | (b2[1] << 16);
   }
-  *reinterpret_cast<uint4*>(tile + row * 128 + ((Q ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 template <int C0>
@@ -1479,45 +1522,65 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
     if (leader) umma_commit(&tfull_bar);
     __syncwarp();
   } else {
-    // ===== builders: 256 threads = 64 pixel rows x 4 parts; part p writes column chunk p (and p + 4) =====
+    // ===== builders: 256 threads = 64 pixel rows x 4 parts; part p writes column chunk p (and p + 4).  The gather
+    // for chunk c+1 is issued before the stage of chunk c is awaited, so its global-load latency hides behind the
+    // barrier wait and the stores of chunk c =====
     const int bt = threadIdx.x - 64;
     const int row = bt & 63, part = bt >> 6;
     const int Wp = W + 2;
-    const long long HWp = (long long)(H + 2) * Wp;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int c = c_begin; c < c_end; ++c) {
+    const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(xin);
+    auto gather = [&](int c, uint4& o0, uint4& o1) {
       const long long m = (long long)c * 64 + row;
       int yp = 0, xp = 0;
       if (m < Mp) {
-        const long long b = m / HWp;
-        const int r = (int)(m - b * HWp);
-        yp = r / Wp;
-        xp = r - yp * Wp;
+        const unsigned b = (unsigned)m / HWp;
+        const unsigned r = (unsigned)m - b * HWp;
+        yp = (int)(r / (unsigned)Wp);
+        xp = (int)(r - (unsigned)yp * (unsigned)Wp);
       }
-      const bool safe = (m >= Wp + 1) && (m + Wp + 1 < Mp);
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* tile = smem + stage * 2 * kFwTile;
+      const unsigned short* rp[3];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        long long p = m + (ky - 1) * Wp - 1;
+        p = p < 0 ? 0 : (p > Mp - 3 ? Mp - 3 : p);
+        rp[ky] = xs + p * C0;
+      }
+      o0 = o1 = make_uint4(0, 0, 0, 0);
       // `part` is warp-uniform (two builder warps per part): the switch does not diverge
       switch (part) {
         case 0:
-          fw_build_chunk<C0, 0>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
-          if (NQ > 4) fw_build_chunk<C0, 4>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          o0 = fw_chunk<C0, 0>(rp[0], rp[1], rp[2], yp, xp, H, W);
+          if (NQ > 4) o1 = fw_chunk<C0, 4>(rp[0], rp[1], rp[2], yp, xp, H, W);
           break;
         case 1:
-          fw_build_chunk<C0, 1>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          o0 = fw_chunk<C0, 1>(rp[0], rp[1], rp[2], yp, xp, H, W);
           break;
         case 2:
-          fw_build_chunk<C0, 2>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          o0 = fw_chunk<C0, 2>(rp[0], rp[1], rp[2], yp, xp, H, W);
           break;
         default:
-          if (NQ > 3) fw_build_chunk<C0, 3>(tile, row, xin, m, Mp, safe, yp, xp, H, W);
+          if (NQ > 3) o0 = fw_chunk<C0, 3>(rp[0], rp[1], rp[2], yp, xp, H, W);
           break;
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    uint4 cur0, cur1, nxt0, nxt1;
+    cur0 = cur1 = nxt0 = nxt1 = make_uint4(0, 0, 0, 0);
+    if (c_begin < c_end) gather(c_begin, cur0, cur1);
+    for (int c = c_begin; c < c_end; ++c) {
+      if (c + 1 < c_end) gather(c + 1, nxt0, nxt1);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* tile = smem + stage * 2 * kFwTile;
+      if (part < NQ) *reinterpret_cast<uint4*>(tile + row * 128 + ((part ^ (row & 7)) << 4)) = cur0;
+      if (NQ > 4 && part == 0) *reinterpret_cast<uint4*>(tile + row * 128 + ((4 ^ (row & 7)) << 4)) = cur1;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
       if (++stage == kFwStages) { stage = 0; phase ^= 1; }
+      cur0 = nxt0;
+      cur1 = nxt1;
     }
     // ===== epilogue (accumulator rows 0..K+9 live in TMEM lanes 0..63 -> quarters 0 and 1) =====
     const int q = warp & 3;
@@ -1558,7 +1621,7 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
                           int Cout, cudaStream_t s) {
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_wgrad_tc: C0=%d Cout=%d", C0, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
-  L3_REQUIRE(Mp + 1024 < 0x7fffffffLL, "first_wgrad_tc: too many pixels");
+  L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_wgrad_tc: pixel count out of range");
   if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
   const int smem = kFwStages * 2 * kFwTile + 1024;
   static bool configured = false;
@@ -1576,6 +1639,223 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
   ctas = (total_chunks + cpc - 1) / cpc;
   if (C0 == 1) k_first_wgrad_tc<1><<<ctas, kFwThreads, smem, s>>>(tmZ, xin, dw, db, d1, H, W, Mp, total_chunks, cpc);
   else k_first_wgrad_tc<3><<<ctas, kFwThreads, smem, s>>>(tmZ, xin, dw, db, d1, H, W, Mp, total_chunks, cpc);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- first-layer forward on tensor cores -------------------------------------------------------------------
+// Cin = 1 / 3: K = 9*C0 = 9 / 27 is too narrow for a TMA box, and the SIMT kernel it replaces ran at a third of the
+// fp32 pipe (0.45 ms for a layer whose output write takes 0.06 ms of HBM time).  Four builder warps gather the
+// im2col rows of a 128-pixel tile (flattened padded index, like every other conv here) straight from the padded
+// bf16 input -- per pixel three contiguous runs of 3*C0 values, prefetched into registers one tile ahead -- and
+// write them as a K-major, 128-byte-swizzled UMMA operand ([128 px][KPAD], KPAD = 16 / 32); the weight tile
+// ([64 co][KPAD], built once per CTA from the fp32 HWIO kernel) is the B operand.  One elected thread issues KPAD/16
+// MMAs (128x64x16) per tile into one of four TMEM accumulators; eight epilogue warps add the fp32 bias, store bf16
+// and carry the per-lane BN statistics in registers (one transposing butterfly per kernel).  HBM-bound by design:
+// algorithmic bytes per pixel = 2*C0 (input) + 128 (output).
+template <int C0>
+struct FcCfg {
+  static const int K = 9 * C0;
+  static const int KPAD = (K + 15) / 16 * 16;   // 16 (C0 = 1) / 32 (C0 = 3)
+  static const int NQ = KPAD / 8;               // 16-byte chunks per operand row
+  static const int kStages = 4;
+  static const int kATile = kBM * 128;          // 128 rows x 128 B (only the first KPAD*2 bytes of a row are used)
+  static const int kWTile = 64 * 128;
+  static const int kSmem = kStages * kATile + kWTile + 1024;
+  static const int kAccs = 4;                   // TMEM accumulators of 64 columns
+};
+static const int kFcThreads = 32 + 128 + 256;   // MMA warp, 4 builder warps, 8 epilogue warps
+
+template <int C0>
+__device__ __forceinline__ void fc_load_row(const unsigned short* __restrict__ xin, long long m, int Wp, long long Mp,
+                                            unsigned short (&v)[9 * C0]) {
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    long long p = m + (ky - 1) * Wp - 1;     // leftmost tap of filter row ky
+    p = p < 0 ? 0 : (p > Mp - 3 ? Mp - 3 : p);   // only halo / out-of-range rows are ever clamped (their output is dropped)
+    const unsigned short* src = xin + p * C0;
+#pragma unroll
+    for (int j = 0; j < 3 * C0; ++j) v[ky * 3 * C0 + j] = __ldg(src + j);
+  }
+}
+
+template <int C0>
+__global__ void __launch_bounds__(kFcThreads, 1)
+k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
+                bf16* __restrict__ out, int H, int W, long long Mp, int num_tiles, double* __restrict__ stats) {
+  using Cfg = FcCfg<C0>;
+  constexpr int K = Cfg::K, KPAD = Cfg::KPAD, NQ = Cfg::NQ, ST = Cfg::kStages, ACCS = Cfg::kAccs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem + ST * Cfg::kATile;
+  __shared__ __align__(8) uint64_t a_full[ST], a_empty[ST], t_full[ACCS], t_empty[ACCS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // weight tile: element (co, k) at co*128 + ((k/8) ^ (co & 7))*16 + (k % 8)*2 ; zero beyond K
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int co = i & 63, k = i >> 6;
+    const float v = k < K ? __ldg(w + k * 64 + co) : 0.f;
+    *reinterpret_cast<bf16*>(smem_w + co * 128 + (((k >> 3) ^ (co & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < ACCS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
+                 "n"(ACCS * 64)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight tile (generic stores) -> visible to UMMA
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int Wp = W + 2;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(kBM, 64, 0, 0);
+    constexpr uint32_t hi = desc_hi(1024);
+    const bool leader = elect_one();
+    const uint32_t sa_base = smem_addr(smem);
+    const uint32_t b_lo0 = desc_lo(smem_addr(smem_w), 16);
+    int stage = 0, acc = 0;
+    uint32_t sph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&t_empty[acc], aph ^ 1);
+      mbar_wait(&a_full[stage], sph);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_lo0 = desc_lo(sa_base + stage * Cfg::kATile, 16);
+#pragma unroll
+        for (int k = 0; k < KPAD / 16; ++k)
+          umma_bf16_lh(tmem_base + acc * 64, a_lo0 + (uint32_t)(k * 2), hi, b_lo0 + (uint32_t)(k * 2), hi, idesc, k ? 1u : 0u);
+        umma_commit(&a_empty[stage]);
+        umma_commit(&t_full[acc]);
+      }
+      __syncwarp();
+      if (++stage == ST) { stage = 0; sph ^= 1; }
+      if (++acc == ACCS) { acc = 0; aph ^= 1; }
+    }
+  } else if (warp < 5) {
+    // ===== builders: thread = pixel row of the tile =====
+    const int r = threadIdx.x - 32;
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(xin);
+    int stage = 0;
+    uint32_t sph = 0;
+    unsigned short cur[K], nxt[K];
+    if ((int)blockIdx.x < num_tiles) fc_load_row<C0>(xs, (long long)blockIdx.x * kBM + r, Wp, Mp, cur);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ntile = tile + gridDim.x;
+      if (ntile < num_tiles) fc_load_row<C0>(xs, (long long)ntile * kBM + r, Wp, Mp, nxt);
+      mbar_wait(&a_empty[stage], sph ^ 1);
+      uint8_t* row = smem + stage * Cfg::kATile + r * 128;
+#pragma unroll
+      for (int qd = 0; qd < NQ; ++qd) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = qd * 8 + 2 * e, k1 = k0 + 1;   // compile-time
+          const uint32_t lo = k0 < K ? (uint32_t)cur[k0 < K ? k0 : 0] : 0u;
+          const uint32_t hi16 = k1 < K ? (uint32_t)cur[k1 < K ? k1 : 0] : 0u;
+          pk[e] = lo | (hi16 << 16);
+        }
+        *reinterpret_cast<uint4*>(row + ((qd ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[stage]);
+      if (++stage == ST) { stage = 0; sph ^= 1; }
+#pragma unroll
+      for (int i = 0; i < K; ++i) cur[i] = nxt[i];
+    }
+  } else {
+    // ===== epilogue: warp = (TMEM lane quarter, 32-column half) =====
+    const int q = warp & 3;
+    const int half = (warp - 5) >> 2;
+    const int c0 = half * 32;
+    const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
+    float ca[32], cb[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const unsigned m = (unsigned)tile * kBM + q * 32 + lane;
+      const unsigned b = m / HWp;
+      const unsigned rr = m - b * HWp;
+      const unsigned yp = rr / (unsigned)Wp, xp = rr - yp * (unsigned)Wp;
+      const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
+      bf16* optr = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * 64 + c0;
+      mbar_wait(&t_full[acc], aph);
+      tc_fence_after();
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + c0), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);   // accumulator is in registers: hand it back before the math
+      if (++acc == ACCS) { acc = 0; aph ^= 1; }
+      if (valid) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+          pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+          pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(optr + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        if (stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = __uint_as_float(pk[j] << 16);
+            const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
+            ca[2 * j] += x0; ca[2 * j + 1] += x1;
+            cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
+          }
+        }
+      }
+    }
+    if (stats != nullptr) {
+      __syncwarp();
+      col_butterfly(ca, cb, lane);
+      atomicAdd(&stats[c0 + lane], (double)ca[0]);
+      atomicAdd(&stats[64 + c0 + lane], (double)cb[0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ACCS * 64) : "memory");
+  }
+}
+
+int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf16* out, int B, int H, int W, int C0,
+                         int Cout, double* stats, cudaStream_t s) {
+  L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_conv_tc: C0=%d Cout=%d", C0, Cout);
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_conv_tc: pixel count out of range");
+  static bool configured = false;
+  if (!configured) {
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<1>::kSmem));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<3>::kSmem));
+    configured = true;
+  }
+  if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
+  const int num_tiles = (int)((Mp + kBM - 1) / kBM);
+  const int grid = num_tiles < 148 ? num_tiles : 148;
+  if (C0 == 1) k_first_conv_tc<1><<<grid, kFcThreads, FcCfg<1>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats);
+  else k_first_conv_tc<3><<<grid, kFcThreads, FcCfg<3>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats);
   L3_CHECK_LAUNCH();
   return 0;
 }

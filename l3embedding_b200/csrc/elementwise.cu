@@ -191,29 +191,37 @@ int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, cons
 template int launch_affine_small<float>(const float*, float*, int, int, int, int, const float*, const float*, cudaStream_t);
 template int launch_affine_small<bf16>(const float*, bf16*, int, int, int, int, const float*, const float*, cudaStream_t);
 
-// zero the one-pixel halo of a padded (B,H+2,W+2,C) buffer (buffers re-used at several geometries)
-template <typename T>
+// zero the one-pixel halo of a padded (B,H+2,W+2,C) buffer (buffers re-used at several geometries); one 16-byte
+// store per thread when a pixel's channels are a multiple of 16 bytes (every layer with C >= 64)
+template <typename T, int VEC>
 __global__ void k_zero_halo(T* __restrict__ buf, int B, int H, int W, int C) {
   const int per_img = 2 * (W + 2) + 2 * H;  // halo pixels per image
-  long long total = (long long)B * per_img * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    long long q = i / C;
-    int h = (int)(q % per_img);
-    long long b = q / per_img;
+  const int cv = C / VEC;
+  const unsigned total = (unsigned)B * per_img * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    const unsigned q = i / cv;
+    const int h = (int)(q % per_img);
+    const long long b = q / per_img;
     int yp, xp;
     if (h < W + 2) { yp = 0; xp = h; }
     else if (h < 2 * (W + 2)) { yp = H + 1; xp = h - (W + 2); }
     else { int r = h - 2 * (W + 2); yp = 1 + (r >> 1); xp = (r & 1) ? W + 1 : 0; }
-    buf[((b * (H + 2) + yp) * (long long)(W + 2) + xp) * C + c] = from_f<T>(0.f);
+    T* dst = buf + ((b * (H + 2) + yp) * (long long)(W + 2) + xp) * C + c;
+    if (VEC == 1) *dst = from_f<T>(0.f);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
 }
 template <typename T>
 int launch_zero_halo(T* buf, int B, int H, int W, int C, cudaStream_t s) {
-  long long total = (long long)B * (2 * (W + 2) + 2 * H) * C;
+  constexpr int V = 16 / (int)sizeof(T);
+  const bool vec = (C % V == 0) && (((uintptr_t)buf & 15) == 0);
+  long long total = (long long)B * (2 * (W + 2) + 2 * H) * (vec ? C / V : C);
+  L3_REQUIRE(total < 0x7fffffffLL, "zero_halo: too many elements");
   long long want = (total + kThreads - 1) / kThreads;
   int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
-  k_zero_halo<T><<<blocks, kThreads, 0, s>>>(buf, B, H, W, C);
+  if (vec) k_zero_halo<T, V><<<blocks, kThreads, 0, s>>>(buf, B, H, W, C);
+  else k_zero_halo<T, 1><<<blocks, kThreads, 0, s>>>(buf, B, H, W, C);
   L3_CHECK_LAUNCH();
   return 0;
 }

@@ -156,4 +156,9 @@ int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int 
 int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0,
                           int Cout, cudaStream_t s);
 
+// First-layer (Cin = 1|3, Cout = 64) forward on tensor cores: xin padded bf16 (B,H+2,W+2,C0), w fp32 HWIO, out unpadded
+// bf16 (B,H,W,64); stats as in launch_conv3x3_tc (zeroed here).
+int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf16* out, int B, int H, int W, int C0,
+                         int Cout, double* stats, cudaStream_t s);
+
 }  // namespace l3

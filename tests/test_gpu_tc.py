@@ -56,6 +56,47 @@ def test_tc_forward(lib, shape):
     assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
 
 
+FIRST_SHAPES = [(2, 16, 13, 3, 64), (2, 9, 20, 1, 64), (1, 33, 31, 3, 64), (3, 40, 37, 1, 64), (5, 64, 50, 3, 64)]
+
+
+@pytest.mark.parametrize("shape", FIRST_SHAPES)
+def test_tc_first_layer_forward(lib, shape):
+    """Cin = 1 / 3 forward: the K-major im2col operand is gathered into shared memory by the kernel's builder warps."""
+    test_tc_forward(lib, shape)
+
+
+@pytest.mark.parametrize("relu", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES + FIRST_SHAPES + [(2, 70, 66, 64, 64), (2, 40, 36, 64, 128)])
+def test_tc_forward_fused_bn_statistics(lib, shape, relu):
+    """The epilogue's per-channel sum / sum of squares (BN batch statistics) equal those of the stored bf16 output;
+    the output itself is bit-identical to the statistics-free launch."""
+    from l3embedding_b200 import _lib
+    B, H, W, Ci, Co = shape
+    if relu and Ci < 64:
+        pytest.skip("no relu statistics on the first layer")
+    x, w, b, _ = _setup(shape, seed=11)
+    xp = _pad(x).contiguous().cuda()
+    out = torch.full((B, H, W, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    out0 = torch.full((B, H, W, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((2 * Co,), float("nan"), dtype=torch.float64, device="cuda")
+    scratch = torch.empty(9 * max(Ci, 64) * Co, dtype=torch.bfloat16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    wd, bd = w.cuda(), b.cuda()
+    _lib.check(lib.l3_conv3x3_fwd(_p(xp), _p(wd), _p(bd), _p(out0), B, H, W, Ci, Co, 1, 1, _p(scratch), st), "fwd")
+    _lib.check(lib.l3_conv3x3_fwd_stats(_p(xp), _p(wd), _p(bd), _p(out), B, H, W, Ci, Co, _p(scratch), _p(stats), relu, st),
+               "fwd_stats")
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), out0.view(torch.int16))
+    z = out.double().cpu().reshape(-1, Co)
+    if relu:
+        z = z.clamp_min(0)
+    s1, s2 = z.sum(0), (z * z).sum(0)
+    got = stats.cpu()
+    # fp32 partial sums per lane, double across warps: relative error ~1e-6 of the absolute sums
+    assert (got[:Co] - s1).abs().max().item() <= 1e-5 * z.abs().sum(0).max().item() + 1e-6
+    assert (got[Co:] - s2).abs().max().item() <= 1e-5 * s2.max().item() + 1e-6
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_tc_dgrad(lib, shape):
     from l3embedding_b200 import _lib
