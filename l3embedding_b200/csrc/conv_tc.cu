@@ -690,7 +690,8 @@ struct Conv3Cfg {
   static const int kAStages = (MT == 4) ? 2 : (MT == 2 ? 3 : 4);
   static const int kBStage = (BN / 2) * 128;       // this CTA's half of the weight tile
   static const int kBStages = 8;
-  static const int kSmem = kAStages * kAStage + kBStages * kBStage + 1024;
+  static const int kStatScratch = (BN == 256) ? 0 : 8 * 32 * 36 * 4;   // per-epilogue-warp transposition scratch (BN statistics)
+  static const int kSmem = kAStages * kAStage + kBStages * kBStage + kStatScratch + 1024;
   static const int kTmemCols = 2 * MT * BN;        // 512 for (256,1), (128,2), (64,4)
 };
 
@@ -869,34 +870,26 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // ===== epilogue (both CTAs, own 128 rows): TMEM -> regs -> (+bias from smem) -> bf16 -> HBM, plus the BN batch
-    // statistics of the stored values.  Lane = pixel row, so per-channel sums need a reduction ACROSS lanes (the
-    // 31-shuffle transposing butterfly).  It is the expensive part (the Cin <= 128 layers were epilogue-bound), so
-    // the per-lane partial sums of a chunk's 32 columns are first accumulated in registers over the tile's MT
-    // m-tiles -- and, when a warp owns a single chunk (BN = 64), over ALL tiles of the kernel -- and the butterfly
-    // runs once per (tile, chunk) resp. once per kernel.
+    // statistics of the stored values.  Lane = pixel row, so per-channel sums need a reduction ACROSS lanes.  The
+    // 31-shuffle transposing butterfly costs ~350 instructions per 32x32 chunk and made the Cin <= 128 layers
+    // epilogue-bound; BN < 256 configurations (which have the shared memory to spare) instead transpose the chunk
+    // through a per-warp 32x36-float scratch: 8 conflict-free 16-byte stores per lane, then lane i sums column i
+    // with 32 conflict-free loads.  Register use stays at the level that lets the other tower's element-wise
+    // kernels co-reside on the SM (two-stream overlap).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCH = BN / 32, NST = NCH / 2;
-    constexpr bool CARRY = (NST == 1);
+    constexpr bool SMEM_STATS = Cfg::kStatScratch > 0;
+    float* const sw = reinterpret_cast<float*>(smem_b + BST * Cfg::kBStage) + (warp - 2) * (32 * 36);
     int acc = 0;
     uint32_t acc_phase = 0;
     const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
     float st_sum[NST], st_sq[NST];
 #pragma unroll
     for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
-    float ca[32], cb[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
     int st_n0 = -1;
     auto flush_stats = [&]() {
       if (stats != nullptr && st_n0 >= 0) {
-        if (CARRY) {
-          col_butterfly(ca, cb, lane);
-          st_sum[0] = ca[0];
-          st_sq[0] = cb[0];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
-        }
 #pragma unroll
         for (int i = 0; i < NST; ++i) {
           const int col = st_n0 + (2 * i + half) * 32 + lane;
@@ -910,32 +903,23 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const unsigned mbase = (unsigned)(tile / num_n_tiles) * (2 * MT * kBM) + rank * (MT * kBM) + q * 32 + lane;
       const int n0 = (tile % num_n_tiles) * BN;
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
-      // output pointer / validity of this lane's row in each m-tile (32-bit index math: Mp < 2^31)
-      bool valid[MT];
-      bf16* optr[MT];
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
+        // output pointer / validity of this lane's row (32-bit index math: Mp < 2^31)
         const unsigned m = mbase + t * kBM;
         const unsigned b = m / HWp;
         const unsigned r = m - b * HWp;
         const unsigned yp = r / (unsigned)Wp, xp = r - yp * (unsigned)Wp;
-        valid[t] = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
-        optr[t] = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * (long long)Cout + n0;
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+        const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
+        bf16* const optr = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * (long long)Cout + n0;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
 #pragma unroll
-      for (int chh = 0; chh < NST; ++chh) {
-        const int c0 = (2 * chh + half) * 32;
-        if (!CARRY) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
-        }
-#pragma unroll
-        for (int t = 0; t < MT; ++t) {
-          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
+        for (int chh = 0; chh < NST; ++chh) {
+          const int c0 = (2 * chh + half) * 32;
           uint32_t v[32];
-          __syncwarp();   // reconverge after the per-row `valid` branch: tcgen05.ld is warp-collective
+          __syncwarp();   // reconverge after the per-row `valid` branches: tcgen05.ld is warp-collective
           tmem_ld32(t_row + c0, v);
           tmem_ld_wait();
           uint32_t pk[16];
@@ -950,37 +934,53 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           }
-          if (valid[t]) {
+          if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(optr[t] + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            if (stats != nullptr) {
-              // statistics of the values as stored (bf16-rounded); halo / out-of-range rows contribute nothing
-              if (relu_stats) {
+              *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (stats != nullptr) {
+            // statistics of the values as stored (bf16-rounded), zero for halo / out-of-range rows
+            if (SMEM_STATS) {
+              float4* const wrow = reinterpret_cast<float4*>(sw + lane * 36);
+              if (valid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float x0 = fmaxf(__uint_as_float(pk[j] << 16), 0.f);
-                  const float x1 = fmaxf(__uint_as_float(pk[j] & 0xffff0000u), 0.f);
-                  ca[2 * j] += x0; ca[2 * j + 1] += x1;
-                  cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
+                for (int j = 0; j < 8; ++j) {
+                  float4 x = make_float4(__uint_as_float(pk[2 * j] << 16), __uint_as_float(pk[2 * j] & 0xffff0000u),
+                                         __uint_as_float(pk[2 * j + 1] << 16), __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
+                  if (relu_stats) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                  wrow[j] = x;
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float x0 = __uint_as_float(pk[j] << 16);
-                  const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
-                  ca[2 * j] += x0; ca[2 * j + 1] += x1;
-                  cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
-                }
+                for (int j = 0; j < 8; ++j) wrow[j] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
+              __syncwarp();
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float x = sw[rr * 36 + lane];
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+              }
+              st_sum[chh] += s1;
+              st_sq[chh] += s2;
+              __syncwarp();   // the scratch is rewritten by the next chunk
+            } else {
+              float a[32], b2[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+                float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                a[2 * j] = x0; a[2 * j + 1] = x1;
+                b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
+              }
+              col_butterfly(a, b2, lane);
+              st_sum[chh] += a[0];
+              st_sq[chh] += b2[0];
             }
           }
-        }
-        if (!CARRY && stats != nullptr) {
-          __syncwarp();
-          col_butterfly(ca, cb, lane);
-          st_sum[chh] += ca[0];
-          st_sq[chh] += cb[0];
         }
       }
       tc_fence_before();

@@ -91,6 +91,9 @@ class OracleConfig:
     # (conv inputs, conv outputs z, conv weights of the tensor-core layers, and in backward dz / da); all arithmetic
     # stays in `dtype`.  With this on, the oracle differs from the device only by accumulation order.
     emulate_bf16: bool = False
+    # emulate_bf16 only: the first conv layer (Cin 1/3) also runs on the tensor cores with bf16-rounded weights
+    # (k_first_conv_tc, the default); False = the SIMT first layer with fp32 weights (L3_FIRST_CONV_TC=0)
+    first_layer_bf16_weights: bool = True
 
 
 # Note on adam_eps: keras 2.0.9 Adam(epsilon=1e-8) is the constructor default; the update is
@@ -314,10 +317,11 @@ def _bn(x, w, prefix, training, cfg, stats):
 def _conv(x, w, prefix, cfg=None):
     k = w[prefix + "/kernel"].permute(3, 2, 0, 1)     # HWIO -> OIHW
     if cfg is not None and cfg.emulate_bf16:
-        # device: bf16 conv input (gradient da stored as bf16), bf16 packed weights on the tcgen05 layers (Cin >= 64;
-        # the first layer runs SIMT with fp32 weights), fp32 accumulate, output z and its gradient dz stored as bf16
+        # device: bf16 conv input (gradient da stored as bf16), bf16 weight operands on every tcgen05 layer (the first
+        # layer included unless first_layer_bf16_weights is off), fp32 accumulate, output z and its gradient dz
+        # stored as bf16
         x = _RoundGrad.apply(_q(x))
-        if k.shape[1] >= 64:
+        if k.shape[1] >= 64 or cfg.first_layer_bf16_weights:
             k = _q(k)
         return _RoundGrad.apply(_q(F.conv2d(x, k, w[prefix + "/bias"], padding=1)))
     return F.conv2d(x, k, w[prefix + "/bias"], padding=1)
