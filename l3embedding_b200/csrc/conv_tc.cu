@@ -17,6 +17,7 @@
 //   split-K over pixel slices with fp32 atomics into dW.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "kernels.h"
 
 namespace l3 {
@@ -99,6 +100,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -680,7 +690,13 @@ static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias,
 // ready" to both.
 static const int kConv3Threads = 64 + 256;
 static const int kMaxCoutTc = 512;   // bias staging in shared memory
-template <int BN_, int MT_>
+// epilogue flavours of k_conv3x3_tc3 (how the per-channel BN statistics are reduced across the 32 pixel rows a warp holds)
+enum { EPI_NONE = 0,        // no statistics (dgrad, inference): leanest register footprint
+       EPI_BUTTERFLY = 1,   // 31-shuffle transposing butterfly per 32x32 chunk (~350 instructions)
+       EPI_SMEM = 2,        // transpose through a per-warp 32x36-float scratch (needs 36 KB of shared memory: BN < 256)
+       EPI_CARRY = 3 };     // per-lane partial sums carried in registers over ALL tiles, one butterfly per kernel
+                            // (a warp must own a single chunk: BN = 64; costs ~50 registers per thread)
+template <int BN_, int MT_, int EPI_>
 struct Conv3Cfg {
   static const int BN = BN_, MT = MT_;
   static const int kARows = MT * kBM + 8;          // this CTA's MT m-tiles + halo
@@ -690,8 +706,10 @@ struct Conv3Cfg {
   static const int kAStages = (MT == 4) ? 2 : (MT == 2 ? 3 : 4);
   static const int kBStage = (BN / 2) * 128;       // this CTA's half of the weight tile
   static const int kBStages = 8;
-  static const int kStatScratch = (BN == 256) ? 0 : 8 * 32 * 36 * 4;   // per-epilogue-warp transposition scratch (BN statistics)
-  static const int kSmem = kAStages * kAStage + kBStages * kBStage + kStatScratch + 1024;
+  static const int EPI = EPI_;
+  static const int kStatScratch = (EPI == EPI_SMEM) ? 8 * 32 * 36 * 4 : 0;   // per-epilogue-warp transposition scratch
+  static const int kStoreScratch = 8 * 32 * 64;    // per-epilogue-warp store transposition scratch
+  static const int kSmem = kAStages * kAStage + kBStages * kBStage + kStoreScratch + kStatScratch + 1024;
   static const int kTmemCols = 2 * MT * BN;        // 512 for (256,1), (128,2), (64,4)
 };
 
@@ -753,12 +771,12 @@ __device__ __forceinline__ void col_butterfly(float (&a)[32], float (&b)[32], in
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
               int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
-  using Cfg = Conv3Cfg<BN, MT>;
+  using Cfg = Conv3Cfg<BN, MT, EPI>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -870,26 +888,37 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // ===== epilogue (both CTAs, own 128 rows): TMEM -> regs -> (+bias from smem) -> bf16 -> HBM, plus the BN batch
-    // statistics of the stored values.  Lane = pixel row, so per-channel sums need a reduction ACROSS lanes.  The
-    // 31-shuffle transposing butterfly costs ~350 instructions per 32x32 chunk and made the Cin <= 128 layers
-    // epilogue-bound; BN < 256 configurations (which have the shared memory to spare) instead transpose the chunk
-    // through a per-warp 32x36-float scratch: 8 conflict-free 16-byte stores per lane, then lane i sums column i
-    // with 32 conflict-free loads.  Register use stays at the level that lets the other tower's element-wise
-    // kernels co-reside on the SM (two-stream overlap).
+    // statistics of the stored values.  Lane = pixel row, so per-channel sums need a reduction ACROSS lanes; the
+    // EPI template parameter selects how (see the enum above).  The per-item butterfly made the Cin <= 128 layers
+    // epilogue-bound.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCH = BN / 32, NST = NCH / 2;
-    constexpr bool SMEM_STATS = Cfg::kStatScratch > 0;
-    float* const sw = reinterpret_cast<float*>(smem_b + BST * Cfg::kBStage) + (warp - 2) * (32 * 36);
+    static_assert(EPI != EPI_CARRY || NST == 1, "EPI_CARRY needs one chunk per warp");
+    uint4* const st_scr = reinterpret_cast<uint4*>(smem_b + BST * Cfg::kBStage) + (warp - 2) * 128;   // 32 rows x 64 B
+    float* const sw = reinterpret_cast<float*>(smem_b + BST * Cfg::kBStage + Cfg::kStoreScratch) + (warp - 2) * (32 * 36);
     int acc = 0;
     uint32_t acc_phase = 0;
     const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
     float st_sum[NST], st_sq[NST];
 #pragma unroll
     for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
+    float ca[EPI == EPI_CARRY ? 32 : 1], cb[EPI == EPI_CARRY ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < (EPI == EPI_CARRY ? 32 : 1); ++j) ca[j] = cb[j] = 0.f;
     int st_n0 = -1;
     auto flush_stats = [&]() {
-      if (stats != nullptr && st_n0 >= 0) {
+      if (EPI != EPI_NONE && stats != nullptr && st_n0 >= 0) {
+        if (EPI == EPI_CARRY) {
+          __syncwarp();
+          float (&fa)[32] = reinterpret_cast<float (&)[32]>(ca);
+          float (&fb)[32] = reinterpret_cast<float (&)[32]>(cb);
+          col_butterfly(fa, fb, lane);
+          st_sum[0] = ca[0];
+          st_sq[0] = cb[0];
+#pragma unroll
+          for (int j = 0; j < (EPI == EPI_CARRY ? 32 : 1); ++j) ca[j] = cb[j] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < NST; ++i) {
           const int col = st_n0 + (2 * i + half) * 32 + lane;
@@ -905,81 +934,131 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < MT; ++t) {
-        // output pointer / validity of this lane's row (32-bit index math: Mp < 2^31)
+        // output pixel of this lane's row, -1 for halo / out-of-range rows (32-bit index math: Mp < 2^31)
         const unsigned m = mbase + t * kBM;
         const unsigned b = m / HWp;
         const unsigned r = m - b * HWp;
         const unsigned yp = r / (unsigned)Wp, xp = r - yp * (unsigned)Wp;
         const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
-        bf16* const optr = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * (long long)Cout + n0;
+        const int opix = valid ? (int)((b * (unsigned)H + (yp - 1)) * (unsigned)W + (xp - 1)) : -1;
+        // store phase: lane l writes 16-byte piece (l & 3) of rows (l >> 2) + 8 i
+        int spix[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
 #pragma unroll
         for (int chh = 0; chh < NST; ++chh) {
           const int c0 = (2 * chh + half) * 32;
-          uint32_t v[32];
-          __syncwarp();   // reconverge after the per-row `valid` branches: tcgen05.ld is warp-collective
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
           uint32_t pk[16];
-          if (bias != nullptr) {
+          if (EPI == EPI_CARRY || EPI == EPI_NONE) {
+            // 16 columns at a time: half the live registers of the 32-column path
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + 4 * j]);
-              pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-              pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
-            }
-          } else {
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16];
+              tmem_ld16(t_row + c0 + hh * 16, v);
+              tmem_ld_wait();
+              if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          }
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-          if (stats != nullptr) {
-            // statistics of the values as stored (bf16-rounded), zero for halo / out-of-range rows
-            if (SMEM_STATS) {
-              float4* const wrow = reinterpret_cast<float4*>(sw + lane * 36);
-              if (valid) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float4 x = make_float4(__uint_as_float(pk[2 * j] << 16), __uint_as_float(pk[2 * j] & 0xffff0000u),
-                                         __uint_as_float(pk[2 * j + 1] << 16), __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
-                  if (relu_stats) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                  wrow[j] = x;
+                for (int j = 0; j < 4; ++j) {
+                  const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + hh * 16 + 4 * j]);
+                  pk[hh * 8 + 2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                  pk[hh * 8 + 2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wrow[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < 8; ++j)
+                  pk[hh * 8 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               }
-              __syncwarp();
-              float s1 = 0.f, s2 = 0.f;
+            }
+          } else {
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);
+            tmem_ld_wait();
+            if (bias != nullptr) {
 #pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                const float x = sw[rr * 36 + lane];
-                s1 += x;
-                s2 = fmaf(x, x, s2);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + 4 * j]);
+                pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
               }
-              st_sum[chh] += s1;
-              st_sq[chh] += s2;
-              __syncwarp();   // the scratch is rewritten by the next chunk
             } else {
-              float a[32], b2[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            }
+          }
+          // coalesced store: lane = row would emit 32 scattered 16-byte pieces per instruction (one L2 request each --
+          // measured: the request rate, not the bytes, bounded the Cout <= 128 layers).  The 32x64-byte chunk is
+          // transposed through a private swizzled scratch so that one instruction writes 8 rows x 64 contiguous bytes.
+          {
+            uint4* const srow = st_scr + lane * 4;
+            const int sw4 = (lane >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) srow[c ^ sw4] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int R = (lane >> 2) + 8 * i;
+              const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
+              if (spix[i] >= 0)
+                *reinterpret_cast<uint4*>(out + (long long)spix[i] * Cout + n0 + c0 + (lane & 3) * 8) = val;
+            }
+            __syncwarp();   // the scratch is rewritten by the next chunk
+          }
+          if (EPI == EPI_NONE || stats == nullptr) continue;
+          // statistics of the values as stored (bf16-rounded); halo / out-of-range rows contribute nothing
+          if (EPI == EPI_CARRY) {
+            if (valid) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-                float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+                float x0 = __uint_as_float(pk[j] << 16);
+                float x1 = __uint_as_float(pk[j] & 0xffff0000u);
                 if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                a[2 * j] = x0; a[2 * j + 1] = x1;
-                b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
+                const int i0 = (EPI == EPI_CARRY) ? 2 * j : 0, i1 = (EPI == EPI_CARRY) ? 2 * j + 1 : 0;
+                ca[i0] += x0; ca[i1] += x1;
+                cb[i0] = fmaf(x0, x0, cb[i0]); cb[i1] = fmaf(x1, x1, cb[i1]);
               }
-              col_butterfly(a, b2, lane);
-              st_sum[chh] += a[0];
-              st_sq[chh] += b2[0];
             }
+            __syncwarp();
+          } else if (EPI == EPI_SMEM) {
+            float4* const wrow = reinterpret_cast<float4*>(sw + lane * 36);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 x = make_float4(__uint_as_float(pk[2 * j] << 16), __uint_as_float(pk[2 * j] & 0xffff0000u),
+                                       __uint_as_float(pk[2 * j + 1] << 16), __uint_as_float(pk[2 * j + 1] & 0xffff0000u));
+                if (relu_stats) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                wrow[j] = x;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) wrow[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float x = sw[rr * 36 + lane];
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            st_sum[chh] += s1;
+            st_sq[chh] += s2;
+            __syncwarp();   // the scratch is rewritten by the next chunk
+          } else {
+            float a[32], b2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+              float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+              if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              a[2 * j] = x0; a[2 * j + 1] = x1;
+              b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
+            }
+            col_butterfly(a, b2, lane);
+            st_sum[chh] += a[0];
+            st_sq[chh] += b2[0];
           }
         }
       }
@@ -1000,14 +1079,14 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int EPI>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
                         long long Mp, double* stats, int relu_stats, cudaStream_t s) {
-  using Cfg = Conv3Cfg<BN, MT>;
+  using Cfg = Conv3Cfg<BN, MT, EPI>;
   L3_REQUIRE(Cout <= kMaxCoutTc, "conv_tc: Cout=%d exceeds the bias staging buffer", Cout);
   static bool configured = false;
   if (!configured) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured = true;
   }
   CUtensorMap tmA, tmB;
@@ -1017,10 +1096,43 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   long long tiles = (long long)num_mp * num_n;
   int pairs = (int)(tiles < 74 ? tiles : 74);
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
-  k_conv3x3_tc3<BN, MT><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n, stats,
-                                                            relu_stats);
+  k_conv3x3_tc3<BN, MT, EPI><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n,
+                                                                 stats, relu_stats);
   L3_CHECK_LAUNCH();
   return 0;
+}
+
+// L3_CONV_EPI (statistics epilogue of the CTA-pair kernel): carry (default: EPI_CARRY for Cout 64, EPI_SMEM for Cout 128),
+// smem (EPI_SMEM for both), butterfly (EPI_BUTTERFLY everywhere).  Cout % 256 == 0 layers always use the butterfly
+// (no shared memory to spare, and their MMA time per output element hides it).
+static int conv_epi_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_CONV_EPI");
+    v = 0;
+    if (e && !strcmp(e, "smem")) v = 1;
+    else if (e && !strcmp(e, "butterfly")) v = 2;
+  }
+  return v;
+}
+static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
+                            int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s) {
+#define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s)
+  const int mode = conv_epi_mode();
+  if (BN == 256) {
+    if (stats == nullptr) L3_GO(256, 1, EPI_NONE);
+    L3_GO(256, 1, EPI_BUTTERFLY);
+  }
+  if (BN == 128) {
+    if (stats == nullptr) L3_GO(128, 2, EPI_NONE);
+    if (mode == 2) L3_GO(128, 2, EPI_BUTTERFLY);
+    L3_GO(128, 2, EPI_SMEM);
+  }
+  if (stats == nullptr) L3_GO(64, 4, EPI_NONE);
+  if (mode == 2) L3_GO(64, 4, EPI_BUTTERFLY);
+  if (mode == 1) L3_GO(64, 4, EPI_SMEM);
+  L3_GO(64, 4, EPI_CARRY);
+#undef L3_GO
 }
 
 // L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions, 3 = shared-halo regions on CTA
@@ -1048,9 +1160,7 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const int variant = conv_variant();
   if (variant >= 2) {
     if (variant == 3) {
-      if (BN == 256) return launch_conv3<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-      if (BN == 128) return launch_conv3<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-      return launch_conv3<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
+      return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     }
     if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
     if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
@@ -1661,7 +1771,8 @@ struct FcCfg {
   static const int kStages = 4;
   static const int kATile = kBM * 128;          // 128 rows x 128 B (only the first KPAD*2 bytes of a row are used)
   static const int kWTile = 64 * 128;
-  static const int kSmem = kStages * kATile + kWTile + 1024;
+  static const int kStoreScratch = 8 * 32 * 64; // per-epilogue-warp store transposition scratch (see k_conv3x3_tc3)
+  static const int kSmem = kStages * kATile + kWTile + kStoreScratch + 1024;
   static const int kAccs = 4;                   // TMEM accumulators of 64 columns
 };
 static const int kFcThreads = 32 + 128 + 256;   // MMA warp, 4 builder warps, 8 epilogue warps
@@ -1781,6 +1892,7 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
     const int half = (warp - 5) >> 2;
     const int c0 = half * 32;
     const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
+    uint4* const st_scr = reinterpret_cast<uint4*>(smem_w + Cfg::kWTile) + (warp - 5) * 128;
     float ca[32], cb[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
@@ -1792,7 +1904,10 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       const unsigned rr = m - b * HWp;
       const unsigned yp = rr / (unsigned)Wp, xp = rr - yp * (unsigned)Wp;
       const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
-      bf16* optr = out + (((long long)b * H + ((int)yp - 1)) * W + ((int)xp - 1)) * 64 + c0;
+      const int opix = valid ? (int)((b * (unsigned)H + (yp - 1)) * (unsigned)W + (xp - 1)) : -1;
+      int spix[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
       mbar_wait(&t_full[acc], aph);
       tc_fence_after();
       uint32_t v[32];
@@ -1803,25 +1918,35 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);   // accumulator is in registers: hand it back before the math
       if (++acc == ACCS) { acc = 0; aph ^= 1; }
-      if (valid) {
-        uint32_t pk[16];
+      uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
-          pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-          pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+        pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+        pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+      }
+      {
+        // coalesced store through the warp's swizzled scratch: one instruction writes 8 rows x 64 contiguous bytes
+        uint4* const srow = st_scr + lane * 4;
+        const int sw4 = (lane >> 1) & 3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) srow[c ^ sw4] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int R = (lane >> 2) + 8 * i;
+          const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
+          if (spix[i] >= 0) *reinterpret_cast<uint4*>(out + (long long)spix[i] * 64 + c0 + (lane & 3) * 8) = val;
         }
+        __syncwarp();
+      }
+      if (valid && stats != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(optr + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        if (stats != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x0 = __uint_as_float(pk[j] << 16);
-            const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
-            ca[2 * j] += x0; ca[2 * j + 1] += x1;
-            cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float x0 = __uint_as_float(pk[j] << 16);
+          const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
+          ca[2 * j] += x0; ca[2 * j + 1] += x1;
+          cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
         }
       }
     }

@@ -238,45 +238,63 @@ __device__ __forceinline__ void act8(const float (&z)[8], const float (&sc)[8], 
     y[i] = relu_first ? fmaxf(z[i], 0.f) * sc[i] + sh[i] : fmaxf(z[i] * sc[i] + sh[i], 0.f);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// Several independent 16-byte loads are issued per thread before any is consumed (U pixels, or U 2x2 windows): next to
+// a resident tensor-core CTA of the other tower's stream only ONE of these blocks fits on an SM, and its bytes in
+// flight -- not the block count -- then set the achieved HBM bandwidth.
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256, 3)
 k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int OH, int OW, long long npix,
-          const float* __restrict__ scale, const float* __restrict__ shift, int pool, int relu_first) {
+          const float* __restrict__ scale, const float* __restrict__ shift, int relu_first) {
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   float sc[8], sh[8];
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sh);
-  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
-    // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
-    const unsigned pr = (unsigned)p / (unsigned)OW;
-    const int ox = (int)((unsigned)p - pr * (unsigned)OW);
-    const long long b = pr / (unsigned)OH;
-    const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
-    float y[8];
-    if (!pool) {
-      float v[8];
-      load8(z + p * C + g * 8, v);
-      act8(v, sc, sh, relu_first, y);
-    } else {
-      const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
-      float v0[8], v1[8], v2[8], v3[8], t[8];
-      load8(z00, v0);
-      load8(z00 + C, v1);
-      load8(z00 + (long long)W * C, v2);
-      load8(z00 + (long long)W * C + C, v3);
-      act8(v0, sc, sh, relu_first, y);
-      act8(v1, sc, sh, relu_first, t);
+  constexpr int U = (POOL ? 2 : 4) / (sizeof(T) == 4 ? 2 : 1);   // fp32 (parity mode): half as many, the raw loads are twice as wide
+  const long long stride = (long long)gridDim.x * lanes;
+  for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+    Raw8<T> v[U][POOL ? 4 : 1];
+    long long dst[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
-      act8(v2, sc, sh, relu_first, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
-      act8(v3, sc, sh, relu_first, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      dst[u] = -1;
+      if (p < npix) {
+        // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
+        const unsigned pr = (unsigned)p / (unsigned)OW;
+        const int ox = (int)((unsigned)p - pr * (unsigned)OW);
+        const long long b = pr / (unsigned)OH;
+        const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
+        dst[u] = pad_off(b, oy, ox, OH, OW, C) + g * 8;
+        if (!POOL) {
+          ldraw(z + p * C + g * 8, v[u][0]);
+        } else {
+          const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+          ldraw(z00, v[u][0]);
+          ldraw(z00 + C, v[u][POOL ? 1 : 0]);
+          ldraw(z00 + (long long)W * C, v[u][POOL ? 2 : 0]);
+          ldraw(z00 + (long long)W * C + C, v[u][POOL ? 3 : 0]);
+        }
+      }
     }
-    store8(a + pad_off(b, oy, ox, OH, OW, C) + g * 8, y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (dst[u] < 0) continue;
+      float y[8], x[8];
+      unraw(v[u][0], x);
+      act8(x, sc, sh, relu_first, y);
+      if (POOL) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          float t[8];
+          unraw(v[u][POOL ? k : 0], x);
+          act8(x, sc, sh, relu_first, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], t[i]);
+        }
+      }
+      store8(a + dst[u], y);
+    }
   }
 }
 template <typename T>
@@ -289,7 +307,8 @@ int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* sc
   int lanes = kThreads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  k_act_fwd<T><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, pool, relu_first);
+  if (pool) k_act_fwd<T, true><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first);
+  else k_act_fwd<T, false><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -425,32 +444,36 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   const long long stride = (long long)gridDim.x * lanes;
   if (!POOL) {
-    constexpr int U = 2;
+    constexpr int U = sizeof(T) == 4 ? 2 : 4;   // 8 independent 16-byte loads in flight per thread (see k_act_fwd)
     for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
-      float g8[U][8], zs[U][8];
+      Raw8<T> rg[U], rz[U];
+      bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long p = p0 + u * stride;
-        if (p < npix) {
-          load8(da + p * C + g * 8, g8[u]);
-          load8(z + p * C + g * 8, zs[u]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { g8[u][i] = 0.f; zs[u][i] = 0.f; }
+        ok[u] = p < npix;
+        if (ok[u]) {
+          ldraw(da + p * C + g * 8, rg[u]);
+          ldraw(z + p * C + g * 8, rz[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float g8[8], zs[8];
+        unraw(rg[u], g8);
+        unraw(rz[u], zs);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float zz = zs[u][i];
+          const float zz = zs[i];
           // normal: dy = da where bn(z) > 0, xin = z ; relu_first: dy = da, xin = relu(z)
-          const float d = relu_first ? g8[u][i] : (fmaf(zz, sc[i], sf[i]) > 0.f ? g8[u][i] : 0.f);
+          const float d = relu_first ? g8[i] : (fmaf(zz, sc[i], sf[i]) > 0.f ? g8[i] : 0.f);
           float xin = relu_first ? fmaxf(zz, 0.f) : zz;
           if (kCentre) xin -= mu[i];
           s1[i] += d;
           s2[i] = fmaf(d, xin, s2[i]);
         }
+      }
     }
   } else {
     for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += stride) {
@@ -557,6 +580,40 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   load8(bn.c1 + g * 8, k.cb);
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!POOL) {
+    constexpr int U = sizeof(T) == 4 ? 2 : 4;   // 8 independent 16-byte loads in flight per thread (see k_act_fwd)
+    const long long stride = (long long)gridDim.x * lanes;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+      Raw8<T> rg[U], rv[U];
+      long long dst[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * stride;
+        dst[u] = -1;
+        if (p < npix) {
+          const unsigned pr = (unsigned)p / (unsigned)OW;
+          const int ox = (int)((unsigned)p - pr * (unsigned)OW);
+          const long long b = pr / (unsigned)OH;
+          const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
+          dst[u] = pad_off(b, oy, ox, H, W, C) + g * 8;
+          ldraw(da + p * C + g * 8, rg[u]);
+          ldraw(z + p * C + g * 8, rv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (dst[u] < 0) continue;
+        float g8[8], v[8], y[8], d[8];
+        unraw(rg[u], g8);
+        unraw(rv[u], v);
+        act8(v, k.sc, sf, relu_first, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
+        bwd_emit<T>(dz + dst[u], v, d, k, relu_first);
+      }
+    }
+    return;
+  }
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
     // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
     const unsigned pr = (unsigned)p / (unsigned)OW;
@@ -565,15 +622,6 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
     const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
     float g8[8];
     load8(da + p * C + g * 8, g8);
-    if (!POOL) {
-      float v[8], y[8], d[8];
-      load8(z + p * C + g * 8, v);
-      act8(v, k.sc, sf, relu_first, y);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
-      bwd_emit<T>(dz + pad_off(b, oy, ox, H, W, C) + g * 8, v, d, k, relu_first);
-      continue;
-    }
     float v[4][8], m[8];
     int arg[8];
     {
