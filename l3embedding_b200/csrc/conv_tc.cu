@@ -1518,6 +1518,55 @@ static int wgrad_variant() {
   return v;
 }
 
+// ---- raw input staging for the first-layer kernels ----------------------------------------------------------
+// Cin = 1 / 3 rows are 2 / 6 bytes per pixel: no TMA box fits, and gathering the taps with per-thread global loads
+// put one DRAM latency on the critical path of every tile (measured: the builder warps sat on their first use of the
+// loaded values).  Instead one thread stages, per tile of NPX consecutive flattened pixels, the three contiguous runs
+// of (NPX + 2) * C0 input values (filter rows ky = 0..2) into a shared-memory ring with 1-D bulk copies
+// (cp.async.bulk, 16-byte aligned windows around each run), several tiles ahead; the builders then read their taps
+// from shared memory.  Runs that stick out of the buffer are clipped -- only halo rows ever see the unloaded bytes.
+template <int C0, int NPX>
+struct RawCfg {
+  static const int kLen = 2 * C0 * (NPX + 2);           // bytes of one filter row's run
+  static const int kSeg = (kLen + 16 + 15) / 16 * 16;   // segment stride in the stage (room for the alignment slack)
+  static const int kStage = 3 * kSeg;
+};
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// one thread: the three bulk copies of the tile starting at flattened pixel m0; total16 = input bytes rounded up to 16
+template <int C0, int NPX>
+__device__ __forceinline__ void raw_issue(const uint8_t* __restrict__ xin, long long m0, int Wp, long long total16,
+                                          uint8_t* stage, uint64_t* bar) {
+  using R = RawCfg<C0, NPX>;
+  long long src[3];
+  int nb[3], shift[3];
+  uint32_t tx = 0;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const long long start = 2LL * C0 * (m0 + (ky - 1) * Wp - 1);
+    const long long a = start & ~15LL;                       // floor to 16 (also for negative starts)
+    const long long e = (start + R::kLen + 15) & ~15LL;
+    const long long ac = a < 0 ? 0 : a, ec = e > total16 ? total16 : e;
+    src[ky] = ac;
+    nb[ky] = ec > ac ? (int)(ec - ac) : 0;
+    shift[ky] = (int)(ac - a);
+    tx += (uint32_t)nb[ky];
+  }
+  mbar_expect_tx(bar, tx);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+    if (nb[ky] > 0) bulk_g2s(stage + ky * R::kSeg + shift[ky], xin + src[ky], (uint32_t)nb[ky], bar);
+}
+// byte offset, inside a stage, of tap column 0 of filter row ky for the tile's first pixel
+template <int C0, int NPX>
+__device__ __forceinline__ int raw_row_off(long long m0, int Wp, int ky) {
+  const long long start = 2LL * C0 * (m0 + (ky - 1) * Wp - 1);
+  return ky * RawCfg<C0, NPX>::kSeg + (int)(start & 15);
+}
+
 // ---- first-layer weight gradient on tensor cores ------------------------------------------------------------
 // Cin = 1 / 3 is far too narrow for a TMA box, so the im2col operand is BUILT in shared memory by 8 warps: per
 // 64-pixel chunk a [64 px][64] bf16 MN-major tile whose columns are the 9*C0 window taps, the 9 "inside" indicators
@@ -1527,12 +1576,14 @@ static int wgrad_variant() {
 //   D[col][co] += sum_px tile[px][col] * dz[px][co]        (M = 128 with the upper half aliasing the lower, N = 64)
 // so dW (27 or 9 rows), d1 (9 rows) and db (1 row) come out of ONE accumulator.  Replaces a 1.9 ms SIMT reduction.
 static const int kFwStages = 4;
+static const int kFwRawStages = 8;   // staged input runs (RawCfg<C0, 64>), a few hundred bytes each
 static const int kFwThreads = 64 + 256;
 static const int kFwTile = 64 * 128;   // bytes: A tile and dz tile
 
 // one 16-byte column chunk Q (columns 8Q .. 8Q+7) of a pixel row as raw bf16 bits; Q is a template parameter so tap /
 // channel / address offsets of every column fold to constants.  r0/r1/r2 point at the leftmost tap of the three filter
-// rows (clamped into the buffer for halo / out-of-range rows: their dz row is zero, so any finite value will do).
+// rows in the staged input runs (runs are clipped at the buffer ends: halo / out-of-range rows may read stale but
+// finite bytes -- their dz row is zero).
 template <int C0, int Q>
 __device__ __forceinline__ uint4 fw_chunk(const unsigned short* __restrict__ r0, const unsigned short* __restrict__ r1,
                                           const unsigned short* __restrict__ r2, int yp, int xp, int H, int W) {
@@ -1548,7 +1599,7 @@ __device__ __forceinline__ uint4 fw_chunk(const unsigned short* __restrict__ r0,
       if (i < K) {
         const int tap = i / C0, c = i - tap * C0, ky = tap / 3, kx = tap % 3;
         const unsigned short* rp = ky == 0 ? r0 : (ky == 1 ? r1 : r2);
-        bits = (uint32_t)__ldg(rp + kx * C0 + c);
+        bits = (uint32_t)rp[kx * C0 + c];
       } else if (i < K + 9) {
         const int tap = i - K;
         const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
@@ -1571,16 +1622,23 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
   constexpr int K = 9 * C0, NQ = (K + 10 + 7) / 8;   // 16-byte column chunks in use: 5 (C0=3) / 3 (C0=1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[kFwStages], empty_bar[kFwStages], tfull_bar;
+  using Raw = RawCfg<C0, 64>;
+  uint8_t* smem_in = smem + kFwStages * 2 * kFwTile;   // ring of staged input runs
+  __shared__ __align__(8) uint64_t full_bar[kFwStages], empty_bar[kFwStages], tfull_bar, r_full[kFwRawStages],
+      r_empty[kFwRawStages];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // zero every A tile once: the unused columns must read as zeros for the whole kernel
+  // zero every A tile once: the unused columns must read as zeros for the whole kernel; and the input ring, so that
+  // bytes a clipped run leaves unwritten are finite
   for (int i = threadIdx.x; i < kFwStages * kFwTile / 16; i += blockDim.x) {
     const int st = i / (kFwTile / 16), o = i % (kFwTile / 16);
     reinterpret_cast<uint4*>(smem + st * 2 * kFwTile)[o] = make_uint4(0, 0, 0, 0);
   }
+  for (int i = threadIdx.x; i < kFwRawStages * Raw::kStage / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_in)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFwStages; ++i) { mbar_init(&full_bar[i], 9); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kFwRawStages; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 8); }
     mbar_init(&tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1599,13 +1657,24 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      // producer: dz tiles (2-D TMA) and, kFwRawStages chunks ahead, the input runs the builders gather from
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(xin);
+      const long long total16 = (Mp * C0 * 2 + 15) & ~15LL;
+      const int Wp = W + 2;
+      int stage = 0, rs = 0;
+      uint32_t phase = 0, rph = 0;
+      for (int c = c_begin; c < c_end && c < c_begin + kFwRawStages; ++c)   // fresh ring: no wait
+        raw_issue<C0, 64>(xb, (long long)c * 64, Wp, total16, smem_in + (c - c_begin) * Raw::kStage, &r_full[c - c_begin]);
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], kFwTile);
         tma_load_2d(&tmZ, &full_bar[stage], smem + stage * 2 * kFwTile + kFwTile, 0, c * 64);
         if (++stage == kFwStages) { stage = 0; phase ^= 1; }
+        if (c + kFwRawStages < c_end) {   // the slot of chunk c is re-used by chunk c + kFwRawStages
+          mbar_wait(&r_empty[rs], rph);
+          raw_issue<C0, 64>(xb, (long long)(c + kFwRawStages) * 64, Wp, total16, smem_in + rs * Raw::kStage, &r_full[rs]);
+        }
+        if (++rs == kFwRawStages) { rs = 0; rph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -1632,16 +1701,17 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
     if (leader) umma_commit(&tfull_bar);
     __syncwarp();
   } else {
-    // ===== builders: 256 threads = 64 pixel rows x 4 parts; part p writes column chunk p (and p + 4).  The gather
-    // for chunk c+1 is issued before the stage of chunk c is awaited, so its global-load latency hides behind the
-    // barrier wait and the stores of chunk c =====
+    // ===== builders: 256 threads = 64 pixel rows x 4 parts; part p writes column chunk p (and p + 4) of the im2col
+    // tile, gathering its taps from the staged input runs (shared memory: no global latency on this path) =====
     const int bt = threadIdx.x - 64;
     const int row = bt & 63, part = bt >> 6;
     const int Wp = W + 2;
     const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
-    const unsigned short* xs = reinterpret_cast<const unsigned short*>(xin);
-    auto gather = [&](int c, uint4& o0, uint4& o1) {
-      const long long m = (long long)c * 64 + row;
+    int stage = 0, rs = 0;
+    uint32_t phase = 0, rph = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      const long long m0 = (long long)c * 64;
+      const long long m = m0 + row;
       int yp = 0, xp = 0;
       if (m < Mp) {
         const unsigned b = (unsigned)m / HWp;
@@ -1649,14 +1719,13 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
         yp = (int)(r / (unsigned)Wp);
         xp = (int)(r - (unsigned)yp * (unsigned)Wp);
       }
+      mbar_wait(&r_full[rs], rph);
+      const uint8_t* in_stage = smem_in + rs * Raw::kStage;
       const unsigned short* rp[3];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        long long p = m + (ky - 1) * Wp - 1;
-        p = p < 0 ? 0 : (p > Mp - 3 ? Mp - 3 : p);
-        rp[ky] = xs + p * C0;
-      }
-      o0 = o1 = make_uint4(0, 0, 0, 0);
+      for (int ky = 0; ky < 3; ++ky)
+        rp[ky] = reinterpret_cast<const unsigned short*>(in_stage + raw_row_off<C0, 64>(m0, Wp, ky)) + row * C0;
+      uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
       // `part` is warp-uniform (two builder warps per part): the switch does not diverge
       switch (part) {
         case 0:
@@ -1673,24 +1742,18 @@ k_first_wgrad_tc(const __grid_constant__ CUtensorMap tmZ, const bf16* __restrict
           if (NQ > 3) o0 = fw_chunk<C0, 3>(rp[0], rp[1], rp[2], yp, xp, H, W);
           break;
       }
-    };
-    int stage = 0;
-    uint32_t phase = 0;
-    uint4 cur0, cur1, nxt0, nxt1;
-    cur0 = cur1 = nxt0 = nxt1 = make_uint4(0, 0, 0, 0);
-    if (c_begin < c_end) gather(c_begin, cur0, cur1);
-    for (int c = c_begin; c < c_end; ++c) {
-      if (c + 1 < c_end) gather(c + 1, nxt0, nxt1);
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* tile = smem + stage * 2 * kFwTile;
-      if (part < NQ) *reinterpret_cast<uint4*>(tile + row * 128 + ((part ^ (row & 7)) << 4)) = cur0;
-      if (NQ > 4 && part == 0) *reinterpret_cast<uint4*>(tile + row * 128 + ((4 ^ (row & 7)) << 4)) = cur1;
+      if (part < NQ) *reinterpret_cast<uint4*>(tile + row * 128 + ((part ^ (row & 7)) << 4)) = o0;
+      if (NQ > 4 && part == 0) *reinterpret_cast<uint4*>(tile + row * 128 + ((4 ^ (row & 7)) << 4)) = o1;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (lane == 0) {
+        mbar_arrive(&full_bar[stage]);
+        mbar_arrive(&r_empty[rs]);   // the taps were consumed by the stores above
+      }
       if (++stage == kFwStages) { stage = 0; phase ^= 1; }
-      cur0 = nxt0;
-      cur1 = nxt1;
+      if (++rs == kFwRawStages) { rs = 0; rph ^= 1; }
     }
     // ===== epilogue (accumulator rows 0..K+9 live in TMEM lanes 0..63 -> quarters 0 and 1) =====
     const int q = warp & 3;
@@ -1733,7 +1796,8 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_wgrad_tc: pixel count out of range");
   if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
-  const int smem = kFwStages * 2 * kFwTile + 1024;
+  L3_REQUIRE(((uintptr_t)xin & 15) == 0, "first_wgrad_tc: input must be 16-byte aligned (bulk copies)");
+  const int smem = kFwStages * 2 * kFwTile + kFwRawStages * RawCfg<3, 64>::kStage + 1024;
   static bool configured = false;
   if (!configured) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_wgrad_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1772,34 +1836,25 @@ struct FcCfg {
   static const int kATile = kBM * 128;          // 128 rows x 128 B (only the first KPAD*2 bytes of a row are used)
   static const int kWTile = 64 * 128;
   static const int kStoreScratch = 8 * 32 * 64; // per-epilogue-warp store transposition scratch (see k_conv3x3_tc3)
-  static const int kSmem = kStages * kATile + kWTile + kStoreScratch + 1024;
+  static const int kRawStages = 8;
+  static const int kRawStage = RawCfg<C0, kBM>::kStage;
+  static const int kSmem = kStages * kATile + kWTile + kStoreScratch + kRawStages * kRawStage + 1024;
   static const int kAccs = 4;                   // TMEM accumulators of 64 columns
 };
-static const int kFcThreads = 32 + 128 + 256;   // MMA warp, 4 builder warps, 8 epilogue warps
-
-template <int C0>
-__device__ __forceinline__ void fc_load_row(const unsigned short* __restrict__ xin, long long m, int Wp, long long Mp,
-                                            unsigned short (&v)[9 * C0]) {
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    long long p = m + (ky - 1) * Wp - 1;     // leftmost tap of filter row ky
-    p = p < 0 ? 0 : (p > Mp - 3 ? Mp - 3 : p);   // only halo / out-of-range rows are ever clamped (their output is dropped)
-    const unsigned short* src = xin + p * C0;
-#pragma unroll
-    for (int j = 0; j < 3 * C0; ++j) v[ky * 3 * C0 + j] = __ldg(src + j);
-  }
-}
+static const int kFcThreads = 32 + 128 + 256 + 32;   // MMA warp, 4 builder warps, 8 epilogue warps, raw-copy warp
 
 template <int C0>
 __global__ void __launch_bounds__(kFcThreads, 1)
 k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
                 bf16* __restrict__ out, int H, int W, long long Mp, int num_tiles, double* __restrict__ stats) {
   using Cfg = FcCfg<C0>;
-  constexpr int K = Cfg::K, KPAD = Cfg::KPAD, NQ = Cfg::NQ, ST = Cfg::kStages, ACCS = Cfg::kAccs;
+  constexpr int K = Cfg::K, KPAD = Cfg::KPAD, NQ = Cfg::NQ, ST = Cfg::kStages, ACCS = Cfg::kAccs, RS = Cfg::kRawStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_w = smem + ST * Cfg::kATile;
-  __shared__ __align__(8) uint64_t a_full[ST], a_empty[ST], t_full[ACCS], t_empty[ACCS];
+  uint8_t* smem_scr = smem_w + Cfg::kWTile;
+  uint8_t* smem_in = smem_scr + Cfg::kStoreScratch;
+  __shared__ __align__(8) uint64_t a_full[ST], a_empty[ST], t_full[ACCS], t_empty[ACCS], r_full[RS], r_empty[RS];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[64];
 
@@ -1810,10 +1865,13 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
     const float v = k < K ? __ldg(w + k * 64 + co) : 0.f;
     *reinterpret_cast<bf16*>(smem_w + co * 128 + (((k >> 3) ^ (co & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
   }
+  for (int i = threadIdx.x; i < RS * Cfg::kRawStage / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_in)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 64) s_bias[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < ACCS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < RS; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -1822,14 +1880,27 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight tile (generic stores) -> visible to UMMA
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight tile / zeroed ring (generic stores) -> async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int Wp = W + 2;
 
-  if (warp == 0) {
+  if (warp == 13) {
+    // ===== raw-input producer: bulk copies run up to RS tiles ahead of the builders =====
+    if (lane == 0) {
+      const long long total16 = (Mp * C0 * 2 + 15) & ~15LL;
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&r_empty[rs], rph ^ 1);
+        raw_issue<C0, kBM>(reinterpret_cast<const uint8_t*>(xin), (long long)tile * kBM, Wp, total16,
+                           smem_in + rs * Cfg::kRawStage, &r_full[rs]);
+        if (++rs == RS) { rs = 0; rph ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(kBM, 64, 0, 0);
     constexpr uint32_t hi = desc_hi(1024);
@@ -1855,16 +1926,22 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       if (++acc == ACCS) { acc = 0; aph ^= 1; }
     }
   } else if (warp < 5) {
-    // ===== builders: thread = pixel row of the tile =====
+    // ===== builders: thread = pixel row of the tile; taps come from the staged input runs =====
     const int r = threadIdx.x - 32;
-    const unsigned short* xs = reinterpret_cast<const unsigned short*>(xin);
-    int stage = 0;
-    uint32_t sph = 0;
-    unsigned short cur[K], nxt[K];
-    if ((int)blockIdx.x < num_tiles) fc_load_row<C0>(xs, (long long)blockIdx.x * kBM + r, Wp, Mp, cur);
+    int stage = 0, rs = 0;
+    uint32_t sph = 0, rph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ntile = tile + gridDim.x;
-      if (ntile < num_tiles) fc_load_row<C0>(xs, (long long)ntile * kBM + r, Wp, Mp, nxt);
+      const long long m0 = (long long)tile * kBM;
+      mbar_wait(&r_full[rs], rph);
+      const uint8_t* in_stage = smem_in + rs * Cfg::kRawStage;
+      unsigned short v[K];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const unsigned short* src =
+            reinterpret_cast<const unsigned short*>(in_stage + raw_row_off<C0, kBM>(m0, Wp, ky)) + r * C0;
+#pragma unroll
+        for (int j = 0; j < 3 * C0; ++j) v[ky * 3 * C0 + j] = src[j];
+      }
       mbar_wait(&a_empty[stage], sph ^ 1);
       uint8_t* row = smem + stage * Cfg::kATile + r * 128;
 #pragma unroll
@@ -1873,18 +1950,20 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k0 = qd * 8 + 2 * e, k1 = k0 + 1;   // compile-time
-          const uint32_t lo = k0 < K ? (uint32_t)cur[k0 < K ? k0 : 0] : 0u;
-          const uint32_t hi16 = k1 < K ? (uint32_t)cur[k1 < K ? k1 : 0] : 0u;
+          const uint32_t lo = k0 < K ? (uint32_t)v[k0 < K ? k0 : 0] : 0u;
+          const uint32_t hi16 = k1 < K ? (uint32_t)v[k1 < K ? k1 : 0] : 0u;
           pk[e] = lo | (hi16 << 16);
         }
         *reinterpret_cast<uint4*>(row + ((qd ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to UMMA
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[stage]);
+      if (lane == 0) {
+        mbar_arrive(&a_full[stage]);
+        mbar_arrive(&r_empty[rs]);   // the taps were consumed by the stores above
+      }
       if (++stage == ST) { stage = 0; sph ^= 1; }
-#pragma unroll
-      for (int i = 0; i < K; ++i) cur[i] = nxt[i];
+      if (++rs == RS) { rs = 0; rph ^= 1; }
     }
   } else {
     // ===== epilogue: warp = (TMEM lane quarter, 32-column half) =====
@@ -1892,7 +1971,7 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
     const int half = (warp - 5) >> 2;
     const int c0 = half * 32;
     const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
-    uint4* const st_scr = reinterpret_cast<uint4*>(smem_w + Cfg::kWTile) + (warp - 5) * 128;
+    uint4* const st_scr = reinterpret_cast<uint4*>(smem_scr) + (warp - 5) * 128;
     float ca[32], cb[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
@@ -1970,6 +2049,7 @@ int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf1
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_conv_tc: C0=%d Cout=%d", C0, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_conv_tc: pixel count out of range");
+  L3_REQUIRE(((uintptr_t)xin & 15) == 0, "first_conv_tc: input must be 16-byte aligned (bulk copies)");
   static bool configured = false;
   if (!configured) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<1>::kSmem));

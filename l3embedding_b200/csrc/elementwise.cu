@@ -252,12 +252,12 @@ k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int O
   load8(shift + g * 8, sh);
   constexpr int U = (POOL ? 2 : 4) / (sizeof(T) == 4 ? 2 : 1);   // fp32 (parity mode): half as many, the raw loads are twice as wide
   const long long stride = (long long)gridDim.x * lanes;
-  for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+  for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
     Raw8<T> v[U][POOL ? 4 : 1];
     long long dst[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long p = p0 + u * stride;
+      const long long p = p0 + u * lanes;
       dst[u] = -1;
       if (p < npix) {
         // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
@@ -423,7 +423,7 @@ template int launch_gmaxpool_bwd<bf16>(const float*, int, const int*, const bf16
 // normalised sum the BN backward needs is sum(dy*xhat) = invstd * (S2 - mean * S1), formed in double precision by
 // k_bn_bwd_finalize.  (Fewer instructions per element: these kernels are issue-bound, not HBM-bound.)
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(256, POOL ? 2 : 3)
+__global__ void __launch_bounds__(256, 2)
 k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int C, int OH, int OW, long long npix,
             BnRef bn, int relu_first) {
   extern __shared__ float sh[];  // 2*C
@@ -445,12 +445,12 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   const long long stride = (long long)gridDim.x * lanes;
   if (!POOL) {
     constexpr int U = sizeof(T) == 4 ? 2 : 4;   // 8 independent 16-byte loads in flight per thread (see k_act_fwd)
-    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+    for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
       Raw8<T> rg[U], rz[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long p = p0 + u * stride;
+        const long long p = p0 + u * lanes;
         ok[u] = p < npix;
         if (ok[u]) {
           ldraw(da + p * C + g * 8, rg[u]);
@@ -581,14 +581,14 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (!POOL) {
-    constexpr int U = sizeof(T) == 4 ? 2 : 4;   // 8 independent 16-byte loads in flight per thread (see k_act_fwd)
+    constexpr int U = sizeof(T) == 4 ? 2 : 4;   // independent 16-byte load pairs in flight per thread (see k_act_fwd)
     const long long stride = (long long)gridDim.x * lanes;
-    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < npix; p0 += stride * U) {
+    for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
       Raw8<T> rg[U], rv[U];
       long long dst[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long p = p0 + u * stride;
+        const long long p = p0 + u * lanes;
         dst[u] = -1;
         if (p < npix) {
           const unsigned pr = (unsigned)p / (unsigned)OW;
