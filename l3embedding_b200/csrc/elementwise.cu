@@ -3,6 +3,7 @@
 // Reference semantics: keras BatchNormalization / Activation('relu') / MaxPooling2D as instantiated in
 // l3embedding/audio_model.py:370-437 and l3embedding/vision_model.py:124-190; Adam at l3embedding/train.py:282.
 // All activations are NHWC; per-thread work is 8 channels (one 16-byte bf16 vector) with coalesced access.
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace l3 {
@@ -567,7 +568,7 @@ __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8
   store8(dst, o);
 }
 
-template <typename T, bool POOL>
+template <typename T, bool POOL, int UU>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
             long long npix, BnRef bn, int relu_first) {
@@ -581,7 +582,7 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (!POOL) {
-    constexpr int U = sizeof(T) == 4 ? 2 : 4;   // independent 16-byte load pairs in flight per thread (see k_act_fwd)
+    constexpr int U = UU;   // independent 16-byte load pairs in flight per thread (see k_act_fwd)
     const long long stride = (long long)gridDim.x * lanes;
     for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
       Raw8<T> rg[U], rv[U];
@@ -682,8 +683,15 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
-  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  static int u = -1;   // L3_APPLY_U: pixels per thread-iteration of the un-pooled kernel (1 | 2 | 4)
+  if (u < 0) {
+    const char* e = getenv("L3_APPLY_U");
+    u = e ? atoi(e) : 1;
+  }
+  if (pool) k_bwd_apply<T, true, 1><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  else if (u == 4 && sizeof(T) == 2) k_bwd_apply<T, false, 4><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  else if (u == 2) k_bwd_apply<T, false, 2><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  else k_bwd_apply<T, false, 1><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
