@@ -627,77 +627,60 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
     }
     return;
   }
-  // pooled: software-pipelined like k_bwd_stats -- the next window's five raw loads fly during the current window's math
-  const long long pstride = (long long)gridDim.x * lanes;
-  auto fetch = [&](long long p, Raw8<T>& rg, Raw8<T> (&rz)[4]) {
-    ldraw(da + p * C + g * 8, rg);
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
     // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
     const unsigned pr = (unsigned)p / (unsigned)OW;
     const int ox = (int)((unsigned)p - pr * (unsigned)OW);
     const long long b = pr / (unsigned)OH;
     const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
-    const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
-    ldraw(z00, rz[0]);
-    ldraw(z00 + C, rz[1]);
-    ldraw(z00 + (long long)W * C, rz[2]);
-    ldraw(z00 + (long long)W * C + C, rz[3]);
-  };
-  long long p = (long long)blockIdx.x * lanes + lane;
-  Raw8<T> cg, cz[4], ng, nz[4];
-  if (p < npix) fetch(p, cg, cz);
-  while (p < npix) {
-    const long long pn = p + pstride;
-    if (pn < npix) fetch(pn, ng, nz);
-    const unsigned pr = (unsigned)p / (unsigned)OW;
-    const int ox = (int)((unsigned)p - pr * (unsigned)OW);
-    const long long b = pr / (unsigned)OH;
-    const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
-    float g8[8], m[8], x[8], y[8];
+    float g8[8];
+    load8(da + p * C + g * 8, g8);
+    float v[4][8], m[8];
     int arg[8];
-    unraw(cg, g8);
-    unraw(cz[0], x);
-    act8(x, k.sc, sf, relu_first, m);
+    {
+      const T* z00 = z + ((b * H + 2 * oy) * W + 2 * ox) * C + g * 8;
+      load8(z00, v[0]);
+      load8(z00 + C, v[1]);
+      load8(z00 + (long long)W * C, v[2]);
+      load8(z00 + (long long)W * C + C, v[3]);
+      float y[8];
+      act8(v[0], k.sc, sf, relu_first, m);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) arg[i] = 0;
+      for (int i = 0; i < 8; ++i) arg[i] = 0;
 #pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      unraw(cz[q], x);
-      act8(x, k.sc, sf, relu_first, y);
+      for (int q = 1; q < 4; ++q) {
+        act8(v[q], k.sc, sf, relu_first, y);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+        for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float d[8];
-      unraw(cz[q], x);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = (arg[i] == q && (relu_first || m[i] > 0.f)) ? g8[i] : 0.f;
-      bwd_emit<T>(dz + pad_off(b, 2 * oy + (q >> 1), 2 * ox + (q & 1), H, W, C) + g * 8, x, d, k, relu_first);
+      bwd_emit<T>(dz + pad_off(b, 2 * oy + (q >> 1), 2 * ox + (q & 1), H, W, C) + g * 8, v[q], d, k, relu_first);
     }
     // rows / columns dropped by valid pooling of odd sizes: dy = 0
     const bool last_x = (W & 1) && ox == OW - 1, last_y = (H & 1) && oy == OH - 1;
     if (last_x) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        load8(z + ((b * H + 2 * oy + r) * W + W - 1) * C + g * 8, x);
-        bwd_emit<T>(dz + pad_off(b, 2 * oy + r, W - 1, H, W, C) + g * 8, x, zero8, k, relu_first);
+        load8(z + ((b * H + 2 * oy + r) * W + W - 1) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, 2 * oy + r, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
       }
     }
     if (last_y) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        load8(z + ((b * H + H - 1) * W + 2 * ox + r) * C + g * 8, x);
-        bwd_emit<T>(dz + pad_off(b, H - 1, 2 * ox + r, H, W, C) + g * 8, x, zero8, k, relu_first);
+        load8(z + ((b * H + H - 1) * W + 2 * ox + r) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, H - 1, 2 * ox + r, H, W, C) + g * 8, v[0], zero8, k, relu_first);
       }
       if (last_x) {
-        load8(z + ((b * H + H - 1) * W + W - 1) * C + g * 8, x);
-        bwd_emit<T>(dz + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, x, zero8, k, relu_first);
+        load8(z + ((b * H + H - 1) * W + W - 1) * C + g * 8, v[0]);
+        bwd_emit<T>(dz + pad_off(b, H - 1, W - 1, H, W, C) + g * 8, v[0], zero8, k, relu_first);
       }
     }
-    cg = ng;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cz[q] = nz[q];
-    p = pn;
   }
 }
 // dz: zero-haloed padded (B,H+2,W+2,C); the halo is (re)zeroed here because the buffer is shared between layers
@@ -715,7 +698,7 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   static int u = -1;   // L3_APPLY_U: pixels per thread-iteration of the un-pooled kernel (1 | 2 | 4)
   if (u < 0) {
     const char* e = getenv("L3_APPLY_U");
-    u = e ? atoi(e) : 2;
+    u = e ? atoi(e) : 1;   // measured: 1 is fastest (776 us per step vs 977 / 867 for 2 / 4: the kernel is write-heavy)
   }
   if (pool) k_bwd_apply<T, true, 1><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   else if (u == 4 && sizeof(T) == 2) k_bwd_apply<T, false, 4><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
