@@ -580,7 +580,7 @@ __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8
   store8(dst, o);
 }
 
-template <typename T, bool POOL, int UU>
+template <typename T, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
             long long npix, BnRef bn, int relu_first) {
@@ -593,40 +593,6 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   load8(bn.c1 + g * 8, k.cb);
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (!POOL) {
-    constexpr int U = UU;   // independent 16-byte load pairs in flight per thread (see k_act_fwd)
-    const long long stride = (long long)gridDim.x * lanes;
-    for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
-      Raw8<T> rg[U], rv[U];
-      long long dst[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long p = p0 + u * lanes;
-        dst[u] = -1;
-        if (p < npix) {
-          const unsigned pr = (unsigned)p / (unsigned)OW;
-          const int ox = (int)((unsigned)p - pr * (unsigned)OW);
-          const long long b = pr / (unsigned)OH;
-          const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
-          dst[u] = pad_off(b, oy, ox, H, W, C) + g * 8;
-          ldraw(da + p * C + g * 8, rg[u]);
-          ldraw(z + p * C + g * 8, rv[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (dst[u] < 0) continue;
-        float g8[8], v[8], y[8], d[8];
-        unraw(rg[u], g8);
-        unraw(rv[u], v);
-        act8(v, k.sc, sf, relu_first, y);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
-        bwd_emit<T>(dz + dst[u], v, d, k, relu_first);
-      }
-    }
-    return;
-  }
   for (long long p = (long long)blockIdx.x * lanes + lane; p < npix; p += (long long)gridDim.x * lanes) {
     // 32-bit index math (npix < 2^31): 64-bit divisions cost ~100 instructions each in these issue-bound kernels
     const unsigned pr = (unsigned)p / (unsigned)OW;
@@ -635,6 +601,15 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
     const int oy = (int)(pr - (unsigned)b * (unsigned)OH);
     float g8[8];
     load8(da + p * C + g * 8, g8);
+    if (!POOL) {
+      float v[8], y[8], d[8];
+      load8(z + p * C + g * 8, v);
+      act8(v, k.sc, sf, relu_first, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = relu_first ? g8[i] : (y[i] > 0.f ? g8[i] : 0.f);
+      bwd_emit<T>(dz + pad_off(b, oy, ox, H, W, C) + g * 8, v, d, k, relu_first);
+      continue;
+    }
     float v[4][8], m[8];
     int arg[8];
     {
@@ -683,6 +658,8 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
     }
   }
 }
+// (Measured: more loads in flight per thread -- 2 / 4 pixels per iteration, or prefetching the next 2x2 window --
+// makes this write-heavy kernel SLOWER; it wants resident warps: 4 blocks / SM at 63 registers.)
 // dz: zero-haloed padded (B,H+2,W+2,C); the halo is (re)zeroed here because the buffer is shared between layers
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
@@ -695,15 +672,8 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  static int u = -1;   // L3_APPLY_U: pixels per thread-iteration of the un-pooled kernel (1 | 2 | 4)
-  if (u < 0) {
-    const char* e = getenv("L3_APPLY_U");
-    u = e ? atoi(e) : 1;   // measured: 1 is fastest (776 us per step vs 977 / 867 for 2 / 4: the kernel is write-heavy)
-  }
-  if (pool) k_bwd_apply<T, true, 1><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
-  else if (u == 4 && sizeof(T) == 2) k_bwd_apply<T, false, 4><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
-  else if (u == 2) k_bwd_apply<T, false, 2><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
-  else k_bwd_apply<T, false, 1><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
