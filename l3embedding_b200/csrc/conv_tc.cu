@@ -83,6 +83,30 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
+// division of n < 2^31 by a launch-time constant d >= 2 (Granlund-Montgomery): q = umulhi(n, mul) >> shift.  The
+// epilogues turn a flattened padded pixel index into (image, row, column) once per tile row; two hardware-less 32-bit
+// divisions (~60 dependent instructions) sat on every epilogue warp's per-tile critical path.
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;               // ceil(log2 d), d >= 2 -> l >= 1
+  f.mul = (uint32_t)(((1ull << (31 + l)) / d) + 1);
+  f.shift = l - 1;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.shift; }
+// flattened padded pixel m -> output pixel index (b*H + y)*W + x of the un-padded tensor, or -1 for halo / out-of-range
+__device__ __forceinline__ int out_pixel(uint32_t m, long long Mp, int H, int W, const FastDiv& dHWp, const FastDiv& dWp) {
+  const uint32_t b = fdiv(m, dHWp);
+  const uint32_t r = m - b * dHWp.d;
+  const uint32_t yp = fdiv(r, dWp), xp = r - yp * dWp.d;
+  const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
+  return valid ? (int)((b * (uint32_t)H + (yp - 1)) * (uint32_t)W + (xp - 1)) : -1;
+}
 // 16-byte vector reduction into global memory (sm_90+): one L2 atomic op for four consecutive floats
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -775,7 +799,7 @@ template <int BN, int MT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-              int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
+              int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats, FastDiv dHWp, FastDiv dWp) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -899,7 +923,6 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float* const sw = reinterpret_cast<float*>(smem_b + BST * Cfg::kBStage + Cfg::kStoreScratch) + (warp - 2) * (32 * 36);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
     float st_sum[NST], st_sq[NST];
 #pragma unroll
     for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
@@ -937,12 +960,8 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll 1
       for (int t = 0; t < MT; ++t) {
         // output pixel of this lane's row, -1 for halo / out-of-range rows (32-bit index math: Mp < 2^31)
-        const unsigned m = mbase + t * kBM;
-        const unsigned b = m / HWp;
-        const unsigned r = m - b * HWp;
-        const unsigned yp = r / (unsigned)Wp, xp = r - yp * (unsigned)Wp;
-        const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
-        const int opix = valid ? (int)((b * (unsigned)H + (yp - 1)) * (unsigned)W + (xp - 1)) : -1;
+        const int opix = out_pixel(mbase + t * kBM, Mp, H, W, dHWp, dWp);
+        const bool valid = opix >= 0;
         // store phase: lane l writes 16-byte piece (l & 3) of rows (l >> 2) + 8 i
         int spix[4];
 #pragma unroll
@@ -1097,7 +1116,9 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   int pairs = (int)(tiles < 74 ? tiles : 74);
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
   k_conv3x3_tc3<BN, MT, EPI><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n,
-                                                                 stats, relu_stats);
+                                                                 stats, relu_stats,
+                                                                 make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)),
+                                                                 make_fastdiv((uint32_t)(W + 2)));
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -1835,18 +1856,20 @@ struct FcCfg {
   static const int kStages = 4;
   static const int kATile = kBM * 128;          // 128 rows x 128 B (only the first KPAD*2 bytes of a row are used)
   static const int kWTile = 64 * 128;
-  static const int kStoreScratch = 8 * 32 * 64; // per-epilogue-warp store transposition scratch (see k_conv3x3_tc3)
+  static const int kEpiWarps = 16;              // two groups of 8: group g takes the CTA's tiles with local index = g mod 2
+  static const int kStoreScratch = kEpiWarps * 32 * 64;   // per-epilogue-warp store transposition scratch (see k_conv3x3_tc3)
   static const int kRawStages = 8;
   static const int kRawStage = RawCfg<C0, kBM>::kStage;
   static const int kSmem = kStages * kATile + kWTile + kStoreScratch + kRawStages * kRawStage + 1024;
   static const int kAccs = 4;                   // TMEM accumulators of 64 columns
 };
-static const int kFcThreads = 32 + 128 + 256 + 32;   // MMA warp, 4 builder warps, 8 epilogue warps, raw-copy warp
+static const int kFcThreads = 32 + 128 + 512 + 32;   // MMA warp, 4 builder warps, 16 epilogue warps, raw-copy warp
 
 template <int C0>
 __global__ void __launch_bounds__(kFcThreads, 1)
 k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
-                bf16* __restrict__ out, int H, int W, long long Mp, int num_tiles, double* __restrict__ stats) {
+                bf16* __restrict__ out, int H, int W, long long Mp, int num_tiles, double* __restrict__ stats,
+                FastDiv dHWp, FastDiv dWp) {
   using Cfg = FcCfg<C0>;
   constexpr int K = Cfg::K, KPAD = Cfg::KPAD, NQ = Cfg::NQ, ST = Cfg::kStages, ACCS = Cfg::kAccs, RS = Cfg::kRawStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1887,7 +1910,7 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
   const uint32_t tmem_base = tmem_base_s;
   const int Wp = W + 2;
 
-  if (warp == 13) {
+  if (warp == 5 + Cfg::kEpiWarps) {
     // ===== raw-input producer: bulk copies run up to RS tiles ahead of the builders =====
     if (lane == 0) {
       const long long total16 = (Mp * C0 * 2 + 15) & ~15LL;
@@ -1966,24 +1989,23 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       if (++rs == RS) { rs = 0; rph ^= 1; }
     }
   } else {
-    // ===== epilogue: warp = (TMEM lane quarter, 32-column half) =====
+    // ===== epilogue: warp = (tile group, TMEM lane quarter, 32-column half).  One warp's work on a tile is a long
+    // dependent chain (wait, TMEM load, pack, transpose, store, statistics: ~1900 cycles measured), so the tiles of
+    // a CTA alternate between two independent groups of 8 warps; each accumulator (tile index mod 4) belongs to one
+    // group.  Statistics are column sums read back from the store scratch -- no per-lane accumulators, which keeps
+    // the 704-thread CTA inside the register file =====
+    const int ew = warp - 5;
+    const int grp = ew >> 3;
     const int q = warp & 3;
-    const int half = (warp - 5) >> 2;
+    const int half = (ew >> 2) & 1;
     const int c0 = half * 32;
-    const unsigned HWp = (unsigned)(H + 2) * (unsigned)Wp;
-    uint4* const st_scr = reinterpret_cast<uint4*>(smem_scr) + (warp - 5) * 128;
-    float ca[32], cb[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) ca[j] = cb[j] = 0.f;
-    int acc = 0;
-    uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const unsigned m = (unsigned)tile * kBM + q * 32 + lane;
-      const unsigned b = m / HWp;
-      const unsigned rr = m - b * HWp;
-      const unsigned yp = rr / (unsigned)Wp, xp = rr - yp * (unsigned)Wp;
-      const bool valid = ((long long)m < Mp) && (yp >= 1) && ((int)yp <= H) && (xp >= 1) && ((int)xp <= W);
-      const int opix = valid ? (int)((b * (unsigned)H + (yp - 1)) * (unsigned)W + (xp - 1)) : -1;
+    uint4* const st_scr = reinterpret_cast<uint4*>(smem_scr) + ew * 128;
+    float s1 = 0.f, s2 = 0.f;   // this lane's column (c0 + lane): sum and sum of squares over the warp's tiles
+    int it = grp;               // local tile index
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & (ACCS - 1);
+      const uint32_t aph = (uint32_t)(it / ACCS) & 1u;
+      const int opix = out_pixel((uint32_t)tile * kBM + q * 32 + lane, Mp, H, W, dHWp, dWp);
       int spix[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
@@ -1996,7 +2018,6 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);   // accumulator is in registers: hand it back before the math
-      if (++acc == ACCS) { acc = 0; aph ^= 1; }
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -2004,36 +2025,37 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
         pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
         pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
       }
-      {
-        // coalesced store through the warp's swizzled scratch: one instruction writes 8 rows x 64 contiguous bytes
-        uint4* const srow = st_scr + lane * 4;
-        const int sw4 = (lane >> 1) & 3;
+      if (opix < 0) {   // halo / out-of-range rows: not stored, and zero in the statistics
 #pragma unroll
-        for (int c = 0; c < 4; ++c) srow[c ^ sw4] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int R = (lane >> 2) + 8 * i;
-          const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
-          if (spix[i] >= 0) *reinterpret_cast<uint4*>(out + (long long)spix[i] * 64 + c0 + (lane & 3) * 8) = val;
-        }
-        __syncwarp();
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
       }
-      if (valid && stats != nullptr) {
+      // coalesced store through the warp's swizzled scratch: one instruction writes 8 rows x 64 contiguous bytes
+      uint4* const srow = st_scr + lane * 4;
+      const int sw4 = (lane >> 1) & 3;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x0 = __uint_as_float(pk[j] << 16);
-          const float x1 = __uint_as_float(pk[j] & 0xffff0000u);
-          ca[2 * j] += x0; ca[2 * j + 1] += x1;
-          cb[2 * j] = fmaf(x0, x0, cb[2 * j]); cb[2 * j + 1] = fmaf(x1, x1, cb[2 * j + 1]);
+      for (int c = 0; c < 4; ++c) srow[c ^ sw4] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int R = (lane >> 2) + 8 * i;
+        const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
+        if (spix[i] >= 0) *reinterpret_cast<uint4*>(out + (long long)spix[i] * 64 + c0 + (lane & 3) * 8) = val;
+      }
+      if (stats != nullptr) {
+        // column `lane` of the 32 x 32 chunk: element (R, lane) sits in 16-byte piece (lane >> 3) ^ ((R >> 1) & 3)
+        const unsigned short* sc16 = reinterpret_cast<const unsigned short*>(st_scr);
+#pragma unroll
+        for (int R = 0; R < 32; ++R) {
+          const float x = __uint_as_float((uint32_t)sc16[R * 32 + ((((lane >> 3) ^ ((R >> 1) & 3)) << 3) | (lane & 7))] << 16);
+          s1 += x;
+          s2 = fmaf(x, x, s2);
         }
       }
+      __syncwarp();   // the scratch is rewritten by the next tile
     }
     if (stats != nullptr) {
-      __syncwarp();
-      col_butterfly(ca, cb, lane);
-      atomicAdd(&stats[c0 + lane], (double)ca[0]);
-      atomicAdd(&stats[64 + c0 + lane], (double)cb[0]);
+      atomicAdd(&stats[c0 + lane], (double)s1);
+      atomicAdd(&stats[64 + c0 + lane], (double)s2);
     }
   }
   tc_fence_before();
@@ -2059,8 +2081,9 @@ int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf1
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
   const int num_tiles = (int)((Mp + kBM - 1) / kBM);
   const int grid = num_tiles < 148 ? num_tiles : 148;
-  if (C0 == 1) k_first_conv_tc<1><<<grid, kFcThreads, FcCfg<1>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats);
-  else k_first_conv_tc<3><<<grid, kFcThreads, FcCfg<3>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats);
+  const FastDiv dHWp = make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)), dWp = make_fastdiv((uint32_t)(W + 2));
+  if (C0 == 1) k_first_conv_tc<1><<<grid, kFcThreads, FcCfg<1>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp);
+  else k_first_conv_tc<3><<<grid, kFcThreads, FcCfg<3>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp);
   L3_CHECK_LAUNCH();
   return 0;
 }
