@@ -17,8 +17,9 @@
 
 namespace l3 {
 
-static const int kFramesPerCta = 16;  // 8 packed complex FFTs per CTA
-static const int kFeThreads = 256;
+static const int kFramesPerCta = 8;   // 4 packed complex FFTs per CTA, transformed CONCURRENTLY (one barrier per pass)
+static const int kFePairs = kFramesPerCta / 2;
+static const int kFeThreads = 512;
 
 // ---- host-side table construction (float64, cast to float32 as kapre stores them) ---------------------
 static void build_mel(int sr, int n_fft, int n_mels, std::vector<int>& start, std::vector<int>& count,
@@ -105,23 +106,42 @@ int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem,
 // ---- device ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// In-place radix-2 DIF FFT on `z` (N complex, shared memory); output is bit-reversed.
-template <int N>
-__device__ __forceinline__ void fft_dif_inplace(float2* z, const float2* __restrict__ tw) {
+// In-place DIF FFT of G independent length-N sequences z[g*N .. g*N+N) (shared memory), radix-4 passes (two radix-2
+// stages fused in registers) plus one final radix-2 pass (log2 N is odd for both 512 and 2048); output bit-reversed.
+// All G transforms advance together, so a pass costs ONE block barrier: the previous version ran 11 barriers per
+// 2048-point transform with four butterflies per thread between them and was barrier-latency bound.
+template <int N, int G>
+__device__ __forceinline__ void fft_dif_batched(float2* z, const float2* __restrict__ tw) {
+  static_assert(N == 512 || N == 2048, "log2(N) must be odd");
 #pragma unroll 1
-  for (int half = N / 2; half >= 1; half >>= 1) {
-    const int tstride = (N / 2) / half;
-    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
-      int j = i & (half - 1);
-      int base = ((i - j) << 1) + j;
-      float2 a = z[base], b = z[base + half];
-      float2 w = tw[j * tstride];
-      float2 d = make_float2(a.x - b.x, a.y - b.y);
-      z[base] = make_float2(a.x + b.x, a.y + b.y);
-      z[base + half] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+  for (int h = N / 2; h >= 2; h >>= 2) {          // fused stages with halves h and h/2
+    const int ts1 = (N / 2) / h, hq = h >> 1;
+    for (int i = threadIdx.x; i < G * (N / 4); i += blockDim.x) {
+      float2* zg = z + (i / (N / 4)) * N;
+      const int q = i & (N / 4 - 1);
+      const int j = q & (hq - 1);
+      const int base = ((q - j) << 2) + j;
+      const float2 x0 = zg[base], x1 = zg[base + hq], x2 = zg[base + h], x3 = zg[base + h + hq];
+      const float2 wa = tw[j * ts1], wb = tw[(j + hq) * ts1], wc = tw[j * 2 * ts1];
+      const float2 y0 = make_float2(x0.x + x2.x, x0.y + x2.y), d0 = make_float2(x0.x - x2.x, x0.y - x2.y);
+      const float2 y1 = make_float2(x1.x + x3.x, x1.y + x3.y), d1 = make_float2(x1.x - x3.x, x1.y - x3.y);
+      const float2 y2 = make_float2(d0.x * wa.x - d0.y * wa.y, d0.x * wa.y + d0.y * wa.x);
+      const float2 y3 = make_float2(d1.x * wb.x - d1.y * wb.y, d1.x * wb.y + d1.y * wb.x);
+      const float2 e0 = make_float2(y0.x - y1.x, y0.y - y1.y), e1 = make_float2(y2.x - y3.x, y2.y - y3.y);
+      zg[base] = make_float2(y0.x + y1.x, y0.y + y1.y);
+      zg[base + hq] = make_float2(e0.x * wc.x - e0.y * wc.y, e0.x * wc.y + e0.y * wc.x);
+      zg[base + h] = make_float2(y2.x + y3.x, y2.y + y3.y);
+      zg[base + h + hq] = make_float2(e1.x * wc.x - e1.y * wc.y, e1.x * wc.y + e1.y * wc.x);
     }
     __syncthreads();
   }
+  // last stage (half = 1): twiddle 1
+  for (int i = threadIdx.x; i < G * (N / 2); i += blockDim.x) {
+    const float2 a = z[2 * i], b = z[2 * i + 1];
+    z[2 * i] = make_float2(a.x + b.x, a.y + b.y);
+    z[2 * i + 1] = make_float2(a.x - b.x, a.y - b.y);
+  }
+  __syncthreads();
 }
 
 // grid: (ceil(n_frames / kFramesPerCta), B).  Shared: clip window (staged by TMA bulk copy), FFT buffer, twiddles,
@@ -132,12 +152,12 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   constexpr int NF = N / 2 + 1;
   constexpr int LOGN = (N == 2048) ? 11 : 9;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* zbuf = reinterpret_cast<float2*>(smem_raw);                       // N complex
-  float2* tw = zbuf + N;                                                    // N/2 complex
+  constexpr int G = kFePairs, PWS = NF + 3;
+  float2* zbuf = reinterpret_cast<float2*>(smem_raw);                       // G x N complex (frame pairs A + iB)
+  float2* tw = zbuf + G * N;                                                // N/2 complex
   float* win = reinterpret_cast<float*>(tw + N / 2);                        // N
-  float* pw0 = win + N;                                                     // NF (+pad) power of frame A
-  float* pw1 = pw0 + (NF + 3);                                              // power of frame B
-  float* tile = pw1 + (NF + 3);                                             // n_out * kFramesPerCta
+  float* pw = win + N;                                                      // kFramesPerCta power spectra of PWS floats
+  float* tile = pw + kFramesPerCta * PWS;                                   // n_out * kFramesPerCta
   unsigned char* stage = reinterpret_cast<unsigned char*>(tile + p.n_out * kFramesPerCta);
   stage = reinterpret_cast<unsigned char*>(((uintptr_t)stage + 15) & ~(uintptr_t)15);
   __shared__ __align__(8) unsigned long long bar;
@@ -186,68 +206,71 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   __syncthreads();
 
   float local_max = -INFINITY;
-  for (int fp = 0; fp < nfr; fp += 2) {
-    const bool has_b = (fp + 1) < nfr;
-    // pack frame A (real) and frame B (imag), windowed; zero outside the clip (TF SAME zero padding)
-    const int sA = (f0 + fp) * p.n_hop - p.left_pad;
-    const int sB = sA + p.n_hop;
-    for (int t = threadIdx.x; t < N; t += blockDim.x) {
-      float xa = 0.f, xb = 0.f;
-      int ia = sA + t, ib = sB + t;
-      if (ia >= 0 && ia < p.n_samples)
-        xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] * (1.0f / 32768.0f)
-                 : reinterpret_cast<const float*>(stage)[ia - a_lo];
-      if (has_b && ib >= 0 && ib < p.n_samples)
-        xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
-                 : reinterpret_cast<const float*>(stage)[ib - a_lo];
-      float w = win[t];
-      zbuf[t] = make_float2(xa * w, xb * w);
-    }
-    __syncthreads();
-    fft_dif_inplace<N>(zbuf, tw);
-    // separate the two real spectra: XA[k] = (Z[k] + conj(Z[N-k]))/2 ; XB[k] = (Z[k] - conj(Z[N-k]))/(2i)
-    for (int k = threadIdx.x; k < NF; k += blockDim.x) {
-      int rk = __brev((unsigned)k) >> (32 - LOGN);
-      int rnk = __brev((unsigned)((N - k) & (N - 1))) >> (32 - LOGN);
-      float2 zk = zbuf[rk], zn = zbuf[rnk];
-      float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-      float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
-      pw0[k] = ar * ar + ai * ai;
-      pw1[k] = br * br + bi * bi;
-    }
-    __syncthreads();
-    // projection + log
-    for (int m = threadIdx.x; m < p.n_out; m += blockDim.x) {
-      float va, vb;
-      if (p.mel) {
-        int k0 = p.mel_start[m], n = p.mel_count[m];
-        const float* w = p.mel_weight + p.mel_offset[m];
-        float sa = 0.f, sb = 0.f;
-        for (int k = 0; k < n; ++k) {
-          float wk = w[k];
-          sa = fmaf(pw0[k0 + k], wk, sa);
-          sb = fmaf(pw1[k0 + k], wk, sb);
-        }
-        va = sqrtf(sa);
-        vb = sqrtf(sb);
-      } else {
-        va = sqrtf(pw0[m]);
-        vb = sqrtf(pw1[m]);
-      }
-      if (p.decibel) {
-        va = 10.0f * (logf(fmaxf(va, 1e-10f)) / 2.302585092994046f);
-        vb = 10.0f * (logf(fmaxf(vb, 1e-10f)) / 2.302585092994046f);
-        local_max = fmaxf(local_max, va);
-        if (has_b) local_max = fmaxf(local_max, vb);
-      } else {
-        va = logf(fmaxf(va, 1e-12f)) / 5.0f;
-        vb = logf(fmaxf(vb, 1e-12f)) / 5.0f;
-      }
-      tile[m * kFramesPerCta + fp] = va;
-      tile[m * kFramesPerCta + fp + 1] = vb;
-    }
-    __syncthreads();
+  // pack frame 2g (real) and frame 2g+1 (imag) of every pair, windowed; zero outside the clip (TF SAME zero padding)
+  // and for frames past the end of the clip's frame range
+  for (int i = threadIdx.x; i < G * N; i += blockDim.x) {
+    const int g = i / N, t = i & (N - 1);
+    const int fa = 2 * g, fb = 2 * g + 1;
+    const int ia = (f0 + fa) * p.n_hop - p.left_pad + t, ib = ia + p.n_hop;
+    float xa = 0.f, xb = 0.f;
+    if (fa < nfr && ia >= 0 && ia < p.n_samples)
+      xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] * (1.0f / 32768.0f)
+               : reinterpret_cast<const float*>(stage)[ia - a_lo];
+    if (fb < nfr && ib >= 0 && ib < p.n_samples)
+      xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
+               : reinterpret_cast<const float*>(stage)[ib - a_lo];
+    const float w = win[t];
+    zbuf[i] = make_float2(xa * w, xb * w);
   }
+  __syncthreads();
+  fft_dif_batched<N, G>(zbuf, tw);
+  // separate the two real spectra: XA[k] = (Z[k] + conj(Z[N-k]))/2 ; XB[k] = (Z[k] - conj(Z[N-k]))/(2i)
+  for (int i = threadIdx.x; i < G * NF; i += blockDim.x) {
+    const int g = i / NF, k = i - g * NF;
+    const int rk = __brev((unsigned)k) >> (32 - LOGN);
+    const int rnk = __brev((unsigned)((N - k) & (N - 1))) >> (32 - LOGN);
+    const float2 zk = zbuf[g * N + rk], zn = zbuf[g * N + rnk];
+    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+    const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+    pw[(2 * g) * PWS + k] = ar * ar + ai * ai;
+    pw[(2 * g + 1) * PWS + k] = br * br + bi * bi;
+  }
+  __syncthreads();
+  // projection + log: one (frame pair, output bin) item per thread-iteration
+  for (int i = threadIdx.x; i < G * p.n_out; i += blockDim.x) {
+    const int g = i / p.n_out, m = i - g * p.n_out;
+    const float* pw0 = pw + (2 * g) * PWS;
+    const float* pw1 = pw0 + PWS;
+    const bool has_a = 2 * g < nfr, has_b = 2 * g + 1 < nfr;
+    float va, vb;
+    if (p.mel) {
+      const int k0 = p.mel_start[m], n = p.mel_count[m];
+      const float* w = p.mel_weight + p.mel_offset[m];
+      float sa = 0.f, sb = 0.f;
+      for (int k = 0; k < n; ++k) {
+        const float wk = w[k];
+        sa = fmaf(pw0[k0 + k], wk, sa);
+        sb = fmaf(pw1[k0 + k], wk, sb);
+      }
+      va = sqrtf(sa);
+      vb = sqrtf(sb);
+    } else {
+      va = sqrtf(pw0[m]);
+      vb = sqrtf(pw1[m]);
+    }
+    if (p.decibel) {
+      va = 10.0f * (logf(fmaxf(va, 1e-10f)) / 2.302585092994046f);
+      vb = 10.0f * (logf(fmaxf(vb, 1e-10f)) / 2.302585092994046f);
+      if (has_a) local_max = fmaxf(local_max, va);
+      if (has_b) local_max = fmaxf(local_max, vb);
+    } else {
+      va = logf(fmaxf(va, 1e-12f)) / 5.0f;
+      vb = logf(fmaxf(vb, 1e-12f)) / 5.0f;
+    }
+    tile[m * kFramesPerCta + 2 * g] = va;
+    tile[m * kFramesPerCta + 2 * g + 1] = vb;
+  }
+  __syncthreads();
   // write the tile: rows of nfr contiguous floats
   for (int i = threadIdx.x; i < p.n_out * kFramesPerCta; i += blockDim.x) {
     int m = i / kFramesPerCta, f = i % kFramesPerCta;
@@ -285,7 +308,7 @@ static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out
   constexpr int NF = N / 2 + 1;
   constexpr int ES = I16 ? 2 : 4;
   size_t stage_elems = (size_t)(kFramesPerCta - 1) * p.n_hop + N + 16;
-  size_t smem = (size_t)N * 8 + (size_t)(N / 2) * 8 + (size_t)N * 4 + 2 * (size_t)(NF + 3) * 4 +
+  size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + (size_t)N * 4 + kFramesPerCta * (size_t)(NF + 3) * 4 +
                 (size_t)p.n_out * kFramesPerCta * 4 + 16 + stage_elems * ES;
   static bool configured = false;
   if (!configured) {
