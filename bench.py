@@ -49,9 +49,15 @@ def conv_class_gflop_per_pair():
     return {"conv_fwd": t, "conv_dgrad": t, "conv_wgrad": t}
 
 
-# DRAM bytes (read + write) per training step at B=64, summed over the launches of each convolution class, from ONE
-# `ncu --set full --clock-control none` capture of a whole step (profiles/r1_ncu_full_conv_step.txt)
-NCU_DRAM_BYTES_PER_STEP_B64 = {"conv_fwd": 4336.0e6, "conv_dgrad": 3753.7e6, "conv_wgrad": 5448.2e6}
+# DRAM bytes (read + write) per training step at B=64 and the time-weighted tensor-pipe activity, summed over the
+# launches of each convolution class, from ONE `ncu --clock-control none` capture of a whole step
+# (profiles/r1_ncu_full_conv_step.txt, reduced to profiles/r1_ncu_conv_classes.json by tools/ncu_conv_step.py)
+def ncu_conv_classes():
+    p = os.path.join(ROOT, "profiles", "r1_ncu_conv_classes.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -268,6 +274,7 @@ def main_gpu(args):
                 kernels[k] = {"ms_per_step": kms / prof_steps, "launches_per_step": n / prof_steps,
                               "frac_of_serial_step": kms / ms_serial}
         dom = max((k for k in kernels if k in gf), key=lambda k: kernels[k]["ms_per_step"])
+        ncu = ncu_conv_classes()
         achieved = kernels[dom]["tflops"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -287,8 +294,10 @@ def main_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         "traffic": (NCU_DRAM_BYTES_PER_STEP_B64[dom] if (B == 64 and args.dtype == "bf16") else None),
+                         "traffic": (ncu.get(dom, {}).get("dram_bytes") if (B == 64 and args.dtype == "bf16") else None),
                          "traffic_unit": "DRAM bytes per step for the class (ncu, profiles/r1_ncu_full_conv_step.txt)",
+                         "tensor_pipe_active_pct_ncu": {k: round(v["tensor_pipe_active_pct_time_weighted"], 1)
+                                                        for k, v in ncu.items()},
                          "peak_source": peak_src,
                          "whole_step_frac": value * TRAIN_GFLOP / 1e3 / world / peak_tf,
                          "serial_ms_per_step": ms_serial / prof_steps,
