@@ -125,6 +125,12 @@ int l3_conv3x3_fwd_stats(const void* in, const float* w, const float* bias, void
  * scratch >= 9*Cin*Cout floats. */
 int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
                      int use_tc, void* scratch, void* stream);
+/* the tensor-core data gradient with pass 1 of the BN/ReLU backward of the layer below fused into its epilogue (what
+ * the training step runs for un-pooled Conv -> BN -> ReLU layers): as l3_conv3x3_dgrad with dtype bf16 / use_tc 1, plus
+ * z_below (B,H,W,Cin) bf16, scale / shift (Cin floats: bn(z) = scale*z + shift) and
+ * sums: device double[2*Cin] <- sum(dy), sum(dy*z_below) per channel, dy = da where bn(z_below) > 0, else 0. */
+int l3_conv3x3_dgrad_stats(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, void* scratch,
+                           const void* z_below, const float* scale, const float* shift, double* sums, void* stream);
 /* weight/bias gradient: a zero-haloed padded (B,H+2,W+2,Cin), dz zero-haloed padded (B,H+2,W+2,Cout);
  * dw (3,3,Cin,Cout) and db (Cout, may be NULL) are overwritten. */
 int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,

@@ -525,9 +525,16 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     // this kernel's epilogue was tried and measured SLOWER -- +1.7 ms per step: the extra z loads and the second
     // transposing reduction make the epilogue, not the MMA pipe, the critical path of every dgrad launch.)
     ConvLayer& Lp = tw.L[l - 1];
+    // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) rides in the dgrad
+    // epilogue, in the coalesced store-phase mapping, and da is not read again for it
+    const bool fuse_stats = L.tc && c->use_tc && !Lp.pool && !Lp.relu_first && conv_tc_fuses_bwd_stats();
     {
       ProfScope ps(c, PROF_CONV_DGRAD, s);
-      if (L.tc && c->use_tc) {
+      if (fuse_stats) {
+        if (launch_dgrad3x3_tc_bwdstats((const bf16*)dz, L.wt_pk, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, (const bf16*)Lp.z,
+                                        Lp.bn.scale, Lp.bn.shift, Lp.bn.sum, s))
+          return -1;
+      } else if (L.tc && c->use_tc) {
         if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
       } else {
         if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
@@ -536,7 +543,8 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     }
     // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz (padded, full resolution)
     long long rows_p = (long long)B * Lp.H * Lp.W;
-    if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+    if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s))
+      return -1;
     if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
     if (launch_bwd_apply<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
   }
@@ -1049,6 +1057,16 @@ int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int
   if (dtype == L3_DTYPE_BF16)
     return launch_conv3x3_simt<bf16>((const bf16*)dz, (const float*)scratch, nullptr, (bf16*)da, B, H, W, Cout, Cin, s);
   return launch_conv3x3_simt<float>((const float*)dz, (const float*)scratch, nullptr, (float*)da, B, H, W, Cout, Cin, s);
+}
+int l3_conv3x3_dgrad_stats(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, void* scratch,
+                           const void* z_below, const float* scale, const float* shift, double* sums, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  L3_REQUIRE(scratch && z_below && scale && shift && sums, "dgrad_stats: NULL argument");
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc dgrad: C%%64");
+  L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+  if (launch_pack_weights_tc(w, (bf16*)scratch, Cin, Cout, 1, s)) return -1;
+  return launch_dgrad3x3_tc_bwdstats((const bf16*)dz, (const bf16*)scratch, (bf16*)da, B, H, W, Cout, Cin,
+                                     (const bf16*)z_below, scale, shift, sums, s);
 }
 int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                      int dtype, int use_tc, void* stream) {

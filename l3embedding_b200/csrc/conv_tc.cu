@@ -718,8 +718,12 @@ static const int kMaxCoutTc = 512;   // bias staging in shared memory
 enum { EPI_NONE = 0,        // no statistics (dgrad, inference): leanest register footprint
        EPI_BUTTERFLY = 1,   // 31-shuffle transposing butterfly per 32x32 chunk (~350 instructions)
        EPI_SMEM = 2,        // transpose through a per-warp 32x36-float scratch (needs 36 KB of shared memory: BN < 256)
-       EPI_CARRY = 3 };     // per-lane partial sums carried in registers over ALL tiles, one butterfly per kernel
+       EPI_CARRY = 3,       // per-lane partial sums carried in registers over ALL tiles, one butterfly per kernel
                             // (a warp must own a single chunk: BN = 64; costs ~50 registers per thread)
+       EPI_FWD2 = 4,        // statistics taken in the STORE-phase mapping (lane = 16-byte piece of 4 rows): 8 column
+                            // partials per lane and chunk, carried over the tiles; works for every BN
+       EPI_BWD = 5 };       // dgrad: the same mapping reads the matching 16 bytes of the layer-below's z (coalesced) and
+                            // carries sum(dy), sum(dy*z) -- pass 1 of the BN/ReLU backward without re-reading da
 template <int BN_, int MT_, int EPI_>
 struct Conv3Cfg {
   static const int BN = BN_, MT = MT_;
@@ -799,7 +803,8 @@ template <int BN, int MT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-              int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats, FastDiv dHWp, FastDiv dWp) {
+              int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats, FastDiv dHWp, FastDiv dWp,
+              const bf16* __restrict__ zprev, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -808,11 +813,17 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[kMaxCoutTc];   // whole bias vector, read by the epilogue as float4
+  __shared__ __align__(16) float s_aux[EPI == EPI_BWD ? 2 * kMaxCoutTc : 4];   // EPI_BWD: BN scale | shift of the layer below
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   if (bias != nullptr)
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_bias[i] = __ldg(bias + i);
+  if (EPI == EPI_BWD)
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+      s_aux[i] = __ldg(bn_scale + i);
+      s_aux[kMaxCoutTc + i] = __ldg(bn_shift + i);
+    }
   if (threadIdx.x == 0) {
     for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -929,8 +940,39 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float ca[EPI == EPI_CARRY ? 32 : 1], cb[EPI == EPI_CARRY ? 32 : 1];
 #pragma unroll
     for (int j = 0; j < (EPI == EPI_CARRY ? 32 : 1); ++j) ca[j] = cb[j] = 0.f;
+    // EPI_FWD2 / EPI_BWD: lane l carries, per chunk slot, the partial sums of columns (l & 3) * 8 .. + 7 over the rows
+    // (l >> 2) + 8 i it stores
+    constexpr bool kStorePhaseStats = (EPI == EPI_FWD2 || EPI == EPI_BWD);
+    float f1[kStorePhaseStats ? NST : 1][8], f2[kStorePhaseStats ? NST : 1][8];
+#pragma unroll
+    for (int c = 0; c < (kStorePhaseStats ? NST : 1); ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f1[c][j] = f2[c][j] = 0.f;
     int st_n0 = -1;
     auto flush_stats = [&]() {
+      if (kStorePhaseStats) {
+        if (stats != nullptr && st_n0 >= 0) {
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < (kStorePhaseStats ? NST : 1); ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = f1[c][j], b = f2[c][j];
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+              }
+              if (lane < 4) {
+                const int col = st_n0 + (2 * c + half) * 32 + lane * 8 + j;
+                atomicAdd(&stats[col], (double)a);
+                atomicAdd(&stats[Cout + col], (double)b);
+              }
+              f1[c][j] = f2[c][j] = 0.f;
+            }
+        }
+        return;
+      }
       if (EPI != EPI_NONE && stats != nullptr && st_n0 >= 0) {
         if (EPI == EPI_CARRY) {
           __syncwarp();
@@ -971,7 +1013,15 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int chh = 0; chh < NST; ++chh) {
           const int c0 = (2 * chh + half) * 32;
           uint32_t pk[16];
-          if (EPI == EPI_CARRY || EPI == EPI_NONE) {
+          uint4 zr[EPI == EPI_BWD ? 4 : 1];
+          if (EPI == EPI_BWD) {
+            // the layer-below's z for the pieces this lane will store: issued before the TMEM load / transposition
+#pragma unroll
+            for (int i = 0; i < (EPI == EPI_BWD ? 4 : 1); ++i)
+              if (spix[i] >= 0)
+                zr[i] = *reinterpret_cast<const uint4*>(zprev + (long long)spix[i] * Cout + n0 + c0 + (lane & 3) * 8);
+          }
+          if (EPI == EPI_CARRY || EPI == EPI_NONE || kStorePhaseStats) {
             // 16 columns at a time: half the live registers of the 32-column path
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -1020,12 +1070,48 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int i = 0; i < 4; ++i) {
               const int R = (lane >> 2) + 8 * i;
               const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
-              if (spix[i] >= 0)
+              if (spix[i] >= 0) {
                 *reinterpret_cast<uint4*>(out + (long long)spix[i] * Cout + n0 + c0 + (lane & 3) * 8) = val;
+                if (kStorePhaseStats && stats != nullptr) {
+                  const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+                  float x[8];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    x[2 * j] = __uint_as_float(w4[j] << 16);
+                    x[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+                  }
+                  constexpr int CS = kStorePhaseStats ? 1 : 0;
+                  if (EPI == EPI_FWD2) {
+                    // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float xv = relu_stats ? fmaxf(x[j], 0.f) : x[j];
+                      f1[chh * CS][j] += xv;
+                      f2[chh * CS][j] = fmaf(xv, xv, f2[chh * CS][j]);
+                    }
+                  } else {
+                    // dy = da where bn(z) > 0 (ReLU after BN), raw sums sum(dy), sum(dy*z) -- k_bwd_stats<bf16>'s contract
+                    const uint32_t z4[4] = {zr[i * CS].x, zr[i * CS].y, zr[i * CS].z, zr[i * CS].w};
+                    const float* scp = &s_aux[n0 + c0 + (lane & 3) * 8];
+                    const float4 sc0 = *reinterpret_cast<const float4*>(scp), sc1 = *reinterpret_cast<const float4*>(scp + 4);
+                    const float4 sh0 = *reinterpret_cast<const float4*>(scp + kMaxCoutTc);
+                    const float4 sh1 = *reinterpret_cast<const float4*>(scp + kMaxCoutTc + 4);
+                    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float zz = __uint_as_float((j & 1) ? (z4[j >> 1] & 0xffff0000u) : (z4[j >> 1] << 16));
+                      const float d = fmaf(zz, sc[j], sh[j]) > 0.f ? x[j] : 0.f;
+                      f1[chh * CS][j] += d;
+                      f2[chh * CS][j] = fmaf(d, zz, f2[chh * CS][j]);
+                    }
+                  }
+                }
+              }
             }
             __syncwarp();   // the scratch is rewritten by the next chunk
           }
-          if (EPI == EPI_NONE || stats == nullptr) continue;
+          if (EPI == EPI_NONE || kStorePhaseStats || stats == nullptr) continue;
           // statistics of the values as stored (bf16-rounded); halo / out-of-range rows contribute nothing
           if (EPI == EPI_CARRY) {
             if (valid) {
@@ -1098,9 +1184,14 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+// EPI_BWD only: z / BN scale / BN shift of the layer whose activation gradient this dgrad produces
+struct BwdFuse {
+  const bf16* z;
+  const float *scale, *shift;
+};
 template <int BN, int MT, int EPI>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
-                        long long Mp, double* stats, int relu_stats, cudaStream_t s) {
+                        long long Mp, double* stats, int relu_stats, cudaStream_t s, BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   L3_REQUIRE(Cout <= kMaxCoutTc, "conv_tc: Cout=%d exceeds the bias staging buffer", Cout);
   static bool configured = false;
@@ -1118,7 +1209,7 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   k_conv3x3_tc3<BN, MT, EPI><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n,
                                                                  stats, relu_stats,
                                                                  make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)),
-                                                                 make_fastdiv((uint32_t)(W + 2)));
+                                                                 make_fastdiv((uint32_t)(W + 2)), bf.z, bf.scale, bf.shift);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -1130,16 +1221,30 @@ static int conv_epi_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("L3_CONV_EPI");
-    v = 0;
+    v = 3;
     if (e && !strcmp(e, "smem")) v = 1;
     else if (e && !strcmp(e, "butterfly")) v = 2;
+    else if (e && !strcmp(e, "carry")) v = 0;
+    else if (e && !strcmp(e, "store")) v = 3;
   }
   return v;
 }
 static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
-                            int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s) {
-#define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s)
+                            int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s,
+                            BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
+#define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s, bf)
   const int mode = conv_epi_mode();
+  if (bf.z != nullptr) {   // dgrad with fused BN-backward statistics
+    L3_REQUIRE(stats != nullptr && bias == nullptr && !relu_stats, "fused dgrad statistics: stats, no bias, no relu_first");
+    if (BN == 256) L3_GO(256, 1, EPI_BWD);
+    if (BN == 128) L3_GO(128, 2, EPI_BWD);
+    L3_GO(64, 4, EPI_BWD);
+  }
+  if (mode == 3 && stats != nullptr) {
+    if (BN == 256) L3_GO(256, 1, EPI_FWD2);
+    if (BN == 128) L3_GO(128, 2, EPI_FWD2);
+    L3_GO(64, 4, EPI_FWD2);
+  }
   if (BN == 256) {
     if (stats == nullptr) L3_GO(256, 1, EPI_NONE);
     L3_GO(256, 1, EPI_BUTTERFLY);
@@ -1194,6 +1299,28 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   if (BN == 256) return launch_conv_bn<256>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
   if (BN == 128) return launch_conv_bn<128>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
   return launch_conv_bn<64>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+}
+
+int conv_tc_fuses_bwd_stats() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_DGRAD_FUSE_STATS");
+    v = (e ? atoi(e) : 1) != 0 && conv_variant() == 3;
+  }
+  return v;
+}
+
+int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
+                                const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
+                                cudaStream_t s) {
+  // a conv with Cin' = Cout (of the layer), Cout' = Cin (= channels of the layer below)
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "dgrad_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  L3_REQUIRE(conv_variant() == 3, "fused dgrad statistics need the CTA-pair kernel");
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
+  const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  return launch_conv3_any(BN, dz, packed_wt, nullptr, da, H, W, Cout, Cin, Mp, sums, 0, s,
+                          BwdFuse{z_below, scale_below, shift_below});
 }
 
 // ---------------------------------------------------------------------------------------------------------

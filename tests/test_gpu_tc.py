@@ -119,6 +119,40 @@ def test_tc_dgrad(lib, shape):
     assert err <= 2e-2 * max(1.0, xr.grad.abs().max().item()), err
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(2, 70, 66, 64, 64), (2, 40, 36, 128, 128), (3, 20, 17, 256, 256)])
+def test_tc_dgrad_fused_bn_backward_statistics(lib, shape):
+    """dgrad whose epilogue also reduces sum(dy), sum(dy*z) of the layer below (dy = da where scale*z + shift > 0): da is
+    bit-identical to the plain dgrad, the sums match the stored da."""
+    from l3embedding_b200 import _lib
+    B, H, W, Ci, Co = shape
+    x, w, b, dz = _setup(shape, seed=17)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(B, H, W, Ci, generator=g).bfloat16()
+    scale = torch.randn(Ci, generator=g)            # both signs: the mask is on scale*z + shift, not on z
+    shift = 0.3 * torch.randn(Ci, generator=g)
+    dzp = _pad(dz).contiguous().cuda()
+    da = torch.full((B, H, W, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
+    da0 = torch.full((B, H, W, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
+    sums = torch.full((2 * Ci,), float("nan"), dtype=torch.float64, device="cuda")
+    scratch = torch.empty(9 * Ci * Co * 2, dtype=torch.bfloat16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    wd, zd, scd, shd = w.cuda(), z.cuda(), scale.cuda(), shift.cuda()
+    _lib.check(lib.l3_conv3x3_dgrad(_p(dzp), _p(wd), _p(da0), B, H, W, Ci, Co, 1, 1, _p(scratch), st), "dgrad")
+    _lib.check(lib.l3_conv3x3_dgrad_stats(_p(dzp), _p(wd), _p(da), B, H, W, Ci, Co, _p(scratch), _p(zd), _p(scd), _p(shd),
+                                          _p(sums), st), "dgrad_stats")
+    torch.cuda.synchronize()
+    assert torch.equal(da.view(torch.int16), da0.view(torch.int16))
+    dav, zv = da.float().cpu().reshape(-1, Ci), z.float().reshape(-1, Ci)
+    mask = (zv.double() * scale.double() + shift.double()) > 0   # the kernel's fp32 fma rounds the exact value: same sign
+    dy = torch.where(mask, dav, torch.zeros_like(dav)).double()
+    s1, s2 = dy.sum(0), (dy * zv.double()).sum(0)
+    got = sums.cpu()
+    tol1 = 1e-5 * dy.abs().sum(0).max().item() + 1e-6
+    tol2 = 1e-5 * (dy * zv.double()).abs().sum(0).max().item() + 1e-6
+    assert (got[:Ci] - s1).abs().max().item() <= tol1, ((got[:Ci] - s1).abs().max().item(), tol1)
+    assert (got[Ci:] - s2).abs().max().item() <= tol2, ((got[Ci:] - s2).abs().max().item(), tol2)
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_tc_wgrad(lib, shape):
     from l3embedding_b200 import _lib
