@@ -1214,14 +1214,14 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   return 0;
 }
 
-// L3_CONV_EPI (statistics epilogue of the CTA-pair kernel): carry (default: EPI_CARRY for Cout 64, EPI_SMEM for Cout 128),
-// smem (EPI_SMEM for both), butterfly (EPI_BUTTERFLY everywhere).  Cout % 256 == 0 layers always use the butterfly
-// (no shared memory to spare, and their MMA time per output element hides it).
+// L3_CONV_EPI (statistics epilogue of the CTA-pair kernel): unset = per-configuration best (see launch_conv3_any);
+// carry (EPI_CARRY for Cout 64, EPI_SMEM for Cout 128), smem, butterfly, store (EPI_FWD2 everywhere) force one flavour
+// for A/B runs.  Cout % 256 == 0 layers have no shared memory to spare for EPI_SMEM.
 static int conv_epi_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("L3_CONV_EPI");
-    v = 3;
+    v = 4;   // auto: the fastest flavour measured per tile configuration (profiles/r1_launches_step_detail.txt)
     if (e && !strcmp(e, "smem")) v = 1;
     else if (e && !strcmp(e, "butterfly")) v = 2;
     else if (e && !strcmp(e, "carry")) v = 0;
@@ -1244,6 +1244,13 @@ static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const 
     if (BN == 256) L3_GO(256, 1, EPI_FWD2);
     if (BN == 128) L3_GO(128, 2, EPI_FWD2);
     L3_GO(64, 4, EPI_FWD2);
+  }
+  if (mode == 4 && stats != nullptr) {
+    // measured per launch (B = 64): BN 256: butterfly 127 us vs store-phase 136; BN 128: store-phase 138 vs smem 143;
+    // BN 64: carry 216 vs store-phase 225 vs smem 302
+    if (BN == 256) L3_GO(256, 1, EPI_BUTTERFLY);
+    if (BN == 128) L3_GO(128, 2, EPI_FWD2);
+    L3_GO(64, 4, EPI_CARRY);
   }
   if (BN == 256) {
     if (stats == nullptr) L3_GO(256, 1, EPI_NONE);
@@ -1304,8 +1311,11 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
 int conv_tc_fuses_bwd_stats() {
   static int v = -1;
   if (v < 0) {
+    // default OFF: measured neutral at B = 64 (the fused launches cost what the separate k_bwd_stats launches saved:
+    // 356 vs 210 + 135 us at 64 channels, 206 vs 153 + 77 at 128, 178 vs ~170 + 45 at 256/512) -- the extra z loads sit
+    // on the epilogue's critical path; kept as a tested option
     const char* e = getenv("L3_DGRAD_FUSE_STATS");
-    v = (e ? atoi(e) : 1) != 0 && conv_variant() == 3;
+    v = (e ? atoi(e) : 0) != 0 && conv_variant() == 3;
   }
   return v;
 }
