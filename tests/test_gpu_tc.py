@@ -204,37 +204,41 @@ np.savez(sys.argv[1], **{k.replace('/', '.'): x for k, x in g.items()})
 
 def test_kernel_variants_agree_on_a_training_step(tmp_path):
     """The same bf16 training step through (a) per-CTA kernels with per-chunk butterfly statistics, per-tap wgrad tiles
-    and the SIMT first-layer wgrad (L3_CONV_TC_VARIANT=2, L3_WGRAD_TC_VARIANT=1, L3_FIRST_WGRAD_TC=0) and (b) the
-    default CTA-pair kernels with carried / transposed statistics, shared-halo wgrad and the tensor-core first-layer
-    wgrad: identical math, different reduction orders."""
+    and the SIMT first-layer wgrad (L3_CONV_TC_VARIANT=2, L3_WGRAD_TC_VARIANT=1, L3_FIRST_WGRAD_TC=0), (b) the
+    defaults (CTA-pair kernels, per-configuration statistics epilogues, shared-halo wgrad, tensor-core first layer) and
+    (c) the store-phase statistics everywhere plus BN-backward pass 1 fused into the dgrad epilogues
+    (L3_CONV_EPI=store, L3_DGRAD_FUSE_STATS=1): identical math, different reduction orders."""
     import os
     import subprocess
     import sys
     import numpy as np
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for name, env in (("a", {"L3_CONV_TC_VARIANT": "2", "L3_FIRST_WGRAD_TC": "0", "L3_WGRAD_TC_VARIANT": "1"}), ("b", {})):
+    outs = {}
+    for name, env in (("a", {"L3_CONV_TC_VARIANT": "2", "L3_FIRST_WGRAD_TC": "0", "L3_WGRAD_TC_VARIANT": "1"}), ("b", {}),
+                      ("c", {"L3_CONV_EPI": "store", "L3_DGRAD_FUSE_STATS": "1"})):
         path = str(tmp_path / (name + ".npz"))
         e = dict(os.environ)
         e.update(env)
         subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root, path], check=True, env=e, timeout=300)
-        outs.append(dict(np.load(path)))
-    ga, gb = outs
-    assert abs(float(ga["__loss__"]) - float(gb["__loss__"])) <= 2e-3
-    worst = []
-    for k in ga:
-        if k == "__loss__":
-            continue
-        a, b = ga[k].ravel().astype(np.float64), gb[k].ravel().astype(np.float64)
-        # conv biases before a training-mode BN have analytically zero gradients, and the input-BN gamma/beta are small
-        # residuals of huge cancelling sums: all noise-dominated in bf16 storage (the fp64 and bf16-emulating oracles
-        # themselves differ by 9x on audio/bn0/gamma), so only the well-conditioned tensors are compared
-        if k.endswith(".bias") or ".bn0." in k or a.size < 8:
-            continue
-        cos = float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
-        worst.append((cos, k))
-    worst.sort()
-    print("lowest cosines:", worst[:5])
-    # bf16 storage makes the two reduction orders diverge by 1-ulp flips that re-route ReLU / max-pool gradient paths:
-    # the same bar as the comparison with the bf16-emulating oracle
-    assert worst[0][0] >= 0.9, worst[:5]
+        outs[name] = dict(np.load(path))
+    gb = outs["b"]
+    for other in ("a", "c"):
+        ga = outs[other]
+        assert abs(float(ga["__loss__"]) - float(gb["__loss__"])) <= 2e-3
+        worst = []
+        for k in ga:
+            if k == "__loss__":
+                continue
+            a, b = ga[k].ravel().astype(np.float64), gb[k].ravel().astype(np.float64)
+            # conv biases before a training-mode BN have analytically zero gradients, and the input-BN gamma/beta are
+            # small residuals of huge cancelling sums: all noise-dominated in bf16 storage (the fp64 and bf16-emulating
+            # oracles themselves differ by 9x on audio/bn0/gamma), so only the well-conditioned tensors are compared
+            if k.endswith(".bias") or ".bn0." in k or a.size < 8:
+                continue
+            cos = float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
+            worst.append((cos, k))
+        worst.sort()
+        print(other, "vs b, lowest cosines:", worst[:5])
+        # bf16 storage makes the reduction orders diverge by 1-ulp flips that re-route ReLU / max-pool gradient paths:
+        # the same bar as the comparison with the bf16-emulating oracle
+        assert worst[0][0] >= 0.9, (other, worst[:5])
