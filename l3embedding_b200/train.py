@@ -10,8 +10,9 @@ or lazy; Google-Sheets logging is out of scope (gsheet arguments are accepted an
 Differences that matter for speed, not results: batches are yielded as RAW uint8 video / int16 audio by default
 (`scale_on_host=False`) -- `2*(u8/255)-1` (train.py:186) and `pcm2float` (train.py:189) run on the device and the H2D
 copy is 4x smaller; pass scale_on_host=True for the reference's float arrays (bit-identical model inputs).
-Batch files: the reference's gzip HDF5 blobs (data/avc/sample.py:565-568) need h5py; `.npz` files with the same
-three keys (`audio` (n,1,48000) int16, `video` (n,224,224,3) uint8, `label` (n,2)) are read without it.
+Batch files: the reference's gzip HDF5 blobs (data/avc/sample.py:565-568) are read with h5py when it exists and with
+the built-in reader (l3embedding_b200/minihdf5.py: chunked + deflate/shuffle datasets) otherwise; `.npz` files with the
+same three keys (`audio` (n,1,48000) int16, `video` (n,224,224,3) uint8, `label` (n,2)) work too.
 """
 from __future__ import annotations
 
@@ -150,10 +151,31 @@ def cycle_shuffle(iterable, shuffle=True):
             random.shuffle(lst)
 
 
+class _H5Blob:
+    """The three datasets of one reference batch file read with the built-in HDF5 reader (minihdf5): each dataset is
+    decompressed once, on first use, and sliced from memory afterwards."""
+
+    def __init__(self, path):
+        from . import minihdf5
+        self._f = minihdf5.File(path)
+        self._cache = {}
+
+    def __getitem__(self, key):
+        if key not in self._cache:
+            self._cache[key] = np.asarray(self._f[key])
+        return self._cache[key]
+
+    def close(self):
+        self._cache.clear()
+
+
 def _open_blob(path):
     if path.endswith('.npz'):
         return np.load(path), lambda b: b.close()
-    import h5py  # the reference's format; optional dependency
+    try:
+        import h5py  # the reference's reader, when it exists
+    except ImportError:
+        return _H5Blob(path), lambda b: b.close()
     f = h5py.File(path, 'r')
     return f, lambda b: b.close()
 

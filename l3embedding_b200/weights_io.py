@@ -3,10 +3,10 @@
 The reference saves with keras `save_weights` (HDF5; l3embedding/train.py:316-355) and loads with `load_weights`
 (l3embedding/model.py:119).  h5py does not exist in the build environment, so the canonical interchange format
 here is an ordered .npz whose entries are the arrays of keras `Model.get_weights()` in that order, stored under
-the keras-style names below; when h5py is importable the same arrays are read from / written to the keras 2.0.9
-HDF5 layout (one group per top-level layer, `weight_names` attributes).  The HDF5 branch could not be exercised
-here (no h5py) and is marked unverified in DESIGN.md.  Files are recognised by magic bytes, not by extension, so
-`model_latest.h5` written by this package loads back regardless of which branch wrote it.
+the keras-style names below.  Paths ending in .h5 / .hdf5 are written in the keras 2.0.9 HDF5 layout (one group per
+top-level layer, `weight_names` attributes) -- through h5py when it is importable, otherwise through the package's own
+minimal HDF5 writer (minihdf5.py; its reader is checked against a libhdf5-written file, the writer by round trip).
+Files are recognised by magic bytes, not by extension.
 """
 from __future__ import annotations
 
@@ -91,14 +91,12 @@ def _is_hdf5(path) -> bool:
 
 
 def save_weights(path, model):
+    """keras `Model.save_weights`: a path ending in .h5 / .hdf5 gets the keras 2.0.9 HDF5 layout (through h5py when it is
+    installed, else through the built-in writer in minihdf5.py); anything else the ordered .npz."""
     names = model.weight_names()
     arrays = model.get_weights()
-    try:
-        import h5py  # noqa: F401
-        if str(path).endswith((".h5", ".hdf5")):
-            return _save_h5(path, model, names, arrays)
-    except ImportError:
-        pass
+    if str(path).endswith((".h5", ".hdf5")):
+        return _save_h5(path, model, names, arrays)
     payload = {"__order__": np.array(names), "__model_type__": np.array(model.model_type)}
     for n, a in zip(names, arrays):
         payload[n] = a
@@ -108,11 +106,6 @@ def save_weights(path, model):
 
 def load_weights(path, model):
     if _is_hdf5(path):
-        try:
-            import h5py  # noqa: F401
-        except ImportError as e:
-            raise ImportError("%s is a keras HDF5 checkpoint; reading it needs h5py (convert it to .npz with "
-                              "tools/h5_to_npz.py where h5py exists)" % path) from e
         return _load_h5(path, model)
     if not zipfile.is_zipfile(path):
         raise ValueError("%s is neither a keras HDF5 file nor an l3embedding_b200 .npz checkpoint" % path)
@@ -124,11 +117,11 @@ def load_weights(path, model):
 
 
 def _keras_groups(model):
-    """[(top-level layer name, [(keras weight name, canonical name)])] as keras 2.0.9 save_weights groups them."""
+    """[(top-level layer name, [(keras weight name, canonical name)])] as keras 2.0.9 save_weights groups them: EVERY
+    layer of `model.layers` gets a group (weight-less ones with an empty `weight_names`), datasets are named after the
+    backend variables ('<layer>/<weight>:0'; the slash makes h5py nest a sub-group)."""
     groups = []
     for layer in model.layers:
-        if not layer._weight_names:
-            continue
         entries = []
         for cn in layer._weight_names:
             parts = cn.split("/")
@@ -137,29 +130,61 @@ def _keras_groups(model):
     return groups
 
 
-def _save_h5(path, model, names, arrays):   # unverified: no h5py in the build environment
-    import h5py
+def _save_h5(path, model, names, arrays):
     by_name = dict(zip(names, arrays))
-    with h5py.File(path, "w") as f:
-        groups = _keras_groups(model)
-        f.attrs["layer_names"] = [g.encode("utf8") for g, _ in groups]
-        f.attrs["backend"] = b"tensorflow"
-        f.attrs["keras_version"] = b"2.0.9"
-        for gname, entries in groups:
-            g = f.create_group(gname)
-            g.attrs["weight_names"] = [kn.encode("utf8") for kn, _ in entries]
-            for kn, cn in entries:
-                g.create_dataset(kn, data=by_name[cn])
+    groups = _keras_groups(model)
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is not None:   # not exercised in the build environment (no h5py there)
+        with h5py.File(path, "w") as f:
+            f.attrs["layer_names"] = [g.encode("utf8") for g, _ in groups]
+            f.attrs["backend"] = b"tensorflow"
+            f.attrs["keras_version"] = b"2.0.9"
+            for gname, entries in groups:
+                g = f.create_group(gname)
+                g.attrs["weight_names"] = [kn.encode("utf8") for kn, _ in entries]
+                for kn, cn in entries:
+                    g.create_dataset(kn, data=by_name[cn])
+        return
+    from . import minihdf5
+    tree = {}
+    for gname, entries in groups:
+        wn = np.array([kn.encode("utf8") for kn, _ in entries]) if entries else np.zeros((0,), "S1")
+        node = {"__attrs__": {"weight_names": wn}}
+        for kn, cn in entries:
+            sub = node
+            parts = kn.split("/")
+            for part in parts[:-1]:
+                sub = sub.setdefault(part, {})
+            sub[parts[-1]] = np.asarray(by_name[cn])
+        tree[gname] = node
+    minihdf5.write_tree(path, tree, attrs={"layer_names": np.array([g.encode("utf8") for g, _ in groups]),
+                                           "backend": np.bytes_(b"tensorflow"), "keras_version": np.bytes_(b"2.0.9")})
 
 
-def _load_h5(path, model):   # unverified: no h5py in the build environment
-    import h5py
-    with h5py.File(path, "r") as f:
-        arrays = []
-        layer_names = [n.decode("utf8") if isinstance(n, bytes) else n for n in f.attrs["layer_names"]]
-        for ln in layer_names:
-            g = f[ln]
-            for wn in g.attrs["weight_names"]:
-                wn = wn.decode("utf8") if isinstance(wn, bytes) else wn
-                arrays.append(np.asarray(g[wn]))
-        model.set_weights(arrays)
+def _load_h5(path, model):
+    """keras `load_weights` (topological): arrays are taken group by group in `layer_names` order and, inside a group,
+    in `weight_names` order -- names themselves are not compared, so real keras checkpoints (variables called
+    conv2d_7/kernel:0 ...) and the files written here load alike."""
+    try:
+        import h5py
+        f = h5py.File(path, "r")
+    except ImportError:
+        from . import minihdf5
+        f = minihdf5.File(path)
+    dec = lambda n: n.decode("utf8") if isinstance(n, bytes) else str(n)
+    root = f["model_weights"] if ("layer_names" not in f.attrs and "model_weights" in f) else f   # Model.save() files
+    arrays = []
+    for ln in [dec(n) for n in root.attrs["layer_names"]]:
+        g = root[ln]
+        for wn in g.attrs["weight_names"]:
+            arrays.append(np.asarray(g[dec(wn)]))
+    expected = model.weight_names()
+    if len(arrays) != len(expected):
+        raise ValueError("checkpoint %s holds the weights of a different model layout (%d arrays, the %s model has %d)"
+                         % (path, len(arrays), model.model_type, len(expected)))
+    model.set_weights(arrays)
+    if hasattr(f, "close"):
+        f.close()
