@@ -169,8 +169,13 @@ struct Tower {
   unsigned long long* pool_scratch;  // (B,512) packed (value, ~index) keys of the global max-pool
   float* d1;    // 9*64 floats + 1 int flag: first-layer "ones" weight gradient for the input-BN backward
   int concat_off;
-  void *g0, *g1;         // backward ping-pong of this tower: padded dz / unpadded da
+  void *g0, *g1;         // backward buffers of this tower: padded dz / unpadded da
+  void* g0b;             // second dz buffer: layer l's dz lives in {g0, g0b}[l & 1] so that its weight gradient can run
+                         // on the side stream while the layers below already write the other buffer
   cudaStream_t stream;   // stream this tower's kernels are launched on (set by the caller of tower_*)
+  cudaStream_t wstream;  // low-priority side stream for the weight-gradient kernels (null: same stream)
+  cudaEvent_t ev_dz[2], ev_wg[2];   // dz(l) ready / wgrad(l) done, per dz buffer
+  int wg_pending[2];
 };
 
 }  // namespace l3
@@ -196,6 +201,12 @@ struct l3_ctx {
   cudaStream_t stream2;
   cudaEvent_t ev_fork, ev_join;
   int two_streams;
+  // Inside a tower the backward chain is dgrad -> BN/ReLU backward (HBM-bound) -> dgrad ...; the weight gradients hang
+  // off it as leaves.  With wgrad_streams they run on a low-priority side stream per tower and fill the tensor pipe
+  // while the chain is in its HBM-bound kernels (needs the double dz buffer and the internal tower streams).
+  cudaStream_t stream_v;        // vision tower's own (high-priority) stream when two_streams: the caller's stream has
+  cudaEvent_t ev_join_v;        // the default (lowest) priority and would not win against the side streams
+  int wgrad_streams;
   // host staging
   void *st_video, *st_audio;
   float* st_labels;
@@ -320,6 +331,7 @@ static long long carve(l3_ctx* c) {
     tw.pool_scratch = (unsigned long long*)bp.take(8 * B * 512);
     tw.d1 = (float*)bp.take(4 * (9 * 64 + 4));
     tw.g0 = training ? bp.take(es * g0_max) : nullptr;
+    tw.g0b = training ? bp.take(es * g0_max) : nullptr;
     tw.g1 = training ? bp.take(es * g1_max) : nullptr;
   }
   HeadRef& h = c->head;
@@ -473,41 +485,58 @@ static bool first_wgrad_tc_enabled() {
 template <typename T>
 static int tower_backward(l3_ctx* c, Tower& tw, int B) {
   cudaStream_t s = tw.stream;
-  T* dz = (T*)tw.g0;
+  // dz(l) lives in dzbuf[l & 1]; with `defer` the weight gradient of layer l runs on the tower's side stream, ordered by
+  // two events per buffer: ev_dz (dz(l) complete -> wgrad(l) may read it) and ev_wg (wgrad(l) done -> the BN/ReLU
+  // backward of layer l-2 may overwrite the buffer)
+  T* dzbuf[2] = {(T*)tw.g0, (T*)tw.g0b};
+  const bool defer = tw.wstream != nullptr && c->wgrad_streams && c->two_streams && s != c->stream;
+  cudaStream_t ws = defer ? tw.wstream : s;
+  tw.wg_pending[0] = tw.wg_pending[1] = 0;
   T* da = (T*)tw.g1;
   {
     ConvLayer& L = tw.L[7];
-    if (launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, dz, L.bn, B, L.H, L.W,
+    if (launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, dzbuf[1], L.bn, B, L.H, L.W,
                                L.Cout, s))
       return -1;
   }
   for (int l = 7; l >= 0; --l) {
     ConvLayer& L = tw.L[l];
+    T* dz = dzbuf[l & 1];
     long long rows = (long long)B * L.H * L.W;
     if (l == 7) {
       // dz holds the scattered dy of the global max-pool and bn.sum its sums: finish BN backward in place
       if (launch_bn_bwd_finalize(L.bn, rows, 0, s)) return -1;
       if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
     }
-    // weight / bias gradient
+    // weight / bias gradient (layer 0 stays on the main stream: the input-BN gradient is derived from its result)
     {
-      ProfScope ps(c, PROF_CONV_WGRAD, s);
+      const bool side = defer && l > 0;
+      cudaStream_t sw = side ? ws : s;
+      if (side) {
+        L3_CHECK_CUDA(cudaEventRecord(tw.ev_dz[l & 1], s));
+        L3_CHECK_CUDA(cudaStreamWaitEvent(ws, tw.ev_dz[l & 1], 0));
+      }
+      ProfScope ps(c, PROF_CONV_WGRAD, sw);
       if (L.tc && c->use_tc) {
         // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
         // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
         if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
-                               L.Cout, s))
+                               L.Cout, sw))
           return -1;
       } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64 && first_wgrad_tc_enabled()) {
         if (launch_first_wgrad_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
-                                  L.Cin, L.Cout, s))
+                                  L.Cin, L.Cout, sw))
           return -1;
       } else if (l == 0) {
         if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
-                                  L.Cin, L.Cout, s))
+                                  L.Cin, L.Cout, sw))
           return -1;
       } else {
-        if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, s)) return -1;
+        if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, sw)) return -1;
+      }
+      if (side) {
+        L3_CHECK_CUDA(cudaEventRecord(tw.ev_wg[l & 1], ws));
+        tw.wg_pending[l & 1] = 1;
       }
     }
     if (l == 0) {
@@ -521,12 +550,10 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       }
       break;
     }
-    // data gradient: da = conv(dz, flip/transpose(w)).  (Fusing pass 1 of the BN/ReLU backward of the layer below into
-    // this kernel's epilogue was tried and measured SLOWER -- +1.7 ms per step: the extra z loads and the second
-    // transposing reduction make the epilogue, not the MMA pipe, the critical path of every dgrad launch.)
+    // data gradient: da = conv(dz, flip/transpose(w))
     ConvLayer& Lp = tw.L[l - 1];
-    // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) rides in the dgrad
-    // epilogue, in the coalesced store-phase mapping, and da is not read again for it
+    // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) can ride in the dgrad
+    // epilogue (L3_DGRAD_FUSE_STATS=1; measured neutral, off by default)
     const bool fuse_stats = L.tc && c->use_tc && !Lp.pool && !Lp.relu_first && conv_tc_fuses_bwd_stats();
     {
       ProfScope ps(c, PROF_CONV_DGRAD, s);
@@ -541,13 +568,25 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
         if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
       }
     }
-    // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz (padded, full resolution)
+    // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
     long long rows_p = (long long)B * Lp.H * Lp.W;
     if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s))
       return -1;
     if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
-    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dz, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+    // dz(l-1) goes into the buffer the weight gradient of layer l+1 read
+    const int nb = (l - 1) & 1;
+    if (tw.wg_pending[nb]) {
+      L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[nb], 0));
+      tw.wg_pending[nb] = 0;
+    }
+    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dzbuf[nb], B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
   }
+  // the tower is complete only when its side stream is
+  for (int b2 = 0; b2 < 2; ++b2)
+    if (tw.wg_pending[b2]) {
+      L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[b2], 0));
+      tw.wg_pending[b2] = 0;
+    }
   return 0;
 }
 
@@ -569,19 +608,24 @@ static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad)
   return launch_pack_weights_batch(pb, c->stream);
 }
 
-// audio tower on stream2 between fork() and join(); everything else on the caller's stream
+// towers on their own streams between fork() and join(); everything else on the caller's stream
 static int fork_streams(l3_ctx* c) {
-  c->vision.stream = c->stream;
+  c->vision.stream = (c->two_streams && c->stream_v) ? c->stream_v : c->stream;
   c->audio.stream = c->two_streams ? c->stream2 : c->stream;
   if (!c->two_streams) return 0;
   L3_CHECK_CUDA(cudaEventRecord(c->ev_fork, c->stream));
   L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  if (c->stream_v) L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream_v, c->ev_fork, 0));
   return 0;
 }
 static int join_streams(l3_ctx* c) {
   if (!c->two_streams) return 0;
   L3_CHECK_CUDA(cudaEventRecord(c->ev_join, c->stream2));
   L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if (c->stream_v) {
+    L3_CHECK_CUDA(cudaEventRecord(c->ev_join_v, c->stream_v));
+    L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join_v, 0));
+  }
   return 0;
 }
 
@@ -694,6 +738,28 @@ int64_t l3_workspace_bytes(int model_type, int max_batch, int dtype, int flags) 
   return carve(&tmp);
 }
 
+// the towers' own streams (highest priority: the caller's stream has the default, lowest one) and the low-priority side
+// streams of the weight gradients, with the events that order them
+static int create_streams(l3_ctx* c) {
+  int least = 0, greatest = 0;
+  L3_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  L3_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest));
+  L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  if (c->wgrad_streams) {
+    L3_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream_v, cudaStreamNonBlocking, greatest));
+    L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join_v, cudaEventDisableTiming));
+    for (Tower* tw : {&c->vision, &c->audio}) {
+      L3_CHECK_CUDA(cudaStreamCreateWithPriority(&tw->wstream, cudaStreamNonBlocking, least));
+      for (int i = 0; i < 2; ++i) {
+        L3_CHECK_CUDA(cudaEventCreateWithFlags(&tw->ev_dz[i], cudaEventDisableTiming));
+        L3_CHECK_CUDA(cudaEventCreateWithFlags(&tw->ev_wg[i], cudaEventDisableTiming));
+      }
+    }
+  }
+  return 0;
+}
+
 l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float* params, float* grads, float* adam_m,
                       float* adam_v, float* bn_state, void* workspace, int64_t workspace_bytes, void* stream) {
   int64_t need = l3_workspace_bytes(model_type, max_batch, dtype, flags);
@@ -738,17 +804,16 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->prof_used = 0;
   c->vision.stream = c->audio.stream = c->stream;
   c->stream2 = nullptr;
+  c->stream_v = nullptr;
+  c->vision.wstream = c->audio.wstream = nullptr;
   {
     const char* e = getenv("L3_TWO_STREAMS");
     c->two_streams = e ? atoi(e) : 1;
-    if (c->two_streams) {
-      if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        set_error("could not create the second stream: %s", cudaGetErrorString(cudaGetLastError()));
-        delete c;
-        return nullptr;
-      }
+    const char* e2 = getenv("L3_WGRAD_STREAMS");
+    c->wgrad_streams = e2 ? atoi(e2) : 1;
+    if (c->two_streams && create_streams(c)) {
+      delete c;
+      return nullptr;
     }
   }
   carve(c);
@@ -780,6 +845,17 @@ void l3_ctx_destroy(l3_ctx* ctx) {
     cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->stream2);
   }
+  if (ctx->stream_v) {
+    cudaStreamSynchronize(ctx->stream_v);
+    cudaEventDestroy(ctx->ev_join_v);
+    cudaStreamDestroy(ctx->stream_v);
+  }
+  for (Tower* tw : {&ctx->vision, &ctx->audio})
+    if (tw->wstream) {
+      cudaStreamSynchronize(tw->wstream);
+      for (int i = 0; i < 2; ++i) { cudaEventDestroy(tw->ev_dz[i]); cudaEventDestroy(tw->ev_wg[i]); }
+      cudaStreamDestroy(tw->wstream);
+    }
   delete ctx;
 }
 
@@ -787,11 +863,7 @@ uint64_t l3_launch_count(void) { return g_launch_count; }
 
 int l3_ctx_set_two_streams(l3_ctx* c, int enable) {
   L3_REQUIRE(c != nullptr, "null ctx");
-  if (enable && !c->stream2) {
-    L3_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  }
+  if (enable && !c->stream2 && create_streams(c)) return -1;
   L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   c->two_streams = enable ? 1 : 0;
   return 0;
