@@ -152,6 +152,8 @@ struct ConvLayer {
   void* in;                 // padded input  (B,H+2,W+2,Cin)
   void* z;                  // raw conv output, unpadded (B,H,W,Cout)
   void* a;                  // padded activation output at post-pool resolution (null for the last layer)
+  void* zsel;               // pooled layers, training: winning pre-activation per pooled element (B,H/2,W/2,Cout)
+  uint8_t* sel;             //   and window position | 4*(max > 0), one byte per pooled element
   float* w_t;               // flipped/transposed fp32 kernel for dgrad-as-conv (SIMT path)
   bf16* w_pk;               // tcgen05 operand packs (forward, dgrad)
   bf16* wt_pk;
@@ -272,6 +274,17 @@ static void carve_bn(Bump& bp, BnRef& bn, int C) {
   bn.c2 = (float*)bp.take(4 * C);
 }
 
+// L3_POOL_RECORD=0: the pooled backward kernels re-derive the max-pool routing from z instead of reading the forward
+// pass's record (A/B checks)
+static bool pool_record_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L3_POOL_RECORD");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 // Walks every workspace allocation; with ctx->ws == nullptr it only measures.
 static long long carve(l3_ctx* c) {
   Bump bp{c->ws, 0};
@@ -317,6 +330,9 @@ static long long carve(l3_ctx* c) {
       carve_bn(bp, L.bn, L.Cout);
       int OH = L.pool ? H / 2 : H, OW = L.pool ? W / 2 : W;  // valid pooling floors; vision sizes are even
       L.a = l < 7 ? bp.take(es * B * (OH + 2) * (OW + 2) * L.Cout) : nullptr;
+      const bool rec = training && L.pool && pool_record_enabled();
+      L.zsel = rec ? bp.take(es * B * OH * OW * L.Cout) : nullptr;
+      L.sel = rec ? (uint8_t*)bp.take(B * OH * OW * L.Cout) : nullptr;
       L.w_t = training ? (float*)bp.take(4LL * 9 * L.Cin * L.Cout) : nullptr;
       L.tc = (c->dtype == L3_DTYPE_BF16 && L.Cin % 64 == 0 && L.Cout % 64 == 0) ? 1 : 0;
       L.w_pk = L.tc ? (bf16*)bp.take(2LL * 9 * L.Cin * L.Cout) : nullptr;
@@ -461,7 +477,8 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
     if (training && !stats_done && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
     if (launch_bn_finalize(L.bn, rows, training, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
     if (l < 7) {
-      if (launch_act_fwd<T>((const T*)L.z, (T*)L.a, B, L.H, L.W, L.Cout, L.bn.scale, L.bn.shift, L.pool, L.relu_first, s))
+      if (launch_act_fwd<T>((const T*)L.z, (T*)L.a, B, L.H, L.W, L.Cout, L.bn.scale, L.bn.shift, L.pool, L.relu_first, s,
+                            training ? (T*)L.zsel : nullptr, training ? L.sel : nullptr))
         return -1;
     } else {
       // MaxPooling2D over the whole final map + Flatten (audio_model.py:436-437, vision_model.py:189-190)
@@ -570,7 +587,8 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
     }
     // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
     long long rows_p = (long long)B * Lp.H * Lp.W;
-    if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s))
+    if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s,
+                                           (const T*)Lp.zsel, Lp.sel))
       return -1;
     if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
     // dz(l-1) goes into the buffer the weight gradient of layer l+1 read
@@ -579,7 +597,8 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[nb], 0));
       tw.wg_pending[nb] = 0;
     }
-    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dzbuf[nb], B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s)) return -1;
+    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dzbuf[nb], B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s, Lp.sel))
+      return -1;
   }
   // the tower is complete only when its side stream is
   for (int b2 = 0; b2 < 2; ++b2)

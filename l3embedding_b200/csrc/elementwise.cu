@@ -242,10 +242,15 @@ __device__ __forceinline__ void act8(const float (&z)[8], const float (&sc)[8], 
 // Several independent 16-byte loads are issued per thread before any is consumed (U pixels, or U 2x2 windows): next to
 // a resident tensor-core CTA of the other tower's stream only ONE of these blocks fits on an SM, and its bytes in
 // flight -- not the block count -- then set the achieved HBM bandwidth.
-template <typename T, bool POOL>
+// REC (training, pooled layers): also records, per pooled element, which window position won and whether the winner is
+// positive (`sel` = position | 4 * (max > 0), one byte) and the winning pre-activation (`zsel`).  The backward kernels
+// then neither recompute the four activations nor -- for the statistics pass -- read the full-resolution z: they were
+// instruction-issue-bound (~450 instructions per 2x2 window) and moved 2.5x the bytes.
+template <typename T, bool POOL, bool REC>
 __global__ void __launch_bounds__(256, 3)
 k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int OH, int OW, long long npix,
-          const float* __restrict__ scale, const float* __restrict__ shift, int relu_first) {
+          const float* __restrict__ scale, const float* __restrict__ shift, int relu_first, T* __restrict__ zsel,
+          uint8_t* __restrict__ sel) {
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   float sc[8], sh[8];
@@ -284,7 +289,31 @@ k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int O
       float y[8], x[8];
       unraw(v[u][0], x);
       act8(x, sc, sh, relu_first, y);
-      if (POOL) {
+      if (POOL && REC) {
+        // first maximum in window order (0,0),(0,1),(1,0),(1,1) -- the rule the backward pass used to re-derive
+        float zs[8];
+        int arg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { zs[i] = x[i]; arg[i] = 0; }
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          float t[8];
+          unraw(v[u][POOL ? k : 0], x);
+          act8(x, sc, sh, relu_first, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (t[i] > y[i]) { y[i] = t[i]; zs[i] = x[i]; arg[i] = k; }
+        }
+        uint32_t s01 = 0, s23 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s01 |= (uint32_t)(arg[i] | (y[i] > 0.f ? 4 : 0)) << (8 * i);
+          s23 |= (uint32_t)(arg[i + 4] | (y[i + 4] > 0.f ? 4 : 0)) << (8 * i);
+        }
+        const long long po = (p0 + u * lanes) * C + g * 8;   // un-padded pooled element offset
+        store8(zsel + po, zs);
+        *reinterpret_cast<uint2*>(sel + po) = make_uint2(s01, s23);
+      } else if (POOL) {
 #pragma unroll
         for (int k = 1; k < 4; ++k) {
           float t[8];
@@ -300,7 +329,7 @@ k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int O
 }
 template <typename T>
 int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
-                   int relu_first, cudaStream_t s) {
+                   int relu_first, cudaStream_t s, T* zsel, uint8_t* sel) {
   L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "act_fwd: C=%d", C);
   int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   long long npix = (long long)B * OH * OW;
@@ -308,13 +337,19 @@ int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* sc
   int lanes = kThreads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  if (pool) k_act_fwd<T, true><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first);
-  else k_act_fwd<T, false><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first);
+  if (pool && zsel && sel)
+    k_act_fwd<T, true, true><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first, zsel, sel);
+  else if (pool)
+    k_act_fwd<T, true, false><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first, nullptr, nullptr);
+  else
+    k_act_fwd<T, false, false><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first, nullptr, nullptr);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_act_fwd<float>(const float*, float*, int, int, int, int, const float*, const float*, int, int, cudaStream_t);
-template int launch_act_fwd<bf16>(const bf16*, bf16*, int, int, int, int, const float*, const float*, int, int, cudaStream_t);
+template int launch_act_fwd<float>(const float*, float*, int, int, int, int, const float*, const float*, int, int, cudaStream_t,
+                                   float*, uint8_t*);
+template int launch_act_fwd<bf16>(const bf16*, bf16*, int, int, int, int, const float*, const float*, int, int, cudaStream_t,
+                                  bf16*, uint8_t*);
 
 // --------------------------------------------------------------------------------------------
 // global max-pool forward over relu(bn(z)) -> (B,C) float + argmax pixel (first max in row-major order)
@@ -540,9 +575,87 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn.sum[i], (double)sh[i]);
 }
+// pooled layers with the forward pass's record: dy = da where the window maximum was positive (always, if relu_first),
+// xin = the winning pre-activation -- two 16-byte loads and 8 selection bytes per 8 channels of a pooled pixel
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_bwd_stats_sel(const T* __restrict__ da, const T* __restrict__ zsel, const uint8_t* __restrict__ sel, int C, long long npix,
+                BnRef bn, int relu_first) {
+  extern __shared__ float sh[];  // 2*C
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  constexpr bool kCentre = sizeof(T) == 4;   // see k_bwd_stats
+  float mu[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mu[i] = s1[i] = s2[i] = 0.f;
+  if (kCentre) load8(bn.mean + g * 8, mu);
+  constexpr int U = sizeof(T) == 4 ? 2 : 4;
+  const long long stride = (long long)gridDim.x * lanes;
+  for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {
+    Raw8<T> rg[U], rz[U];
+    uint2 rs[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * lanes;
+      ok[u] = p < npix;
+      if (ok[u]) {
+        ldraw(da + p * C + g * 8, rg[u]);
+        ldraw(zsel + p * C + g * 8, rz[u]);
+        rs[u] = *reinterpret_cast<const uint2*>(sel + p * C + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float g8[8], zs[8];
+      unraw(rg[u], g8);
+      unraw(rz[u], zs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t sb = ((i < 4 ? rs[u].x : rs[u].y) >> (8 * (i & 3))) & 0xffu;
+        const float d = (relu_first || (sb & 4u)) ? g8[i] : 0.f;
+        float xin = relu_first ? fmaxf(zs[i], 0.f) : zs[i];
+        if (kCentre) xin -= mu[i];
+        s1[i] += d;
+        s2[i] = fmaf(d, xin, s2[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    for (int off = 16; off >= groups; off >>= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+    }
+  }
+  if ((threadIdx.x & 31) < groups || groups >= 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[g * 8 + i], s1[i]);
+      atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn.sum[i], (double)sh[i]);
+}
+
 template <typename T>
 int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const BnRef& bn, int pool, int relu_first,
-                     cudaStream_t s) {
+                     cudaStream_t s, const T* zsel, const uint8_t* sel) {
+  if (pool && zsel && sel) {
+    L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "bwd_stats: C=%d", C);
+    L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
+    const long long npix = (long long)B * (H / 2) * (W / 2);
+    const int lanes = kThreads / (C / 8);
+    long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
+    int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+    k_bwd_stats_sel<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, zsel, sel, C, npix, bn, relu_first);
+    L3_CHECK_LAUNCH();
+    return 0;
+  }
   // The 2x2-pool variants need ~128 registers: in 128-thread blocks (16 K registers) they still fit next to a resident
   // tensor-core CTA (38 K registers) of the other tower's stream; a 256-thread block would not.
   const int threads = pool ? 128 : kThreads;
@@ -558,8 +671,10 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_bwd_stats<float>(const float*, const float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
-template int launch_bwd_stats<bf16>(const bf16*, const bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_bwd_stats<float>(const float*, const float*, int, int, int, int, const BnRef&, int, int, cudaStream_t,
+                                     const float*, const uint8_t*);
+template int launch_bwd_stats<bf16>(const bf16*, const bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t,
+                                    const bf16*, const uint8_t*);
 
 // folded BN-backward coefficients (written by k_bn_bwd_finalize into bn.c1 / bn.c2):
 //   dz = scale*(dy - mean(dy) - xhat*mean(dy*xhat)) = scale*dy + c1*xin + c2,   xin = z (or relu(z) if relu_first)
@@ -583,7 +698,7 @@ __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
-            long long npix, BnRef bn, int relu_first) {
+            long long npix, BnRef bn, int relu_first, const uint8_t* __restrict__ sel) {
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
   float sf[8];
@@ -618,15 +733,26 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
       load8(z00 + C, v[1]);
       load8(z00 + (long long)W * C, v[2]);
       load8(z00 + (long long)W * C + C, v[3]);
-      float y[8];
-      act8(v[0], k.sc, sf, relu_first, m);
+      if (sel != nullptr) {
+        // the forward pass recorded the winning window position and the sign of the maximum (k_act_fwd<.., REC>)
+        const uint2 sb = *reinterpret_cast<const uint2*>(sel + p * C + g * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) arg[i] = 0;
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t b8 = ((i < 4 ? sb.x : sb.y) >> (8 * (i & 3))) & 0xffu;
+          arg[i] = (int)(b8 & 3u);
+          m[i] = (b8 & 4u) ? 1.f : 0.f;
+        }
+      } else {
+        float y[8];
+        act8(v[0], k.sc, sf, relu_first, m);
 #pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        act8(v[q], k.sc, sf, relu_first, y);
+        for (int i = 0; i < 8; ++i) arg[i] = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+        for (int q = 1; q < 4; ++q) {
+          act8(v[q], k.sc, sf, relu_first, y);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (y[i] > m[i]) { m[i] = y[i]; arg[i] = q; }
+        }
       }
     }
 #pragma unroll
@@ -663,7 +789,7 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
 // dz: zero-haloed padded (B,H+2,W+2,C); the halo is (re)zeroed here because the buffer is shared between layers
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
-                     int relu_first, cudaStream_t s) {
+                     int relu_first, cudaStream_t s, const uint8_t* sel) {
   const int threads = pool ? 128 : kThreads;   // see launch_bwd_stats
   L3_REQUIRE(C % 8 == 0 && threads % (C / 8) == 0, "bwd_apply: C=%d", C);
   if (launch_zero_halo<T>(dz, B, H, W, C, s)) return -1;
@@ -672,13 +798,15 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
-  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first);
+  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, sel);
+  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_bwd_apply<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
-template int launch_bwd_apply<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t);
+template int launch_bwd_apply<float>(const float*, const float*, float*, int, int, int, int, const BnRef&, int, int, cudaStream_t,
+                                     const uint8_t*);
+template int launch_bwd_apply<bf16>(const bf16*, const bf16*, bf16*, int, int, int, int, const BnRef&, int, int, cudaStream_t,
+                                    const uint8_t*);
 
 // BN backward finalize: dgamma, dbeta and the folded coefficients of dz = scale*dy + c1*xin + c2
 //   c1 = -scale*invstd*mean(dy*xhat) ; c2 = -scale*mean(dy) - c1*mean

@@ -43,9 +43,11 @@ int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, cons
                         cudaStream_t s);   // out: zero-haloed padded (B,H+2,W+2,C)
 template <typename T>
 int launch_zero_halo(T* buf, int B, int H, int W, int C, cudaStream_t s);
+// zsel / sel (optional, pooled layers in training): the winning pre-activation (B,H/2,W/2,C) and one byte per pooled
+// element (window position | 4 * (max > 0)) for the backward kernels
 template <typename T>
 int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
-                   int relu_first, cudaStream_t s);
+                   int relu_first, cudaStream_t s, T* zsel = nullptr, uint8_t* sel = nullptr);
 template <typename T>
 int launch_gmaxpool_fwd(const T* z, int B, int HW, int C, const float* scale, const float* shift, float* out,
                         int out_stride, int* argmax, unsigned long long* scratch /* B*C */, cudaStream_t s);
@@ -55,10 +57,10 @@ int launch_gmaxpool_bwd(const float* dpool, int dpool_stride, const int* argmax,
 // activation + BN backward in two passes over (da, z): pass 1 -> bn.sum = {sum dy, sum dy*xhat}; pass 2 -> dz (padded)
 template <typename T>
 int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const BnRef& bn, int pool, int relu_first,
-                     cudaStream_t s);
+                     cudaStream_t s, const T* zsel = nullptr, const uint8_t* sel = nullptr);
 template <typename T>
 int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C, const BnRef& bn, int pool,
-                     int relu_first, cudaStream_t s);
+                     int relu_first, cudaStream_t s, const uint8_t* sel = nullptr);
 // raw_sums: bn.sum[C..2C) holds 0: sum(dy*xhat); 1: sum(dy*xin) (launch_bwd_stats<bf16>); 2: sum(dy*(xin-mean)) (<float>)
 int launch_bn_bwd_finalize(const BnRef& bn, long long count, int raw_sums, cudaStream_t s);
 template <typename T>
