@@ -256,7 +256,9 @@ k_act_fwd(const T* __restrict__ z, T* __restrict__ a, int H, int W, int C, int O
   float sc[8], sh[8];
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sh);
-  constexpr int U = (POOL ? 2 : 4) / (sizeof(T) == 4 ? 2 : 1);   // fp32 (parity mode): half as many, the raw loads are twice as wide
+  // fp32 (parity mode): half as many, the raw loads are twice as wide; the recording variant keeps one window in flight
+  // (its argmax / winner registers would spill otherwise)
+  constexpr int U = REC ? 1 : (POOL ? 2 : 4) / (sizeof(T) == 4 ? 2 : 1);
   const long long stride = (long long)gridDim.x * lanes;
   for (long long p0 = (long long)blockIdx.x * (lanes * U) + lane; p0 < npix; p0 += stride * U) {   // block = U*lanes consecutive pixels
     Raw8<T> v[U][POOL ? 4 : 1];
