@@ -207,7 +207,9 @@ def test_kernel_variants_agree_on_a_training_step(tmp_path):
     and the SIMT first-layer wgrad (L3_CONV_TC_VARIANT=2, L3_WGRAD_TC_VARIANT=1, L3_FIRST_WGRAD_TC=0), (b) the
     defaults (CTA-pair kernels, per-configuration statistics epilogues, shared-halo wgrad, tensor-core first layer) and
     (c) the store-phase statistics everywhere plus BN-backward pass 1 fused into the dgrad epilogues
-    (L3_CONV_EPI=store, L3_DGRAD_FUSE_STATS=1): identical math, different reduction orders."""
+    (L3_CONV_EPI=store, L3_DGRAD_FUSE_STATS=1), (d) max-pool routing re-derived in the backward kernels instead of read
+    from the forward pass's record, weight gradients on the towers' own streams (L3_POOL_RECORD=0, L3_WGRAD_STREAMS=0):
+    identical math, different reduction orders."""
     import os
     import subprocess
     import sys
@@ -215,14 +217,15 @@ def test_kernel_variants_agree_on_a_training_step(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     for name, env in (("a", {"L3_CONV_TC_VARIANT": "2", "L3_FIRST_WGRAD_TC": "0", "L3_WGRAD_TC_VARIANT": "1"}), ("b", {}),
-                      ("c", {"L3_CONV_EPI": "store", "L3_DGRAD_FUSE_STATS": "1"})):
+                      ("c", {"L3_CONV_EPI": "store", "L3_DGRAD_FUSE_STATS": "1"}),
+                      ("d", {"L3_POOL_RECORD": "0", "L3_WGRAD_STREAMS": "0"})):
         path = str(tmp_path / (name + ".npz"))
         e = dict(os.environ)
         e.update(env)
         subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root, path], check=True, env=e, timeout=300)
         outs[name] = dict(np.load(path))
     gb = outs["b"]
-    for other in ("a", "c"):
+    for other in ("a", "c", "d"):
         ga = outs[other]
         assert abs(float(ga["__loss__"]) - float(gb["__loss__"])) <= 2e-3
         worst = []
