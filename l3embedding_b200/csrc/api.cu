@@ -201,7 +201,7 @@ struct l3_ctx {
   // the two towers are independent until the head: the audio tower runs on a second stream so its HBM-bound
   // kernels overlap the vision tower's tensor-core kernels (and vice versa)
   cudaStream_t stream2;
-  cudaEvent_t ev_fork, ev_join;
+  cudaEvent_t ev_fork, ev_join, ev_pack;
   int two_streams;
   // Inside a tower the backward chain is dgrad -> BN/ReLU backward (HBM-bound) -> dgrad ...; the weight gradients hang
   // off it as leaves.  With wgrad_streams they run on a low-priority side stream per tower and fill the tensor pipe
@@ -610,7 +610,7 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
 }
 
 // bf16 tensor-core operand packs of every layer (forward, and dgrad when training), one launch
-static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad) {
+static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad, cudaStream_t stream = nullptr) {
   if (!c->use_tc) return 0;
   PackBatch pb;
   pb.n = 0;
@@ -624,7 +624,7 @@ static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad)
       if (with_dgrad && L.wt_pk) pb.job[pb.n++] = PackJob{L.w, L.wt_pk, L.Cin, L.Cout, 1};
     }
   }
-  return launch_pack_weights_batch(pb, c->stream);
+  return launch_pack_weights_batch(pb, stream ? stream : c->stream);
 }
 
 // towers on their own streams between fork() and join(); everything else on the caller's stream
@@ -651,11 +651,15 @@ static int join_streams(l3_ctx* c) {
 template <typename T>
 static int forward_all(l3_ctx* c, const void* video, int vfmt, const void* audio, int afmt, const float* labels, int B,
                        bool training, float grad_scale) {
-  if (pack_all_weights(c, true, true, training)) return -1;
   if (fork_streams(c)) return -1;
+  // the bf16 operand packs are first needed by the second conv layer: they are built on the vision tower's stream while
+  // the audio stream already runs the front-end (the first-layer kernels read the fp32 weights themselves)
+  if (pack_all_weights(c, true, true, training, c->vision.stream)) return -1;
+  if (c->audio.stream != c->vision.stream) L3_CHECK_CUDA(cudaEventRecord(c->ev_pack, c->vision.stream));
   // interleave the two towers' launches so neither stream starves while the host is still enqueuing the other
   if (tower_input<T>(c, c->vision, false, video, vfmt, B, training)) return -1;
   if (tower_input<T>(c, c->audio, true, audio, afmt, B, training)) return -1;
+  if (c->audio.stream != c->vision.stream) L3_CHECK_CUDA(cudaStreamWaitEvent(c->audio.stream, c->ev_pack, 0));
   if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
   if (tower_forward<T>(c, c->audio, B, training, false)) return -1;
   if (join_streams(c)) return -1;
@@ -765,6 +769,7 @@ static int create_streams(l3_ctx* c) {
   L3_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest));
   L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
   if (c->wgrad_streams) {
     L3_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream_v, cudaStreamNonBlocking, greatest));
     L3_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join_v, cudaEventDisableTiming));
@@ -862,6 +867,7 @@ void l3_ctx_destroy(l3_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream2);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_pack);
     cudaStreamDestroy(ctx->stream2);
   }
   if (ctx->stream_v) {
