@@ -95,9 +95,11 @@ int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem,
     plan->mel_count = (const int*)put(ct.data(), ct.size() * sizeof(int));
     plan->mel_offset = (const int*)put(of.data(), of.size() * sizeof(int));
     plan->mel_weight = (const float*)put(wt.data(), wt.size() * sizeof(float));
+    plan->mel_nnz = (int)wt.size();
   } else {
     plan->mel_start = plan->mel_count = plan->mel_offset = nullptr;
     plan->mel_weight = nullptr;
+    plan->mel_nnz = 0;
   }
   L3_CHECK_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
   return 0;
@@ -158,7 +160,8 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   float* win = reinterpret_cast<float*>(tw + N / 2);                        // N
   float* pw = win + N;                                                      // kFramesPerCta power spectra of PWS floats
   float* tile = pw + kFramesPerCta * PWS;                                   // n_out * kFramesPerCta
-  unsigned char* stage = reinterpret_cast<unsigned char*>(tile + p.n_out * kFramesPerCta);
+  float* melw = tile + p.n_out * kFramesPerCta;                             // mel_nnz packed filter weights
+  unsigned char* stage = reinterpret_cast<unsigned char*>(melw + p.mel_nnz);
   stage = reinterpret_cast<unsigned char*>(((uintptr_t)stage + 15) & ~(uintptr_t)15);
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float red[kFeThreads / 32];
@@ -192,6 +195,8 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   // overlap: constant tables -> shared
   for (int i = threadIdx.x; i < N / 2; i += blockDim.x) tw[i] = p.twiddle[i];
   for (int i = threadIdx.x; i < N; i += blockDim.x) win[i] = p.window[i];
+  // the projection walks up to ~50 weights per (frame, band) item: from shared memory, not through L1/L2
+  for (int i = threadIdx.x; i < p.mel_nnz; i += blockDim.x) melw[i] = p.mel_weight[i];
   // wait for the clip window
   {
     uint32_t done = 0;
@@ -245,7 +250,7 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
     float va, vb;
     if (p.mel) {
       const int k0 = p.mel_start[m], n = p.mel_count[m];
-      const float* w = p.mel_weight + p.mel_offset[m];
+      const float* w = melw + p.mel_offset[m];
       float sa = 0.f, sb = 0.f;
       for (int k = 0; k < n; ++k) {
         const float wk = w[k];
@@ -309,7 +314,7 @@ static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out
   constexpr int ES = I16 ? 2 : 4;
   size_t stage_elems = (size_t)(kFramesPerCta - 1) * p.n_hop + N + 16;
   size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + (size_t)N * 4 + kFramesPerCta * (size_t)(NF + 3) * 4 +
-                (size_t)p.n_out * kFramesPerCta * 4 + 16 + stage_elems * ES;
+                (size_t)p.n_out * kFramesPerCta * 4 + (size_t)p.mel_nnz * 4 + 16 + stage_elems * ES;
   static bool configured = false;
   if (!configured) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -22,6 +22,7 @@ struct FrontendPlan {
   const int* mel_count;     // [n_mels]
   const int* mel_offset;    // [n_mels] into mel_weight
   const float* mel_weight;  // packed non-zeros
+  int mel_nnz;              // number of packed non-zeros (staged into shared memory by the kernel)
 };
 // bytes of device memory needed for the tables
 size_t frontend_table_bytes(int n_dft, int n_mels);
