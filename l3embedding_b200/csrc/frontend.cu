@@ -115,30 +115,47 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <int N, int G>
 __device__ __forceinline__ void fft_dif_batched(float2* z, const float2* __restrict__ tw) {
   static_assert(N == 512 || N == 2048, "log2(N) must be odd");
+  constexpr int TOTAL = G * (N / 4), IT = (TOTAL + kFeThreads - 1) / kFeThreads;   // quad-butterflies per thread and pass
 #pragma unroll 1
   for (int h = N / 2; h >= 2; h >>= 2) {          // fused stages with halves h and h/2
     const int ts1 = (N / 2) / h, hq = h >> 1;
-    for (int i = threadIdx.x; i < G * (N / 4); i += blockDim.x) {
-      float2* zg = z + (i / (N / 4)) * N;
+    // two phases -- all loads, then all math and stores (the quad-butterflies of a pass touch disjoint elements, which
+    // the compiler cannot know): with 16 warps per SM the passes were waiting on one LDS round trip per butterfly
+    float2 x[IT][4];
+    float2* zp[IT];
+    int jj[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int i = threadIdx.x + it * kFeThreads;
       const int q = i & (N / 4 - 1);
       const int j = q & (hq - 1);
-      const int base = ((q - j) << 2) + j;
-      const float2 x0 = zg[base], x1 = zg[base + hq], x2 = zg[base + h], x3 = zg[base + h + hq];
+      jj[it] = j;
+      zp[it] = z + (i / (N / 4)) * N + ((q - j) << 2) + j;
+      if (i < TOTAL) {
+        x[it][0] = zp[it][0]; x[it][1] = zp[it][hq]; x[it][2] = zp[it][h]; x[it][3] = zp[it][h + hq];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      if (threadIdx.x + it * kFeThreads >= TOTAL) continue;
+      const int j = jj[it];
+      const float2 x0 = x[it][0], x1 = x[it][1], x2 = x[it][2], x3 = x[it][3];
       const float2 wa = tw[j * ts1], wb = tw[(j + hq) * ts1], wc = tw[j * 2 * ts1];
       const float2 y0 = make_float2(x0.x + x2.x, x0.y + x2.y), d0 = make_float2(x0.x - x2.x, x0.y - x2.y);
       const float2 y1 = make_float2(x1.x + x3.x, x1.y + x3.y), d1 = make_float2(x1.x - x3.x, x1.y - x3.y);
       const float2 y2 = make_float2(d0.x * wa.x - d0.y * wa.y, d0.x * wa.y + d0.y * wa.x);
       const float2 y3 = make_float2(d1.x * wb.x - d1.y * wb.y, d1.x * wb.y + d1.y * wb.x);
       const float2 e0 = make_float2(y0.x - y1.x, y0.y - y1.y), e1 = make_float2(y2.x - y3.x, y2.y - y3.y);
-      zg[base] = make_float2(y0.x + y1.x, y0.y + y1.y);
-      zg[base + hq] = make_float2(e0.x * wc.x - e0.y * wc.y, e0.x * wc.y + e0.y * wc.x);
-      zg[base + h] = make_float2(y2.x + y3.x, y2.y + y3.y);
-      zg[base + h + hq] = make_float2(e1.x * wc.x - e1.y * wc.y, e1.x * wc.y + e1.y * wc.x);
+      zp[it][0] = make_float2(y0.x + y1.x, y0.y + y1.y);
+      zp[it][hq] = make_float2(e0.x * wc.x - e0.y * wc.y, e0.x * wc.y + e0.y * wc.x);
+      zp[it][h] = make_float2(y2.x + y3.x, y2.y + y3.y);
+      zp[it][h + hq] = make_float2(e1.x * wc.x - e1.y * wc.y, e1.x * wc.y + e1.y * wc.x);
     }
     __syncthreads();
   }
   // last stage (half = 1): twiddle 1
-  for (int i = threadIdx.x; i < G * (N / 2); i += blockDim.x) {
+#pragma unroll
+  for (int i = threadIdx.x; i < G * (N / 2); i += kFeThreads) {
     const float2 a = z[2 * i], b = z[2 * i + 1];
     z[2 * i] = make_float2(a.x + b.x, a.y + b.y);
     z[2 * i + 1] = make_float2(a.x - b.x, a.y - b.y);
