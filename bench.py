@@ -182,9 +182,9 @@ def main_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its debug output (the version banner at NCCL_DEBUG >= VERSION) to STDOUT by default: send it to
+        # stderr so that stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     par = dp.TorchDistReplicas() if world > 1 else dp.SingleReplica()
     B = args.batch
