@@ -182,10 +182,19 @@ def main_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its debug output (the version banner at NCCL_DEBUG >= VERSION) to STDOUT by default: send it to
-        # stderr so that stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner / debug output to STDOUT (fd 1) while the communicator comes up: point fd 1
+        # at stderr for that phase so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     par = dp.TorchDistReplicas() if world > 1 else dp.SingleReplica()
     B = args.batch
     G = B * world
