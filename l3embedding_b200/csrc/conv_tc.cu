@@ -1,6 +1,15 @@
-// tcgen05 (5th-gen tensor core) bf16 implicit-GEMM 3x3 convolutions for sm_100a: forward / data-gradient
-// (k_conv3x3_tc) and weight-gradient (k_wgrad3x3_tc).  Replaces what cuDNN ran for the keras Conv2D layers of
-// l3embedding/audio_model.py:376-432 and l3embedding/vision_model.py:130-186 (forward and backward).
+// tcgen05 (5th-gen tensor core) bf16 implicit-GEMM 3x3 convolutions for sm_100a.  Replaces what cuDNN ran for the keras
+// Conv2D layers of l3embedding/audio_model.py:376-432 and l3embedding/vision_model.py:130-186 (forward and backward).
+//
+// Kernels in this file (the training step uses the ones marked *):
+//   k_conv3x3_tc      forward / dgrad, version 1: one 128 x BN tile per tap and 64-channel chunk          (A/B reference)
+//   k_conv3x3_tc2     version 2: shared-halo A regions, MT m-tiles per CTA, fused BN statistics            (A/B reference)
+// * k_conv3x3_tc3     version 3: version 2 on CTA pairs (cta_group::2), coalescing epilogue, epilogue flavours EPI_*
+//   k_wgrad3x3_tc     weight gradient, version 1 (per-tap boxes)                                           (A/B reference)
+// * k_wgrad3x3_tc2    weight gradient, version 2 (shared-halo regions, tap pairing for Cin = 64)
+// * k_first_conv_tc   Cin = 1 / 3 forward: im2col operand built in shared memory from bulk-copy-staged input runs
+// * k_first_wgrad_tc  Cin = 1 / 3 weight gradient (+ the input-BN / bias gradient columns), same staging
+// * k_pack_weights_batch  fp32 HWIO -> bf16 K-major operand rows, all layers in one launch
 //
 // Layout trick: every convolution input lives in a zero-haloed buffer (B,H+2,W+2,C).  Flattening (b,y,x) to one
 // row index m makes tap (ky,kx) of a 'same' 3x3 convolution a CONSTANT row shift (ky-1)*(W+2)+(kx-1), so the
@@ -11,10 +20,10 @@
 // Forward GEMM  D[m][co] = sum_{tap,ci} A[m+shift(tap)][ci] * Wp[tap][ci][co]      M = pixels, N = Cout, K = 9*Cin
 //   A, B both K-major in shared memory (128-byte swizzle, written by TMA), fp32 accumulators in TMEM (double
 //   buffered so the epilogue of tile i overlaps the MMAs of tile i+1), persistent CTAs, warp-specialised:
-//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator), warps 2..5 = epilogue (TMEM -> regs -> bf16 -> HBM).
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator), 4 (v1) / 8 (v2, v3) epilogue warps.
 // Weight gradient  dW[tap][ci][co] = sum_m A[m+shift(tap)][ci] * dZ[m][co]          M = Cin, N = Cout, K = pixels
 //   both operands are "MN-major" (channels contiguous), which UMMA reads directly from the same TMA boxes;
-//   split-K over pixel slices with fp32 atomics into dW.
+//   split-K over pixel slices with fp32 vector reductions into dW.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
