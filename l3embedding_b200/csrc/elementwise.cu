@@ -697,7 +697,7 @@ __device__ __forceinline__ void bwd_emit(T* __restrict__ dst, const float (&v)[8
   store8(dst, o);
 }
 
-template <typename T, bool POOL>
+template <typename T, bool POOL, bool SEL>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int H, int W, int C, int OH, int OW,
             long long npix, BnRef bn, int relu_first, const uint8_t* __restrict__ sel) {
@@ -706,7 +706,7 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
   float sf[8];
   BnBwdCoef k;
   load8(bn.scale + g * 8, k.sc);
-  load8(bn.shift + g * 8, sf);
+  if (!SEL) load8(bn.shift + g * 8, sf);   // only the re-derivation of the ReLU mask / pool routing needs the shift
   load8(bn.c1 + g * 8, k.cb);
   load8(bn.c2 + g * 8, k.cc);
   const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -735,7 +735,7 @@ k_bwd_apply(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ d
       load8(z00 + C, v[1]);
       load8(z00 + (long long)W * C, v[2]);
       load8(z00 + (long long)W * C + C, v[3]);
-      if (sel != nullptr) {
+      if (SEL) {
         // the forward pass recorded the winning window position and the sign of the maximum (k_act_fwd<.., REC>)
         const uint2 sb = *reinterpret_cast<const uint2*>(sel + p * C + g * 8);
 #pragma unroll
@@ -800,8 +800,9 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_apply<T, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, sel);
-  else k_bwd_apply<T, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);
+  if (pool && sel) k_bwd_apply<T, true, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, sel);
+  else if (pool) k_bwd_apply<T, true, false><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);
+  else k_bwd_apply<T, false, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);
   L3_CHECK_LAUNCH();
   return 0;
 }
