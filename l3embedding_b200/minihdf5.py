@@ -551,7 +551,7 @@ class Writer:
         return self._object_header(msgs)
 
     def dataset_chunked(self, array, chunks, gzip_level: int = 4, shuffle: bool = False, attrs: Optional[dict] = None) -> int:
-        """Chunked + deflate (+ shuffle) dataset with a single-leaf v1 chunk B-tree (at most 64 chunks): the storage
+        """Chunked + deflate (+ shuffle) dataset with a one- or two-level v1 chunk B-tree (at most 4096 chunks): the storage
         h5py's `create_dataset(..., compression='gzip')` uses for the reference's AVC batch files
         (data/avc/sample.py:373-377)."""
         a = np.ascontiguousarray(array)
@@ -573,16 +573,30 @@ class Writer:
                 raw = np.frombuffer(raw, np.uint8).reshape(-1, esz).T.tobytes()
             raw = zlib.compress(raw, gzip_level)
             entries.append((o, len(raw), self._alloc(raw)))
-        if len(entries) > 64:
-            raise HDF5Error("more than 64 chunks: multi-level chunk B-trees are not written")
-        node = bytearray(b"TREE" + bytes([1, 0]) + struct.pack("<H", len(entries)) + struct.pack("<QQ", UNDEF, UNDEF))
-        for o, n, addr in entries:
-            node += struct.pack("<II", n, 0) + b"".join(struct.pack("<Q", x) for x in o) + struct.pack("<Q", 0)
-            node += struct.pack("<Q", addr)
-        node += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in a.shape) + struct.pack("<Q", 0)
+        if len(entries) > 64 * 64:
+            raise HDF5Error("more than 4096 chunks: chunk B-trees deeper than two levels are not written")
         ksz = 8 + 8 * (a.ndim + 1)
-        node += b"\0" * (24 + 64 * (ksz + 8) + ksz - len(node))
-        btree = self._alloc(bytes(node))
+
+        def key(n, o):
+            return struct.pack("<II", n, 0) + b"".join(struct.pack("<Q", x) for x in o) + struct.pack("<Q", 0)
+
+        def write_node(level, items):
+            """items: (first chunk offsets, byte size of that chunk or 0, child address); at most 64 per node"""
+            node = bytearray(b"TREE" + bytes([1, level]) + struct.pack("<H", len(items)) + struct.pack("<QQ", UNDEF, UNDEF))
+            for o, n, addr in items:
+                node += key(n, o) + struct.pack("<Q", addr)
+            node += key(0, a.shape)   # final key: one past the last chunk
+            node += b"\0" * (24 + 64 * (ksz + 8) + ksz - len(node))
+            return self._alloc(bytes(node))
+
+        if len(entries) <= 64:
+            btree = write_node(0, entries)
+        else:   # two levels: leaves of up to 64 chunks under one root
+            leaves = []
+            for i in range(0, len(entries), 64):
+                grp = entries[i:i + 64]
+                leaves.append((grp[0][0], grp[0][1], write_node(0, grp)))
+            btree = write_node(1, leaves)
         filt = b""
         nf = 0
         if shuffle:

@@ -75,6 +75,16 @@ def test_chunked_gzip_batch_file(tmp_path, shuffle):
     assert np.array_equal(f["label"][1:3], label[1:3])
 
 
+def test_two_level_chunk_btree(tmp_path):
+    """More than 64 chunks: the chunk index becomes a two-level B-tree (what h5py's auto-chunking produces for the
+    reference's 1024-sample batch files); the reader walks internal nodes."""
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 255, (40, 30, 7), dtype=np.uint8)
+    p = str(tmp_path / "deep.h5")
+    H.write_tree(p, {"x": H.Chunked(x, (3, 4, 7))})   # 14 * 8 = 112 chunks
+    assert np.array_equal(np.asarray(H.File(p)["x"]), x)
+
+
 def test_data_generator_reads_hdf5_batches(tmp_path):
     from l3embedding_b200 import train as T
     rng = np.random.default_rng(2)

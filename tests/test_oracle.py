@@ -163,3 +163,21 @@ def test_golden_vectors():
                 w = O.to_torch(O.init_weights(mt, seed=meta["weight_seed"], randomize_bn=True), dtype=torch.float64)
                 emb = O.audio_embedding(af, w, mt, "short", cfg).numpy()
                 assert np.abs(emb - z[mt + "/embedding_short"]).max() < 1e-8
+
+
+def test_emulate_bf16_first_layer_weight_switch():
+    """OracleConfig.first_layer_bf16_weights: the bf16-emulating oracle rounds the Cin = 1 / 3 kernels like the tensor-core
+    first layer does (default) or keeps them fp32 like the SIMT first layer (L3_FIRST_CONV_TC=0)."""
+    torch.manual_seed(0)
+    x = torch.randn(1, 3, 9, 11)
+    w = {"t/kernel": torch.randn(3, 3, 3, 64) * 0.2 + 1e-3, "t/bias": torch.zeros(64)}
+    on = O._conv(x, w, "t", O.OracleConfig(emulate_bf16=True))
+    off = O._conv(x, w, "t", O.OracleConfig(emulate_bf16=True, first_layer_bf16_weights=False))
+    wq = {"t/kernel": w["t/kernel"].bfloat16().float(), "t/bias": w["t/bias"]}
+    pre = O._conv(x, wq, "t", O.OracleConfig(emulate_bf16=True, first_layer_bf16_weights=False))
+    assert torch.equal(on, pre) and not torch.equal(on, off)
+    # Cin >= 64 layers are rounded either way
+    x64 = torch.randn(1, 64, 5, 5)
+    w64 = {"t/kernel": torch.randn(3, 3, 64, 64) * 0.05, "t/bias": torch.zeros(64)}
+    assert torch.equal(O._conv(x64, w64, "t", O.OracleConfig(emulate_bf16=True)),
+                       O._conv(x64, w64, "t", O.OracleConfig(emulate_bf16=True, first_layer_bf16_weights=False)))
