@@ -146,6 +146,33 @@ def run_cpu_port(batch, steps, warmup, threads=None):
     return batch * steps / dt, dt / steps, threads
 
 
+def embedding_delta_vs_port():
+    """The second half of BASELINE.json's metric ("embedding max|delta| vs the reference"): the fp32 parity mode's audio
+    embedding and AVC logits on two synthetic pairs against the fp64 CPU restatement (the reference's Keras path cannot
+    run).  Part of the cpu_baseline leg: the only place bench.py touches oracle/."""
+    import numpy as np
+    import torch
+    from l3embedding_b200.engine import Engine
+    from oracle import l3_oracle as O
+    w_np = O.init_weights(MODEL_TYPE, seed=20180123, randomize_bn=True)
+    video, audio, _ = O.synthetic_batch(2, seed=42)
+    eng = Engine(MODEL_TYPE, 2, "f32", training=True, weights=w_np)   # the configuration smoke() validates
+    try:
+        cfg = O.OracleConfig(dtype=torch.float64)
+        w = O.to_torch(w_np, dtype=torch.float64)
+        af = torch.from_numpy(O.pcm2float(audio, "float64"))
+        vf = torch.from_numpy(O.scale_video(video)).double()
+        emb = eng.embed_audio(audio, "original").cpu().numpy()
+        ref = O.audio_embedding(af, w, MODEL_TYPE, "original", cfg).numpy()
+        _, logits = eng.predict(video, audio)
+        ref_logits = O.avc_forward(vf, af, w, MODEL_TYPE, False, cfg).numpy()
+        return {"embedding_max_abs_delta": float(np.abs(emb - ref).max()), "embedding_abs_max": float(np.abs(ref).max()),
+                "logits_max_abs_delta": float(np.abs(logits - ref_logits).max()),
+                "mode": "f32 parity mode vs the fp64 CPU restatement, 2 synthetic pairs, 6144-d audio embedding"}
+    finally:
+        eng.close()
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -323,6 +350,10 @@ def main_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d-pair batch, 1 warm-up + %d timed train_step of the PyTorch-CPU "
                                               "restatement (oracle/), %.1f s/step" % (cb, csteps, sec)}
+            try:
+                line["cpu_baseline"]["parity"] = embedding_delta_vs_port()
+            except Exception as e:   # a reporting extra must never cost the bench line
+                line["cpu_baseline"]["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
