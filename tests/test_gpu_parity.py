@@ -191,6 +191,41 @@ def test_training_step_gradients_f32(model_type):
         assert np.abs(w_after[name] - w_ref[name].numpy()).max() <= 2e-6, name
 
 
+def test_data_parallel_replicas_match_oracle_replica_by_replica():
+    """Row (e): N replicas x B/N samples with PER-REPLICA BatchNorm statistics (training_utils.py:121-170 semantics, no
+    sync-BN).  Two replicas are emulated on one GPU: each slice runs forward/backward with global_batch = 4, the two
+    gradient arenas are summed (what the NCCL all-reduce does) and compared with the oracle evaluated replica by
+    replica and gradient-averaged over the global batch."""
+    mt, G, R = "cnn_L3_melspec2", 4, 2
+    w_np = O.init_weights(mt, seed=11, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(G, seed=909)
+    eng = _engine(mt, G // R, "f32", training=True, weights=w_np)
+    summed, ref = {}, {}
+    loss_dev = loss_ref = 0.0
+    for r in range(R):
+        sl = slice(r * (G // R), (r + 1) * (G // R))          # contiguous slices, training_utils.py:121-133
+        eng.forward_backward(video[sl], audio[sl], label[sl], global_batch=G)
+        loss_dev += eng.metrics()["loss"] * (G // R) / G
+        for k, v in eng.get_grads().items():
+            summed[k] = summed.get(k, 0.0) + v.astype(np.float64)
+        vf, af = _oracle_inputs(video[sl], audio[sl])
+        w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
+        grads, out, _ = O.compute_grads(vf, af, torch.from_numpy(label[sl]), w, mt, F64)
+        loss_ref += float(out["loss"]) * (G // R) / G
+        for k, g in grads.items():
+            g = g.numpy()
+            if k.endswith("/kernel"):
+                g = g - 2e-5 * w_np[k]                          # the l2 term is applied once, inside Adam
+            ref[k] = ref.get(k, 0.0) + g * ((G // R) / G)       # mean over the slice -> share of the global mean
+    assert abs(loss_dev - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
+    bad = []
+    for k in ref:
+        err, max_abs = rel_l2(summed[k], ref[k]), float(np.abs(summed[k] - ref[k]).max())
+        if not (err <= 1e-2 or max_abs <= 1e-4):
+            bad.append((k, err, max_abs))
+    assert not bad, bad
+
+
 def test_input_bn_gradient_fallback_when_gamma_is_zero():
     """The input-BN gradients normally come from the first layer's weight gradient divided by gamma; a zero gamma
     must take the direct path and still match the oracle."""
