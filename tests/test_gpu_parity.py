@@ -217,12 +217,15 @@ def test_data_parallel_replicas_match_oracle_replica_by_replica():
             if k.endswith("/kernel"):
                 g = g - 2e-5 * w_np[k]                          # the l2 term is applied once, inside Adam
             ref[k] = ref.get(k, 0.0) + g * ((G // R) / G)       # mean over the slice -> share of the global mean
-    assert abs(loss_dev - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
+    assert abs(loss_dev - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref)), (loss_dev, loss_ref)
     bad = []
     for k in ref:
         err, max_abs = rel_l2(summed[k], ref[k]), float(np.abs(summed[k] - ref[k]).max())
-        if not (err <= 1e-2 or max_abs <= 1e-4):
-            bad.append((k, err, max_abs))
+        # the input-BN gradients are residuals of large cancelling sums (see the gamma = 0 test below): 2e-2
+        tol = 2e-2 if "/bn0/" in k else 1e-2
+        if not (err <= tol or max_abs <= 1e-4):
+            bad.append((k, round(err, 5), max_abs))
+    print("replica test: loss", loss_dev, loss_ref, "worst", sorted(((rel_l2(summed[k], ref[k]), k) for k in ref), reverse=True)[:4])
     assert not bad, bad
 
 
