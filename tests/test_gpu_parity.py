@@ -225,7 +225,7 @@ def test_data_parallel_replicas_match_oracle_replica_by_replica():
         tol = 2e-2 if "/bn0/" in k else 1e-2
         if not (err <= tol or max_abs <= 1e-4):
             bad.append((k, round(err, 5), max_abs))
-    print("replica test: loss", loss_dev, loss_ref, "worst", sorted(((rel_l2(summed[k], ref[k]), k) for k in ref), reverse=True)[:4])
+    print("replica test: loss (device, oracle)", loss_dev, loss_ref)
     assert not bad, bad
 
 
