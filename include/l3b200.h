@@ -135,6 +135,32 @@ int l3_conv3x3_dgrad_stats(const void* dz, const float* w, void* da, int B, int 
  * dw (3,3,Cin,Cout) and db (Cout, may be NULL) are overwritten. */
 int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                      int dtype, int use_tc, void* stream);
+/* ---- element-wise layer ops of the training step, stand-alone (unit tests).  dtype selects float / bf16 storage; the
+ * ops are the kernels the step itself launches.  Reference semantics: keras BatchNormalization (axis -1) ->
+ * Activation('relu') -> MaxPooling2D(2) as instantiated at audio_model.py:376-437, vision_model.py:130-190; relu_first
+ * is the Conv -> ReLU -> BN order of vision_model.py:135-139. ------------------------------------------------------ */
+/* a = pool2x2?( relu_first ? scale*relu(z)+shift : relu(scale*z+shift) ): z unpadded (B,H,W,C), a zero-haloed padded
+ * (B,OH+2,OW+2,C) with OH = pool ? H/2 : H ('valid' pooling drops odd rows/columns).  The halo of `a` is not written.
+ * zsel / sel (optional, pool only): the winning pre-activation (B,OH,OW,C) and one byte per pooled element
+ * (window position 0..3 | 4*(max > 0)) -- the record the backward pass of the step consumes.                       */
+int l3_act_fwd(const void* z, void* a, int B, int H, int W, int C, const float* scale, const float* shift, int pool,
+               int relu_first, int dtype, void* zsel, uint8_t* sel, void* stream);
+/* Backward of the same block in training mode (gradient through the batch statistics included):
+ * da unpadded (B,OH,OW,C), z unpadded (B,H,W,C) -> dz zero-haloed padded (B,H+2,W+2,C) incl. its halo;
+ * bn4 = float[4*C] {scale = gamma*invstd, shift = beta - mean*scale, mean, invstd} of the batch statistics of z
+ * (of relu(z) if relu_first); d_gamma / d_beta: float[C] outputs.  zsel / sel: the forward record or NULL (the
+ * routing is then re-derived from z).                                                                              */
+int l3_bn_act_bwd(const void* da, const void* z, void* dz, int B, int H, int W, int C, const float* bn4, int pool,
+                  int relu_first, int dtype, const void* zsel, const uint8_t* sel, float* d_gamma, float* d_beta,
+                  void* stream);
+/* MaxPooling2D over the whole map of relu(scale*z+shift) (audio_model.py:436, vision_model.py:189):
+ * out (B,C) float, argmax (B,C) int = first maximum in row-major order.                                            */
+int l3_gmaxpool_fwd(const void* z, int B, int H, int W, int C, const float* scale, const float* shift, int dtype,
+                    float* out, int* argmax, void* stream);
+/* its backward fused with the BN backward of the last layer: dpool (B,C) float -> dz zero-haloed padded (B,H+2,W+2,C). */
+int l3_gmaxpool_bwd(const float* dpool, const int* argmax, const void* z, void* dz, int B, int H, int W, int C,
+                    const float* bn4, int dtype, float* d_gamma, float* d_beta, void* stream);
+
 /* device-side peek at internal activations for tests: which = "audio/z3", "vision/a1", "audio/x0", "concat" ...
  * copies up to `cap` floats (converted to f32) into out_host; returns element count or <0; synchronises. */
 int64_t l3_debug_read(l3_ctx* ctx, const char* which, int batch, float* out_host, int64_t cap);

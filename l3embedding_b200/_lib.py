@@ -58,6 +58,10 @@ SIGNATURES = {
     "l3_ctx_set_two_streams": (_i, [_vp, _i]),
     "l3_ctx_profile_enable": (_i, [_vp, _i]),
     "l3_ctx_profile_read": (_i, [_vp, _fp, C.POINTER(_i)]),
+    "l3_act_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "l3_bn_act_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "l3_gmaxpool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "l3_gmaxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "l3_debug_read": (_i64, [_vp, C.c_char_p, _i, _fp, _i64]),
 }
 

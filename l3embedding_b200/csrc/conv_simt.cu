@@ -102,10 +102,14 @@ template int launch_conv3x3_simt<bf16>(const bf16*, const float*, const float*, 
 
 // ---- weight gradient ----------------------------------------------------------------------------------
 // a: padded (B,H+2,W+2,Cin); dz: padded (B,H+2,W+2,Cout)
-// grid.x = ci tiles * co tiles * 9 taps ; grid.y = split-K slices over the B*H*W pixels (fp32 atomics)
-template <typename T>
+// grid.x = ci tiles * co tiles * 9 taps ; grid.y = split-K slices over the B*H*W pixels.
+// The slice partials are merged with atomics.  ACC = double (parity mode): the merge target is an fp64 scratch
+// (9*Cin*Cout + Cout doubles, zeroed by the launcher) that k_f64_to_f32 rounds once at the end, so the result does not
+// depend on the order in which the slices arrive (an fp32 merge in run-dependent order made the gradients -- and the
+// input-BN gradient derived from them -- differ from run to run by more than the 1e-2 parity bar at small batch).
+template <typename T, typename ACC>
 __global__ void __launch_bounds__(256)
-k_wgrad3x3_simt(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
+k_wgrad3x3_simt(const T* __restrict__ a, const T* __restrict__ dz, ACC* __restrict__ dw, ACC* __restrict__ db,
                 int B, int H, int W, int Cin, int Cout, int ci_tiles, int co_tiles, long long m_per_slice) {
   __shared__ __align__(16) float As[BK][BM];  // [pixel][ci]
   __shared__ __align__(16) float Bs[BK][BN];  // [pixel][co]
@@ -169,15 +173,47 @@ k_wgrad3x3_simt(const T* __restrict__ a, const T* __restrict__ dz, float* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int co = co0 + tx * 4 + j;
-      if (co < Cout) atomicAdd(&dw[((long long)tap * Cin + ci) * Cout + co], acc[i][j]);
+      if (co < Cout) atomicAdd(&dw[((long long)tap * Cin + ci) * Cout + co], (ACC)acc[i][j]);
     }
   }
-  if (do_bias && t < 64 && co0 + t < Cout) atomicAdd(&db[co0 + t], bsum);
+  if (do_bias && t < 64 && co0 + t < Cout) atomicAdd(&db[co0 + t], (ACC)bsum);
 }
+
+// dst[i] = (float)src[i]: the single rounding of an fp64 merge target
+__global__ void k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+static int f64_to_f32(const double* src, float* dst, long long n, cudaStream_t s) {
+  int blocks = (int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+  k_f64_to_f32<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(src, dst, n);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+// fp64 merge scratch: the caller's (carved from the context workspace) or a stream-ordered allocation
+struct Scratch64 {
+  double* p;
+  bool owned;
+  cudaStream_t s;
+  int init(double* given, long long n, cudaStream_t stream) {
+    s = stream;
+    p = given;
+    owned = false;
+    if (!p) {
+      L3_CHECK_CUDA(cudaMallocAsync((void**)&p, sizeof(double) * n, s));
+      owned = true;
+    }
+    L3_CHECK_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * n, s));
+    return 0;
+  }
+  ~Scratch64() {
+    if (owned && p) cudaFreeAsync(p, s);
+  }
+};
 
 template <typename T>
 int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
-                         cudaStream_t s) {
+                         cudaStream_t s, double* scratch64) {
   long long M = (long long)B * H * W;
   int ci_tiles = ceil_div(Cin, BM), co_tiles = ceil_div(Cout, BN);
   int tiles = ci_tiles * co_tiles * 9;
@@ -188,12 +224,24 @@ int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, i
   long long m_per_slice = ((M + slices - 1) / slices + BK - 1) / BK * BK;
   slices = (M + m_per_slice - 1) / m_per_slice;
   dim3 grid(tiles, (unsigned)slices);
-  k_wgrad3x3_simt<T><<<grid, 256, 0, s>>>(a, dz, dw, db, B, H, W, Cin, Cout, ci_tiles, co_tiles, m_per_slice);
+  if (sizeof(T) == 4) {
+    // parity mode: fp64 merge of the slice partials, rounded once (dw / db are overwritten)
+    const long long nw = 9LL * Cin * Cout;
+    Scratch64 sc;
+    if (sc.init(scratch64, nw + Cout, s)) return -1;
+    k_wgrad3x3_simt<T, double><<<grid, 256, 0, s>>>(a, dz, sc.p, db ? sc.p + nw : nullptr, B, H, W, Cin, Cout, ci_tiles,
+                                                    co_tiles, m_per_slice);
+    L3_CHECK_LAUNCH();
+    if (f64_to_f32(sc.p, dw, nw, s)) return -1;
+    if (db && f64_to_f32(sc.p + nw, db, Cout, s)) return -1;
+    return 0;
+  }
+  k_wgrad3x3_simt<T, float><<<grid, 256, 0, s>>>(a, dz, dw, db, B, H, W, Cin, Cout, ci_tiles, co_tiles, m_per_slice);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_wgrad3x3_simt<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
-template int launch_wgrad3x3_simt<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_wgrad3x3_simt<float>(const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t, double*);
+template int launch_wgrad3x3_simt<bf16>(const bf16*, const bf16*, float*, float*, int, int, int, int, int, cudaStream_t, double*);
 
 __global__ void k_flip_transpose(const float* __restrict__ w, float* __restrict__ wt, int Cin, int Cout) {
   long long n = 9LL * Cin * Cout;
@@ -221,6 +269,8 @@ int launch_flip_transpose(const float* w, float* w_t, int Cin, int Cout, cudaStr
 namespace l3 {
 
 static const int kFirstSeg = 16;   // x-segments per image row = pixel lanes per block
+template <typename T> struct FirstMergeT { typedef float type; };
+template <> struct FirstMergeT<float> { typedef double type; };
 
 // forward: out[b,y,x,co] = bias[co] + sum_{ky,kx,c} in[b,y+ky,x+kx,c] (padded coords) * w[ky][kx][c][co]
 // block = 16 channel groups (4 output channels each, weights in registers) x 16 pixel lanes (contiguous x segments)
@@ -293,14 +343,17 @@ k_first_conv(const T* __restrict__ in, const float* __restrict__ w, const float*
     }
   }
   if (stats != nullptr) {
-    __shared__ float red[2][CO];
-    if (threadIdx.x < 2 * CO) (&red[0][0])[threadIdx.x] = 0.f;
+    // merge type: fp64 from the first merge on in parity mode (T = float), fp32 shared atomics otherwise
+    typedef typename FirstMergeT<T>::type ACC;
+    __shared__ ACC red[2][CO];
+    if (threadIdx.x < 2 * CO) (&red[0][0])[threadIdx.x] = (ACC)0;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // lanes l and l+16 of a warp hold the same channel group (cg = tid & 15)
-      float a = ssum[i] + __shfl_xor_sync(0xffffffffu, ssum[i], 16);
-      float b2 = ssq[i] + __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+      ACC a = (ACC)ssum[i], b2 = (ACC)ssq[i];
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, 16);
       if ((threadIdx.x & 31) < 16) { atomicAdd(&red[0][cg * 4 + i], a); atomicAdd(&red[1][cg * 4 + i], b2); }
     }
     __syncthreads();
@@ -330,10 +383,11 @@ template int launch_first_conv<bf16>(const bf16*, const float*, const float*, bf
 //                                                            k_bn0_from_dw for the input-BN gradients)
 // block = 64 output channels x 4 pixel lanes (contiguous x segments); 4 pixels per iteration with all loads issued
 // first (input taps are warp-broadcast loads); every thread keeps its 9*C0 (+9) partial sums in registers.
-template <typename T, int C0>
+// ACC = double (parity mode): block partials are merged into an fp64 scratch and rounded once (see k_wgrad3x3_simt).
+template <typename T, int C0, typename ACC>
 __global__ void __launch_bounds__(256)
-k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restrict__ dw, float* __restrict__ db,
-              float* __restrict__ d1, int B, int H, int W, int rows_per_block) {
+k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, ACC* __restrict__ dw, ACC* __restrict__ db,
+              ACC* __restrict__ d1, int B, int H, int W, int rows_per_block) {
   constexpr int CO = 64, K = 9 * C0;
   const int co = threadIdx.x & 63, lane = threadIdx.x >> 6;
   float acc[K], ones[9];
@@ -392,7 +446,7 @@ k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restri
   __syncthreads();
   for (int i = threadIdx.x; i < (K + 10) * CO; i += blockDim.x) {
     const int k = i / CO, c = i % CO;
-    const float v = red[0][k][c] + red[1][k][c] + red[2][k][c] + red[3][k][c];
+    const ACC v = (ACC)red[0][k][c] + (ACC)red[1][k][c] + (ACC)red[2][k][c] + (ACC)red[3][k][c];
     if (k < K) atomicAdd(&dw[k * CO + c], v);
     else if (k < K + 9) { if (d1) atomicAdd(&d1[(k - K) * CO + c], v); }
     else if (db) atomicAdd(&db[c], v);
@@ -401,20 +455,34 @@ k_first_wgrad(const T* __restrict__ a, const T* __restrict__ dz, float* __restri
 
 template <typename T>
 int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0, int Cout,
-                       cudaStream_t s) {
+                       cudaStream_t s, double* scratch64) {
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_wgrad: C0=%d Cout=%d", C0, Cout);
-  if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
   long long n_rows = (long long)B * H;
   int rpb = (int)((n_rows + 148 * 8 - 1) / (148 * 8));
   if (rpb < 1) rpb = 1;
   int blocks = (int)((n_rows + rpb - 1) / rpb);
-  if (C0 == 1) k_first_wgrad<T, 1><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
-  else k_first_wgrad<T, 3><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
+  if (sizeof(T) == 4) {
+    // parity mode: fp64 merge, rounded once; dw / db / d1 are overwritten.  scratch = [dw 9*C0*64 | d1 9*64 | db 64]
+    const int nw = 9 * C0 * 64;
+    Scratch64 sc;
+    if (sc.init(scratch64, nw + 10 * 64, s)) return -1;
+    double *w64 = sc.p, *o64 = sc.p + nw, *b64 = sc.p + nw + 9 * 64;
+    if (C0 == 1) k_first_wgrad<T, 1, double><<<blocks, 256, 0, s>>>(a, dz, w64, db ? b64 : nullptr, d1 ? o64 : nullptr, B, H, W, rpb);
+    else k_first_wgrad<T, 3, double><<<blocks, 256, 0, s>>>(a, dz, w64, db ? b64 : nullptr, d1 ? o64 : nullptr, B, H, W, rpb);
+    L3_CHECK_LAUNCH();
+    if (f64_to_f32(w64, dw, nw, s)) return -1;
+    if (d1 && f64_to_f32(o64, d1, 9 * 64, s)) return -1;
+    if (db && f64_to_f32(b64, db, 64, s)) return -1;
+    return 0;
+  }
+  if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
+  if (C0 == 1) k_first_wgrad<T, 1, float><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
+  else k_first_wgrad<T, 3, float><<<blocks, 256, 0, s>>>(a, dz, dw, db, d1, B, H, W, rpb);
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_first_wgrad<float>(const float*, const float*, float*, float*, float*, int, int, int, int, int, cudaStream_t);
-template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, float*, int, int, int, int, int, cudaStream_t);
+template int launch_first_wgrad<float>(const float*, const float*, float*, float*, float*, int, int, int, int, int, cudaStream_t, double*);
+template int launch_first_wgrad<bf16>(const bf16*, const bf16*, float*, float*, float*, int, int, int, int, int, cudaStream_t, double*);
 
 // Input-BN gradients from the first layer's weight gradient (no pass over the image at all).  With
 // da = dgrad(dz) and xin = gamma*xhat + beta the zero-padded conv input:
@@ -475,15 +543,18 @@ k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, con
   constexpr int CO = 64;
   if (only_if != nullptr && *only_if == 0) return;   // the algebraic path (k_bn0_from_dw) already produced bn.sum
   __shared__ __align__(16) float ws[9 * C0 * CO];
-  __shared__ float red[2 * C0];
+  __shared__ double red[2 * C0];
   for (int i = threadIdx.x; i < 9 * C0 * CO; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 2 * C0) red[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2 * C0) red[threadIdx.x] = 0.0;
   __syncthreads();
   const int g = threadIdx.x & 7;
   const long long npix = (long long)B * H * W;
-  float s1[C0], s2[C0], mean[C0], inv[C0];
+  // the two sums are residuals of large cancelling terms (sum(da) is ~0 by construction of the BN backward above):
+  // accumulated in fp64 from the first addition on, so that only the per-pixel fp32 products carry rounding
+  double s1[C0], s2[C0];
+  float mean[C0], inv[C0];
 #pragma unroll
-  for (int c = 0; c < C0; ++c) { s1[c] = s2[c] = 0.f; mean[c] = bn.mean[c]; inv[c] = bn.invstd[c]; }
+  for (int c = 0; c < C0; ++c) { s1[c] = s2[c] = 0.0; mean[c] = bn.mean[c]; inv[c] = bn.invstd[c]; }
   const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
   const long long p_end = (npix + stride - 1) / stride * stride;   // all lanes of a warp iterate together (shuffles)
   for (long long p = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); p < p_end; p += stride) {
@@ -516,19 +587,24 @@ k_first_dgrad_bnstats(const T* __restrict__ dz, const float* __restrict__ w, con
       t += __shfl_xor_sync(0xffffffffu, t, 2);
       t += __shfl_xor_sync(0xffffffffu, t, 4);
       if (live && g == 0) {
-        const float xh = (x0[p * C0 + c] - mean[c]) * inv[c];
-        s1[c] += t;
-        s2[c] += t * xh;
+        const double xh = ((double)x0[p * C0 + c] - (double)mean[c]) * (double)inv[c];
+        s1[c] += (double)t;
+        s2[c] += (double)t * xh;
       }
     }
   }
 #pragma unroll
   for (int c = 0; c < C0; ++c) {
-    const float a1 = warp_sum(s1[c]), a2 = warp_sum(s2[c]);
+    double a1 = s1[c], a2 = s2[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
     if ((threadIdx.x & 31) == 0) { atomicAdd(&red[c], a1); atomicAdd(&red[C0 + c], a2); }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * C0) atomicAdd(&bn.sum[threadIdx.x], (double)red[threadIdx.x]);
+  if (threadIdx.x < 2 * C0) atomicAdd(&bn.sum[threadIdx.x], red[threadIdx.x]);
 }
 
 template <typename T>

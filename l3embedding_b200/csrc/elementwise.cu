@@ -11,6 +11,14 @@ namespace l3 {
 static const int kThreads = 256;
 static const int kMaxBlocks = 148 * 8;  // grid-stride kernels: a multiple of the SM count
 
+// Merge type of the per-channel reductions.  bf16 (throughput) mode: fp32 partials merged with fp32 shared-memory
+// atomics, one fp64 global atomic per block and channel.  fp32 (parity) mode: every partial is widened to fp64 BEFORE
+// the first merge (warp shuffles, shared and global atomics all fp64), so the result depends on the run-dependent merge
+// order only at the 1e-16 level -- the BN-backward sums are residuals of cancelling terms, and an fp32 merge in arrival
+// order moved the gradients of identical runs by more than the parity bar.
+template <typename T> struct MergeT { typedef float type; };
+template <> struct MergeT<float> { typedef double type; };
+
 // --------------------------------------------------------------------------------------------
 // video u8 -> float : 2*(x/255) - 1      (train.py:186; divide in fp64 then fp32 affine, as skimage does)
 // --------------------------------------------------------------------------------------------
@@ -45,10 +53,12 @@ int launch_video_to_f32(const uint8_t* v, float* out, long long n, cudaStream_t 
 // --------------------------------------------------------------------------------------------
 template <typename T, bool RELU>
 __global__ void k_channel_stats_vec(const T* __restrict__ x, long long rows, int C, double* __restrict__ sum) {
-  extern __shared__ float sh[];  // 2*C
+  typedef typename MergeT<T>::type ACC;
+  extern __shared__ __align__(8) unsigned char sh_raw[];
+  ACC* sh = reinterpret_cast<ACC*>(sh_raw);  // 2*C
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = (ACC)0;
   __syncthreads();
   float s1[8], s2[8];
 #pragma unroll
@@ -65,28 +75,34 @@ __global__ void k_channel_stats_vec(const T* __restrict__ x, long long rows, int
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    atomicAdd(&sh[g * 8 + i], s1[i]);
-    atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    atomicAdd(&sh[g * 8 + i], (ACC)s1[i]);
+    atomicAdd(&sh[C + g * 8 + i], (ACC)s2[i]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sum[i], (double)sh[i]);
 }
 
-// small C (1..4): one thread per row-strided pixel
+// small C (1..4): one thread per row-strided pixel.  Always merged in fp64 (the input of this kernel is the float
+// front-end / video tensor in both modes, a few hundred values per thread).
 template <typename T>
 __global__ void k_channel_stats_small(const T* __restrict__ x, long long rows, int C, double* __restrict__ sum) {
-  __shared__ float sh[8];
-  if (threadIdx.x < 8) sh[threadIdx.x] = 0.f;
+  __shared__ double sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0.0;
   __syncthreads();
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
     for (int c = 0; c < C; ++c) {
-      float t = to_f(x[r * C + c]);
+      double t = (double)to_f(x[r * C + c]);
       s1[c] += t;
       s2[c] += t * t;
     }
   for (int c = 0; c < C; ++c) {
-    float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+    double a = s1[c], b = s2[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(&sh[c], a);
       atomicAdd(&sh[4 + c], b);
@@ -94,8 +110,8 @@ __global__ void k_channel_stats_small(const T* __restrict__ x, long long rows, i
   }
   __syncthreads();
   if (threadIdx.x < C) {
-    atomicAdd(&sum[threadIdx.x], (double)sh[threadIdx.x]);
-    atomicAdd(&sum[C + threadIdx.x], (double)sh[4 + threadIdx.x]);
+    atomicAdd(&sum[threadIdx.x], sh[threadIdx.x]);
+    atomicAdd(&sum[C + threadIdx.x], sh[4 + threadIdx.x]);
   }
 }
 
@@ -113,10 +129,11 @@ int launch_channel_stats(const T* x, long long rows, int C, int relu, double* su
     int lanes = kThreads / (C / 8);
     long long want = (rows + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
     int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+    const size_t shb = 2 * C * sizeof(typename MergeT<T>::type);
     if (relu)
-      k_channel_stats_vec<T, true><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(x, rows, C, sum);
+      k_channel_stats_vec<T, true><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
     else
-      k_channel_stats_vec<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(x, rows, C, sum);
+      k_channel_stats_vec<T, false><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
   }
   L3_CHECK_LAUNCH();
   return 0;
@@ -464,10 +481,12 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int C, int OH, int OW, long long npix,
             BnRef bn, int relu_first) {
-  extern __shared__ float sh[];  // 2*C
+  typedef typename MergeT<T>::type ACC;
+  extern __shared__ __align__(8) unsigned char sh_raw[];
+  ACC* sh = reinterpret_cast<ACC*>(sh_raw);  // 2*C
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = (ACC)0;
   __syncthreads();
   // fp32 (parity) mode subtracts the batch mean before accumulating (no cancellation in S2 - mean*S1: the
   // near-zero input-BN beta gradient is sensitive to it); bf16 mode keeps the raw products.
@@ -562,16 +581,14 @@ k_bwd_stats(const T* __restrict__ da, const T* __restrict__ z, int H, int W, int
   // lanes of a warp that share a channel group (tid % groups) are `groups` apart: fold them first
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    ACC a1 = (ACC)s1[i], a2 = (ACC)s2[i];
     for (int off = 16; off >= groups; off >>= 1) {
-      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
-      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
     }
-  }
-  if ((threadIdx.x & 31) < groups || groups >= 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[g * 8 + i], s1[i]);
-      atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    if ((threadIdx.x & 31) < groups || groups >= 32) {
+      atomicAdd(&sh[g * 8 + i], a1);
+      atomicAdd(&sh[C + g * 8 + i], a2);
     }
   }
   __syncthreads();
@@ -583,10 +600,12 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 k_bwd_stats_sel(const T* __restrict__ da, const T* __restrict__ zsel, const uint8_t* __restrict__ sel, int C, long long npix,
                 BnRef bn, int relu_first) {
-  extern __shared__ float sh[];  // 2*C
+  typedef typename MergeT<T>::type ACC;
+  extern __shared__ __align__(8) unsigned char sh_raw[];
+  ACC* sh = reinterpret_cast<ACC*>(sh_raw);  // 2*C
   const int groups = C >> 3;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = (ACC)0;
   __syncthreads();
   constexpr bool kCentre = sizeof(T) == 4;   // see k_bwd_stats
   float mu[8], s1[8], s2[8];
@@ -628,16 +647,14 @@ k_bwd_stats_sel(const T* __restrict__ da, const T* __restrict__ zsel, const uint
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    ACC a1 = (ACC)s1[i], a2 = (ACC)s2[i];
     for (int off = 16; off >= groups; off >>= 1) {
-      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
-      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
     }
-  }
-  if ((threadIdx.x & 31) < groups || groups >= 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[g * 8 + i], s1[i]);
-      atomicAdd(&sh[C + g * 8 + i], s2[i]);
+    if ((threadIdx.x & 31) < groups || groups >= 32) {
+      atomicAdd(&sh[g * 8 + i], a1);
+      atomicAdd(&sh[C + g * 8 + i], a2);
     }
   }
   __syncthreads();
@@ -654,7 +671,7 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
     const int lanes = kThreads / (C / 8);
     long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
     int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-    k_bwd_stats_sel<T><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, zsel, sel, C, npix, bn, relu_first);
+    k_bwd_stats_sel<T><<<blocks, kThreads, 2 * C * sizeof(typename MergeT<T>::type), s>>>(da, zsel, sel, C, npix, bn, relu_first);
     L3_CHECK_LAUNCH();
     return 0;
   }
@@ -668,8 +685,9 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
   int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-  if (pool) k_bwd_stats<T, true><<<blocks, threads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
-  else k_bwd_stats<T, false><<<blocks, kThreads, 2 * C * sizeof(float), s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
+  const size_t shb = 2 * C * sizeof(typename MergeT<T>::type);
+  if (pool) k_bwd_stats<T, true><<<blocks, threads, shb, s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
+  else k_bwd_stats<T, false><<<blocks, kThreads, shb, s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -872,48 +890,6 @@ int launch_bn_bwd_apply(T* dy, const T* z, int B, int H, int W, int C, const BnR
 }
 template int launch_bn_bwd_apply<float>(float*, const float*, int, int, int, int, const BnRef&, int, cudaStream_t);
 template int launch_bn_bwd_apply<bf16>(bf16*, const bf16*, int, int, int, int, const BnRef&, int, cudaStream_t);
-
-// input BN (C=1|3) backward sums from da (T) and x0 (float)
-template <typename T>
-__global__ void k_input_bn_bwd_stats(const T* __restrict__ da, const float* __restrict__ x0, long long rows, int C,
-                                     BnRef bn) {
-  __shared__ float sh[8];
-  if (threadIdx.x < 8) sh[threadIdx.x] = 0.f;
-  __syncthreads();
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
-    for (int c = 0; c < C; ++c) {
-      float d = to_f(da[r * C + c]);
-      float xh = (x0[r * C + c] - bn.mean[c]) * bn.invstd[c];
-      s1[c] += d;
-      s2[c] += d * xh;
-    }
-  for (int c = 0; c < C; ++c) {
-    float a = warp_sum(s1[c]), b = warp_sum(s2[c]);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&sh[c], a);
-      atomicAdd(&sh[4 + c], b);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < C) {
-    atomicAdd(&bn.sum[threadIdx.x], (double)sh[threadIdx.x]);
-    atomicAdd(&bn.sum[C + threadIdx.x], (double)sh[4 + threadIdx.x]);
-  }
-}
-template <typename T>
-int launch_input_bn_bwd_stats(const T* da, const float* x0, long long rows, int C, const BnRef& bn, cudaStream_t s) {
-  L3_REQUIRE(C <= 4, "input bn: C<=4");
-  L3_CHECK_CUDA(cudaMemsetAsync(bn.sum, 0, sizeof(double) * 2 * C, s));
-  int blocks = (int)((rows + kThreads * 8 - 1) / (kThreads * 8));
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  if (blocks < 1) blocks = 1;
-  k_input_bn_bwd_stats<T><<<blocks, kThreads, 0, s>>>(da, x0, rows, C, bn);
-  L3_CHECK_LAUNCH();
-  return 0;
-}
-template int launch_input_bn_bwd_stats<float>(const float*, const float*, long long, int, const BnRef&, cudaStream_t);
-template int launch_input_bn_bwd_stats<bf16>(const bf16*, const float*, long long, int, const BnRef&, cudaStream_t);
 
 // --------------------------------------------------------------------------------------------
 // embedding head: MaxPooling2D(pool, padding='same') over the raw conv4b map, Flatten (h,w,c)

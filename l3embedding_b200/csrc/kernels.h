@@ -67,9 +67,6 @@ int launch_bn_bwd_finalize(const BnRef& bn, long long count, int raw_sums, cudaS
 template <typename T>
 int launch_bn_bwd_apply(T* dy_inout, const T* z, int B, int H, int W, int C, const BnRef& bn, int relu_first,
                         cudaStream_t s);   // dy: padded, z: unpadded
-// input BN backward reductions: sum(da), sum(da*xhat) with xhat from float x0
-template <typename T>
-int launch_input_bn_bwd_stats(const T* da, const float* x0, long long rows, int C, const BnRef& bn, cudaStream_t s);
 // embedding head: MaxPooling2D(pool,'same') over raw z (B,H,W,C) -> (B, OH*OW*C) float, flatten (h,w,c)
 template <typename T>
 int launch_embed_pool(const T* z, int B, int H, int W, int C, int ph, int pw, float* out, cudaStream_t s);
@@ -85,9 +82,11 @@ int launch_conv3x3_simt(const T* in, const float* w, const float* bias, T* out, 
                         int Cout, cudaStream_t s);
 // dw[(ky*3+kx)*Cin*Cout + ci*Cout + co] += sum_{b,y,x} a[b,y+ky-1,x+kx-1,ci] * dz[b,y,x,co]   (dw pre-zeroed)
 // db[co] += sum dz
+// T = float (parity mode): the split-K partials are merged in fp64 and rounded once -- dw / db are OVERWRITTEN and the
+// result is independent of the merge order; scratch64 = 9*Cin*Cout + Cout doubles (null: stream-ordered allocation)
 template <typename T>
 int launch_wgrad3x3_simt(const T* a, const T* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
-                         cudaStream_t s);
+                         cudaStream_t s, double* scratch64 = nullptr);
 // first-layer (Cin = 1|3, Cout = 64) backward: weight/bias gradient, and the input-BN backward sums computed
 // straight from dz without materialising the data gradient (bn.sum <- sum(da), sum(da*xhat))
 // stats (optional): double[2*64] per-channel sum / sum of squares of the stored output (BN batch statistics)
@@ -97,7 +96,7 @@ int launch_first_conv(const T* in, const float* w, const float* bias, T* out, in
 // d1 (optional, 9*64 floats): weight gradient w.r.t. an all-ones input plane, consumed by launch_bn0_from_dw
 template <typename T>
 int launch_first_wgrad(const T* a, const T* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0, int Cout,
-                       cudaStream_t s);
+                       cudaStream_t s, double* scratch64 = nullptr);
 // input-BN gradients (bn.sum = {sum da, sum da*xhat}) from dw and d1 alone; *fallback = 1 if some |gamma| ~ 0
 int launch_bn0_from_dw(const float* w, const float* dw, const float* d1, const BnRef& bn, int C0, int* fallback,
                        cudaStream_t s);

@@ -338,7 +338,7 @@ def _pool_same(x, ph, pw):
 
 def tower_forward(x_nhwc: torch.Tensor, w: Dict[str, torch.Tensor], tower: str, model_type: str,
                   training: bool, cfg: OracleConfig = OracleConfig(), stats: Optional[dict] = None,
-                  return_embedding_map: bool = False):
+                  return_embedding_map: bool = False, record: Optional[dict] = None):
     """x_nhwc: vision (B,224,224,3) in [-1,1] / audio front-end output (B,F,T,1).
     Returns (B,512) tower output, or the raw conv4b map (B,H,W,512) (embedding tap,
     audio_model.py:482 / vision_model.py:213) when return_embedding_map."""
@@ -356,8 +356,23 @@ def tower_forward(x_nhwc: torch.Tensor, w: Dict[str, torch.Tensor], tower: str, 
         bnn = f"{tower}/bn{nm[4:]}"
         if tower == "vision" and nm == "conv1b":          # vision_model.py:39-43 / :135-139
             x = _bn(F.relu(z), w, bnn, training, cfg, stats)
+            if record is not None:
+                record.setdefault("relu", {})[i] = (z.detach() > 0).permute(0, 2, 3, 1)
         else:
             x = F.relu(_bn(z, w, bnn, training, cfg, stats))
+        if record is not None:                            # the decisions tower_forward_frozen replays
+            xa = x.detach().permute(0, 2, 3, 1)
+            if nm == "conv4b":
+                B_, H_, W_, C_ = xa.shape
+                flat = xa.reshape(B_, H_ * W_, C_)
+                record["argmax"] = (flat == flat.amax(dim=1, keepdim=True)).to(torch.uint8).argmax(dim=1)
+                record["gmask"] = flat.amax(dim=1) > 0
+            elif nm in ("conv1b", "conv2b", "conv3b"):
+                win = _windows(xa, xa.shape[1] // 2, xa.shape[2] // 2)
+                record.setdefault("pos", {})[i] = (win == win.amax(dim=3, keepdim=True)).to(torch.uint8).argmax(dim=3)
+                record.setdefault("sign", {})[i] = win.amax(dim=3) > 0
+            else:
+                record.setdefault("mask", {})[i] = xa > 0
         if nm in ("conv1b", "conv2b", "conv3b"):
             x = _pool_same(x, 2, 2) if same_pool else F.max_pool2d(x, 2, 2)
     if tower == "audio":
@@ -366,6 +381,63 @@ def tower_forward(x_nhwc: torch.Tensor, w: Dict[str, torch.Tensor], tower: str, 
     else:
         x = _pool_same(x, 28, 28)
     return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)  # Flatten over (H,W,C)
+
+
+def _windows(t_nhwc, OH, OW):
+    """(B,H,W,C) -> (B,OH,OW,4,C): 2x2 windows in the order (0,0),(0,1),(1,0),(1,1); odd tails dropped ('valid')"""
+    B, _, _, C = t_nhwc.shape
+    return (t_nhwc[:, :2 * OH, :2 * OW, :].reshape(B, OH, 2, OW, 2, C).permute(0, 1, 3, 2, 4, 5)
+            .reshape(B, OH, OW, 4, C))
+
+
+def tower_forward_frozen(x_nhwc, w, tower, model_type, cfg, routing, stats=None):
+    """Training-mode tower forward whose DECISIONS (ReLU masks, max-pool routing) are not taken from its own values
+    but from `routing`, recorded on the device: arithmetic differences of one bf16 ulp then stay one-ulp differences
+    instead of re-routing whole gradient paths, so gradients become comparable tensor by tensor.
+      routing["mask"][i]   bool (B,H,W,C)    un-pooled Conv->BN->ReLU layer i: activation > 0
+      routing["relu"][i]   bool (B,H,W,C)    Conv->ReLU->BN layer (vision conv1b): z > 0
+      routing["pos"][i]    int64 (B,OH,OW,C) pooled layer i: winning window position 0..3 (order of _windows)
+      routing["sign"][i]   bool (B,OH,OW,C)  pooled layer i: window maximum > 0
+      routing["argmax"]    int64 (B,512)     global max-pool: winning pixel (row-major) ; routing["gmask"] bool: > 0
+    Same layer sequence as tower_forward (audio_model.py:370-437, vision_model.py:124-190)."""
+    if stats is None:
+        stats = {}
+    spec = (AUDIO_SPECS if tower == "audio" else VISION_SPECS)[model_type]
+    x = x_nhwc.permute(0, 3, 1, 2).to(cfg.dtype)
+    if spec["input_bn"]:
+        x = _bn(x, w, f"{tower}/bn0", True, cfg, stats)
+    for i, nm in enumerate(CONV_NAMES):
+        z = _conv(x, w, f"{tower}/{nm}", cfg)
+        bnn = f"{tower}/bn{nm[4:]}"
+        relu_first = tower == "vision" and nm == "conv1b"
+        if relu_first:
+            z = z * routing["relu"][i].permute(0, 3, 1, 2).contiguous().to(z.dtype)
+        y = _bn(z, w, bnn, True, cfg, stats).permute(0, 2, 3, 1)             # NHWC
+        if nm == "conv4b":
+            B, H, W, C = y.shape
+            v = torch.gather(y.reshape(B, H * W, C), 1, routing["argmax"].unsqueeze(1)).squeeze(1)
+            return v * routing["gmask"].to(v.dtype)
+        if nm in ("conv1b", "conv2b", "conv3b"):
+            OH, OW = y.shape[1] // 2, y.shape[2] // 2                        # even sizes for the vision tower ('same')
+            y = torch.gather(_windows(y, OH, OW), 3, routing["pos"][i].unsqueeze(3)).squeeze(3)
+            if not relu_first:
+                y = y * routing["sign"][i].to(y.dtype)
+        else:
+            y = y * routing["mask"][i].to(y.dtype)
+        x = y.permute(0, 3, 1, 2).contiguous()    # same memory layout (hence conv kernel) as tower_forward
+    raise AssertionError("unreachable")
+
+
+def compute_grads_frozen(video_f, audio_f, label, w, model_type, cfg, routing):
+    """compute_grads with the device's routing decisions (routing = {"vision": ..., "audio": ...})."""
+    st: dict = {}
+    v = tower_forward_frozen(video_f, w, "vision", model_type, cfg, routing["vision"], st)
+    a = tower_forward_frozen(frontend(audio_f, model_type, cfg), w, "audio", model_type, cfg, routing["audio"], st)
+    logits = head_forward(v, a, w)
+    loss, ce, acc = avc_loss(logits, label, w, cfg)
+    names = [k for k, t in w.items() if t.requires_grad]
+    grads = torch.autograd.grad(loss, [w[k] for k in names])
+    return dict(zip(names, grads)), dict(loss=loss.detach(), ce=ce.detach(), acc=acc.detach(), logits=logits.detach())
 
 
 def head_forward(v, a, w):

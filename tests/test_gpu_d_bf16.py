@@ -1,0 +1,181 @@
+"""GPU parity tests, bf16 throughput mode (the tcgen05 path bench.py times): whole-model checks against the fp32 path
+of the same library and against the bf16-emulating oracle (OracleConfig.emulate_bf16 rounds exactly where the device
+stores bf16), forward layer by layer and -- with the device's own ReLU / max-pool routing replayed in the oracle --
+every gradient tensor of a training step.  bf16 cannot meet the 1e-3 embedding bar: its error is reported.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import l3_oracle as O
+from _gpu_common import MODEL_TYPES, GOLDEN, F64, engine as _engine, rel_l2, pad as _pad, oracle_inputs as _oracle_inputs
+
+pytestmark = pytest.mark.gpu
+
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+@pytest.mark.parametrize("batch", [1, 3])
+def test_bf16_tensor_core_path_tracks_f32_path(model_type, batch):
+    """Every model type and odd batch sizes through the tcgen05 path (odd widths 197/199/99/49, 'valid' pooling that
+    drops columns, ReLU-before-BN layer): logits, gradients and a training step against the fp32 SIMT path of the same
+    library on identical inputs.  Bars are bf16-sized: 5 % of the largest logit / of the loss (gradients: see the bf16-emulating-oracle test)."""
+    w_np = O.init_weights(model_type, seed=3, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(batch, seed=505)
+    res = {}
+    for dt in ("f32", "bf16"):
+        eng = _engine(model_type, batch, dt, training=True, weights=w_np)
+        _, logits = eng.predict(video, audio)
+        eng.forward_backward(video, audio, label)
+        m = eng.metrics()
+        res[dt] = (logits, eng.get_grads(), m)
+        if dt == "bf16":
+            assert eng.uses_tensor_cores
+        eng.close()
+    lf, gf, mf = res["f32"]
+    lb, gb, mb = res["bf16"]
+    assert np.abs(lb - lf).max() <= 0.05 * max(1.0, np.abs(lf).max()), (lb, lf)
+    assert abs(mb["loss"] - mf["loss"]) <= 0.05 * max(1.0, abs(mf["loss"]))
+    assert all(np.isfinite(v).all() for v in gb.values())
+
+
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+def test_bf16_path_matches_bf16_emulating_oracle(model_type):
+    """Throughput-mode parity proper: the oracle rounds to bfloat16 at exactly the points where the device stores bf16
+    (OracleConfig.emulate_bf16), so the two differ only by fp32 accumulation order.  Layer by layer (training-mode
+    forward, all real shapes incl. the odd widths 197/199/99/49 and the ReLU-before-BN layer):
+      * every conv output z agrees within 2 (first two layers) / 4 bf16 ulps of the layer's largest value,
+      * the first two layers are bit-identical in >= 99 % / 97 % of their elements (an accumulation-order difference only
+        shows when it straddles a bf16 rounding boundary; deeper layers inherit and multiply those 1-ulp flips --
+        measured 1e-4 -> 6e-4 -> 1.5e-2 -> 0.12 -> ... of the elements, always by one ulp),
+      * logits within 0.06.
+    Gradients: test_bf16_training_step_gradients_with_frozen_routing below."""
+    import torch.nn.functional as F
+    B = 3
+    w_np = O.init_weights(model_type, seed=3, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(B, seed=505)
+    cfg = O.OracleConfig(dtype=torch.float32, emulate_bf16=True)
+    w = O.to_torch(w_np, dtype=torch.float32, requires_grad=True)
+    vf = torch.from_numpy(O.scale_video(video))
+    af = torch.from_numpy(O.pcm2float(audio, "float32"))
+    grads, out, _ = O.compute_grads(vf, af, torch.from_numpy(label), w, model_type, cfg)
+    eng = _engine(model_type, B, "bf16", training=True, weights=w_np)
+    assert eng.uses_tensor_cores
+    eng.forward_backward(video, audio, label)
+    got = eng.get_grads()
+    logits = eng.debug_read("logits", B).reshape(B, 2)
+    with torch.no_grad():
+        wd = O.to_torch(w_np)
+        for tower, x in (("vision", vf), ("audio", O.frontend(af, model_type, cfg))):
+            spec = (O.AUDIO_SPECS if tower == "audio" else O.VISION_SPECS)[model_type]
+            x = x.permute(0, 3, 1, 2)
+            if spec["input_bn"]:
+                x = O._bn(x, wd, f"{tower}/bn0", True, cfg, {})
+            for i, nm in enumerate(O.CONV_NAMES):
+                z = O._conv(x, wd, f"{tower}/{nm}", cfg)
+                zo = z.permute(0, 2, 3, 1).numpy()
+                zd = eng.debug_read(f"{tower}/z{i}", B).reshape(zo.shape)
+                d = np.abs(zd - zo)
+                ulp = 2.0 ** (np.floor(np.log2(np.abs(zo).max())) - 7)      # bf16: 8 significant bits
+                assert d.max() <= (2 if i < 2 else 4) * ulp, (tower, i, d.max(), ulp)   # deeper: several 1-ulp inputs add up
+                if i < 2:
+                    assert (d > 0).mean() <= (1e-2 if i == 0 else 3e-2), (tower, i, (d > 0).mean())
+                bnn = f"{tower}/bn{nm[4:]}"
+                if tower == "vision" and nm == "conv1b":
+                    x = O._bn(F.relu(z), wd, bnn, True, cfg, {})
+                else:
+                    x = F.relu(O._bn(z, wd, bnn, True, cfg, {}))
+                if nm in ("conv1b", "conv2b", "conv3b"):
+                    x = O._pool_same(x, 2, 2) if tower == "vision" else F.max_pool2d(x, 2, 2)
+    d_logit = float(np.abs(logits - out["logits"].numpy()).max())
+    print(model_type, "logits max|d| %.3g" % d_logit)
+    assert d_logit <= 0.06
+
+
+def _device_routing(eng, B, model_type):
+    """The ReLU / max-pool decisions the device took in its last training forward, in the form
+    O.tower_forward_frozen replays (see there)."""
+    routing = {}
+    concat = eng.debug_read("concat", B).reshape(B, 1024)
+    for tower, off in (("vision", 0), ("audio", 512)):
+        r = {"mask": {}, "relu": {}, "pos": {}, "sign": {}}
+        H, W = (224, 224) if tower == "vision" else eng.frontend_shape
+        for i in range(7):
+            C = (64, 64, 128, 128, 256, 256, 512)[i]
+            if i in (1, 3, 5):
+                OH, OW = H // 2, W // 2
+                sel = eng.debug_read("%s/sel%d" % (tower, i), B).reshape(B, OH, OW, C).astype(np.int64)
+                r["pos"][i] = torch.from_numpy(sel & 3)
+                r["sign"][i] = torch.from_numpy(((sel >> 2) & 1).astype(bool))
+                if tower == "vision" and i == 1:
+                    r["relu"][i] = torch.from_numpy(eng.debug_read("vision/z1", B).reshape(B, H, W, C) > 0)
+                H, W = OH, OW
+            else:
+                r["mask"][i] = torch.from_numpy(eng.debug_read("%s/a%d" % (tower, i), B).reshape(B, H, W, C) > 0)
+        r["argmax"] = torch.from_numpy(eng.debug_read(tower + "/argmax", B).reshape(B, 512).astype(np.int64))
+        r["gmask"] = torch.from_numpy(concat[:, off:off + 512] > 0)
+        routing[tower] = r
+    return routing
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_kapredbinputbn"])
+def test_bf16_training_step_gradients_with_frozen_routing(model_type):
+    """bf16 backward parity proper.  On a random network one bf16 ulp of difference in a pre-activation can flip a
+    ReLU or move a max-pool winner and thereby re-route a whole gradient path, which is why free-running comparisons of
+    bf16 gradients only agree in direction (cosine 0.89-0.96, round 1).  Here the bf16-emulating oracle REPLAYS the
+    device's own decisions (ReLU masks from the stored activations, pool winners from the recorded routing bytes, the
+    global max-pool's argmax), so both sides differentiate the same piecewise-linear function and differ only by
+    accumulation order and the 1-ulp bf16 rounding flips that follow from it.  Every gradient tensor of the step must
+    then agree to 2e-2 relative L2 (the near-zero ones -- biases of convolutions feeding a training-mode BN, whose
+    gradient is analytically 0 -- to 2e-2 of the largest gradient magnitude of their layer's kernel instead)."""
+    B = 4
+    w_np = O.init_weights(model_type, seed=3, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(B, seed=515)
+    eng = _engine(model_type, B, "bf16", training=True, weights=w_np)
+    assert eng.uses_tensor_cores
+    eng.forward_backward(video, audio, label)
+    got = eng.get_grads()
+    loss_dev = eng.metrics()["loss"]
+    routing = _device_routing(eng, B, model_type)
+    cfg = O.OracleConfig(dtype=torch.float64, emulate_bf16=True)
+    w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
+    vf = torch.from_numpy(O.scale_video(video)).double()
+    af = torch.from_numpy(O.pcm2float(audio, "float64"))
+    grads, out = O.compute_grads_frozen(vf, af, torch.from_numpy(label), w, model_type, cfg, routing)
+    rows, bad = [], []
+    for name, g_ref in grads.items():
+        g_ref = g_ref.numpy()
+        if name.endswith("/kernel"):
+            g_ref = g_ref - 2e-5 * w_np[name]
+        err = rel_l2(got[name], g_ref)
+        max_abs = float(np.abs(got[name] - g_ref).max())
+        layer_kernel = name.rsplit("/", 1)[0] + "/kernel"
+        scale = float(np.abs(grads[layer_kernel].numpy()).max()) if layer_kernel in grads else float(np.abs(g_ref).max())
+        rows.append((name, round(err, 4), "%.2e" % max_abs))
+        if not (err <= 2e-2 or max_abs <= 2e-2 * scale):
+            bad.append((name, round(err, 4), max_abs, scale))
+    worst = sorted(rows, key=lambda r: -r[1])[:8]
+    print(model_type, "frozen-routing bf16 gradients: loss dev %.5f oracle %.5f; worst rel-L2:" % (loss_dev, float(out["loss"])), worst)
+    assert abs(loss_dev - float(out["loss"])) <= 2e-2 * max(1.0, abs(float(out["loss"])))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2"])
+def test_bf16_throughput_mode_reports_error(model_type):
+    """bf16 storage/operands cannot meet 1e-3; bound it loosely and print the measured error."""
+    B = 2
+    w_np = O.init_weights(model_type, seed=20180123, randomize_bn=True)
+    video, audio, label = O.synthetic_batch(B, seed=202)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64)
+    ref = O.audio_embedding(af, w, model_type, "original", F64).numpy()
+    eng = _engine(model_type, B, "bf16", training=True, weights=w_np)
+    got = eng.embed_audio(audio, "original").cpu().numpy()
+    err = np.abs(got - ref).max()
+    print("bf16 embedding max|d| = %.4g (|e|max %.3g), tensor cores: %s" % (err, np.abs(ref).max(), eng.uses_tensor_cores))
+    assert err <= 0.02 * np.abs(ref).max()      # bf16 operands + bf16 activations: ~1 % of the largest value
+    eng.forward_backward(video, audio, label)
+    assert np.isfinite(eng.metrics()["loss"])
+    g = eng.get_grads()
+    assert all(np.isfinite(v).all() for v in g.values())

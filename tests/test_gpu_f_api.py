@@ -1,0 +1,93 @@
+"""GPU tests of the reference-facing Python surface: keras-style model object (compile / fit_generator / save_weights /
+load_embedding / predict), device-side framing for get_l3_frames_uniform, and train() with its output files and resume
+rule (l3embedding/train.py:218-421, l3embedding/model.py:85-181, data/usc/features.py:256-306).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import l3_oracle as O
+from _gpu_common import MODEL_TYPES, GOLDEN, F64, engine as _engine, rel_l2, pad as _pad, oracle_inputs as _oracle_inputs
+
+pytestmark = pytest.mark.gpu
+
+def test_keras_style_api_end_to_end(tmp_path):
+    from l3embedding_b200 import model as M
+    m, _, _ = M.MODELS["cnn_L3_melspec2"]()
+    m.configure(dtype="f32")
+    m.compile(M.Adam(lr=1e-4), loss="categorical_crossentropy", metrics=["accuracy"])
+    video, audio, label = O.synthetic_batch(2, seed=17)
+
+    def gen():
+        while True:
+            yield [O.scale_video(video), O.pcm2float(audio, "float32")], label
+    h = m.fit_generator(gen(), steps_per_epoch=2, epochs=2, validation_data=gen(), validation_steps=1, verbose=0)
+    assert set(h.history) == {"loss", "acc", "val_loss", "val_acc"} and len(h.history["loss"]) == 2
+    p = str(tmp_path / "model_latest.h5")
+    m.save_weights(p)
+    e = M.load_embedding(p, "cnn_L3_melspec2", "audio", "original")
+    e.parent.configure(dtype="f32")
+    x = O.pcm2float(audio, "float32")
+    emb = e.predict(x)
+    assert emb.shape == (2, 6144)
+    w = O.to_torch(m.named_weights(), dtype=torch.float64)
+    ref = O.audio_embedding(torch.from_numpy(x).double(), w, "cnn_L3_melspec2", "original", F64).numpy()
+    assert np.abs(emb - ref).max() <= 1e-3
+
+
+def test_device_side_framing_equals_host_framing():
+    """get_l3_frames_uniform: embeddings of overlapping 1 s windows read in place on the device == the reference's
+    framed-copy route, for int16 and float32 signals, across a max_batch boundary."""
+    from l3embedding_b200 import model as M
+    from l3embedding_b200.features import get_l3_frames_uniform, frame_signal
+    m, _, _ = M.MODELS["cnn_L3_melspec2"]()
+    m.configure(dtype="f32")
+    m.set_named_weights(O.init_weights("cnn_L3_melspec2", seed=5, randomize_bn=True))
+    e, _, _ = M.convert_audio_model_to_embedding(m.get_layer("audio_model"), m.inputs[1], "cnn_L3_melspec2", "short")
+    rng = np.random.default_rng(0)
+    sig = (0.1 * rng.standard_normal(48000 + 6 * 4800 + 100)).astype(np.float32)
+    got = get_l3_frames_uniform(sig, e, hop_size=0.1)
+    a, hop, n = frame_signal(sig)
+    assert got.shape == (7, 512) and n == 7
+    idx = np.arange(48000)[None, :] + hop * np.arange(n)[:, None]
+    ref = e.predict(a[idx].reshape(n, 1, 48000), batch_size=4)
+    assert np.abs(got - ref).max() <= 1e-5
+    w = O.to_torch(m.named_weights(), dtype=torch.float64)
+    orc = O.audio_embedding(torch.from_numpy(a[idx].reshape(n, 1, 48000)).double(), w, "cnn_L3_melspec2", "short", F64).numpy()
+    assert np.abs(got - orc).max() <= 1e-3
+    eng = e._get_engine(4)       # smaller than n: exercises the chunk loop
+    i16 = np.clip(np.round(sig * 32767), -32768, 32767).astype(np.int16)
+    g16 = eng.embed_audio_frames(i16, hop, "short").cpu().numpy()
+    r16 = eng.embed_audio(i16[idx].reshape(n, 1, 48000)[:4], "short").cpu().numpy()
+    assert np.abs(g16[:4] - r16).max() <= 1e-5
+
+
+def test_train_function_writes_reference_files_and_resumes(tmp_path):
+    """train() (train.py:218-421): same output files, CSV history, and resume from model_latest.h5 + the CSV."""
+    from l3embedding_b200 import train as T
+    from l3embedding_b200.synthetic import synthetic_batch
+    for name, seed in (("demo_train", 0), ("demo_valid", 50)):
+        d = tmp_path / name
+        d.mkdir()
+        for i in range(2):
+            v, a, l = synthetic_batch(4, seed=seed + i)
+            np.savez(d / ("b%d.npz" % i), video=v, audio=a, label=l)
+    kw = dict(train_epoch_size=2, validation_epoch_size=1, train_batch_size=2, validation_batch_size=2,
+              model_type="cnn_L3_melspec2", learning_rate=1e-4, checkpoint_interval=1, disable_logging=True, gpus=1,
+              dtype="bf16")
+    model_dir, hist = T.train(str(tmp_path / "demo_train"), str(tmp_path / "demo_valid"), str(tmp_path / "out"),
+                              num_epochs=2, **kw)
+    files = set(os.listdir(model_dir))
+    assert {"config.json", "model.json", "model_spec.pkl", "model_latest.h5", "model_best_valid_accuracy.h5",
+            "model_best_valid_loss.h5", "model_checkpoint.01.h5", "model_checkpoint.02.h5", "history_checkpoint.pkl",
+            "history_csvlog.csv", "history.pkl"} <= files
+    assert "embedding/demo/cnn_L3_melspec2" in model_dir.replace(os.sep, "/")
+    assert len(hist.history["loss"]) == 2 and set(hist.history) == {"loss", "acc", "val_loss", "val_acc"}
+    assert T.get_restart_info(os.path.join(model_dir, "history_csvlog.csv"))[0] == 1
+    _, hist2 = T.train(str(tmp_path / "demo_train"), str(tmp_path / "demo_valid"), str(tmp_path / "out"), num_epochs=3,
+                       continue_model_dir=model_dir, **kw)
+    assert len(hist2.history["loss"]) == 1                      # only epoch index 2 ran
+    assert T.get_restart_info(os.path.join(model_dir, "history_csvlog.csv"))[0] == 2
