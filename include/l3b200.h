@@ -64,7 +64,11 @@ int l3_ctx_set_use_tensor_cores(l3_ctx* ctx, int enable);
 int l3_ctx_uses_tensor_cores(l3_ctx* ctx);
 
 /* ---- hot path -------------------------------------------------------------------------------------------- */
-/* async H2D of one batch from (pinned) host memory into the ctx staging buffers (needs L3_WS_HOST_STAGING). */
+/* async H2D of one batch from (pinned) host memory into one of the ctx's TWO staging slots, on the ctx's own copy
+ * stream (needs L3_WS_HOST_STAGING).  Staged batches are consumed first-in-first-out by the calls that take NULL
+ * inputs; at most two may be pending.  This is the one entry point that may be called from a second host thread while
+ * another thread drives the step: a prefetch thread uploads batch k+1 while step k runs (the reference's generator,
+ * train.py:142-195, is serial with the step).  Replaces the feed_dict copy of keras train_on_batch. */
 int l3_upload_batch_host(l3_ctx* ctx, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
                          const float* labels_host, int batch);
 /* forward + backward of one AVC batch = the device part of keras train_on_batch (train.py:408-414).
@@ -75,9 +79,12 @@ int l3_forward_backward(l3_ctx* ctx, const void* video, int video_fmt, const voi
 /* Keras-2.0.9 Adam (train.py:282) incl. the l2(1e-5) regulariser gradient; increments the step counter. */
 int l3_adam_step(l3_ctx* ctx, float lr);
 int l3_adam_set_t(l3_ctx* ctx, int64_t t);
+int64_t l3_adam_get_t(l3_ctx* ctx);        /* steps taken so far (checkpointed with the moments; <0 on error) */
 /* out[4] = {sum of per-sample cross-entropy, #correct, l2 penalty (1e-5*sum w^2), batch}; synchronises. */
 int l3_get_metrics(l3_ctx* ctx, float out[4]);
-/* single-GPU convenience: upload (host) + forward_backward + adam + metrics in one call; synchronises. */
+/* one keras train_on_batch on the oldest staged batch: forward_backward + metrics + adam; synchronises once. */
+int l3_train_step_staged(l3_ctx* ctx, int batch, float lr, float out_metrics[4]);
+/* single-GPU convenience: l3_upload_batch_host + l3_train_step_staged in one call. */
 int l3_train_step_host(l3_ctx* ctx, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
                        const float* labels_host, int batch, float lr, float out_metrics[4]);
 /* inference-mode forward (keras predict / evaluate, BN moving statistics): probs (batch,2) device floats;

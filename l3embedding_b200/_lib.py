@@ -42,7 +42,9 @@ SIGNATURES = {
     "l3_forward_backward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i]),
     "l3_adam_step": (_i, [_vp, _f]),
     "l3_adam_set_t": (_i, [_vp, _i64]),
+    "l3_adam_get_t": (_i64, [_vp]),
     "l3_get_metrics": (_i, [_vp, _fp]),
+    "l3_train_step_staged": (_i, [_vp, _i, _f, _fp]),
     "l3_train_step_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _f, _fp]),
     "l3_predict": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "l3_embed_audio": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -14,6 +14,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/l3b200.h"
@@ -211,10 +212,19 @@ struct l3_ctx {
   cudaStream_t stream_v;        // vision tower's own (high-priority) stream when two_streams: the caller's stream has
   cudaEvent_t ev_join_v;        // the default (lowest) priority and would not win against the side streams
   int wgrad_streams;
-  // host staging
-  void *st_video, *st_audio;
-  float* st_labels;
-  int st_video_fmt, st_audio_fmt, st_batch;
+  // host staging: two device slots filled by l3_upload_batch_host on a copy stream (FIFO), so that the upload of batch
+  // k+1 -- issued by a prefetch thread -- overlaps the step of batch k.  ev_staged[s]: upload into slot s complete;
+  // ev_consumed[s]: the step that read slot s has finished reading it (the slot may be overwritten).
+  int device;
+  void *st_video[2], *st_audio[2];
+  float* st_labels[2];
+  int st_video_fmt[2], st_audio_fmt[2], st_batch[2];
+  int st_head, st_tail, st_count;
+  bool st_consumed_valid[2];
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_staged[2], ev_consumed[2];
+  std::mutex st_mu;
+  float* metrics_host;   // pinned: {ce sum, #correct} + l2 (double) of the last enqueue_metrics
   long long adam_t;
   int use_tc;
   int last_batch;
@@ -297,13 +307,11 @@ static long long carve(l3_ctx* c) {
   audio_geometry(c->spec, &n_out, &n_frames, &left);
   c->fe_tables = bp.take(frontend_table_bytes(c->spec.n_dft, c->spec.mel ? c->spec.n_mels : 1));
   c->clip_max = (int*)bp.take(4 * B);
-  if (c->flags & L3_WS_HOST_STAGING) {
-    c->st_video = bp.take(B * 224 * 224 * 3 * 4);
-    c->st_audio = bp.take(B * kSR * 4);
-    c->st_labels = (float*)bp.take(B * 2 * 4);
-  } else {
-    c->st_video = c->st_audio = nullptr;
-    c->st_labels = nullptr;
+  for (int sl = 0; sl < 2; ++sl) {
+    const bool on = (c->flags & L3_WS_HOST_STAGING) != 0;
+    c->st_video[sl] = on ? bp.take(B * 224 * 224 * 3 * 4) : nullptr;
+    c->st_audio[sl] = on ? bp.take(B * kSR * 4) : nullptr;
+    c->st_labels[sl] = on ? (float*)bp.take(B * 2 * 4) : nullptr;
   }
   for (int t = 0; t < 2; ++t) {
     long long g0_max = 0, g1_max = 0;
@@ -837,7 +845,29 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->stream = (cudaStream_t)stream;
   c->adam_t = 0;
   c->use_tc = (dtype == L3_DTYPE_BF16) && conv_tc_supported();
-  c->st_batch = 0;
+  c->device = 0;
+  cudaGetDevice(&c->device);
+  c->st_head = c->st_tail = c->st_count = 0;
+  c->st_batch[0] = c->st_batch[1] = 0;
+  c->st_consumed_valid[0] = c->st_consumed_valid[1] = false;
+  c->copy_stream = nullptr;
+  c->metrics_host = nullptr;
+  if (cudaMallocHost((void**)&c->metrics_host, 64) != cudaSuccess) {
+    set_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  if (flags & L3_WS_HOST_STAGING) {
+    bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&c->ev_staged[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("staging stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+      delete c;
+      return nullptr;
+    }
+  }
   c->last_batch = 0;
   c->prof_on = 0;
   c->prof_used = 0;
@@ -877,7 +907,14 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
 
 void l3_ctx_destroy(l3_ctx* ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->device);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_staged[i]); cudaEventDestroy(ctx->ev_consumed[i]); }
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  if (ctx->metrics_host) cudaFreeHost(ctx->metrics_host);
   if (ctx->stream2) {
     cudaStreamSynchronize(ctx->stream2);
     cudaEventDestroy(ctx->ev_fork);
@@ -944,32 +981,65 @@ int l3_upload_batch_host(l3_ctx* c, const void* video_host, int video_fmt, const
                          const float* labels_host, int batch) {
   if (check_batch(c, batch)) return -2;
   L3_REQUIRE(c->flags & L3_WS_HOST_STAGING, "context was created without L3_WS_HOST_STAGING");
-  if (video_host) {
+  L3_REQUIRE(video_host && audio_host, "video and audio host buffers are required");
+  L3_CHECK_CUDA(cudaSetDevice(c->device));   // may be called from a prefetch thread
+  int slot;
+  {
+    std::lock_guard<std::mutex> lk(c->st_mu);
+    L3_REQUIRE(c->st_count < 2, "both staging slots hold batches that no step has consumed yet");
+    slot = c->st_head;
+  }
+  cudaStream_t cs = c->copy_stream;
+  if (c->st_consumed_valid[slot]) L3_CHECK_CUDA(cudaStreamWaitEvent(cs, c->ev_consumed[slot], 0));
+  {
     size_t n = (size_t)batch * 224 * 224 * 3 * (video_fmt == L3_VIDEO_U8 ? 1 : 4);
-    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_video, video_host, n, cudaMemcpyHostToDevice, c->stream));
+    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_video[slot], video_host, n, cudaMemcpyHostToDevice, cs));
   }
-  if (audio_host) {
+  {
     size_t n = (size_t)batch * kSR * (audio_fmt == L3_AUDIO_I16 ? 2 : 4);
-    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_audio, audio_host, n, cudaMemcpyHostToDevice, c->stream));
+    L3_CHECK_CUDA(cudaMemcpyAsync(c->st_audio[slot], audio_host, n, cudaMemcpyHostToDevice, cs));
   }
-  if (labels_host) L3_CHECK_CUDA(cudaMemcpyAsync(c->st_labels, labels_host, (size_t)batch * 8, cudaMemcpyHostToDevice, c->stream));
-  c->st_video_fmt = video_fmt;
-  c->st_audio_fmt = audio_fmt;
-  c->st_batch = batch;
+  if (labels_host) L3_CHECK_CUDA(cudaMemcpyAsync(c->st_labels[slot], labels_host, (size_t)batch * 8, cudaMemcpyHostToDevice, cs));
+  L3_CHECK_CUDA(cudaEventRecord(c->ev_staged[slot], cs));
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->st_video_fmt[slot] = video_fmt;
+  c->st_audio_fmt[slot] = audio_fmt;
+  c->st_batch[slot] = batch;
+  c->st_head ^= 1;
+  c->st_count++;
   return 0;
 }
 
+// NULL inputs = the oldest staged batch: *slot receives its index (the caller releases it with release_slot once the
+// kernels reading it are enqueued); explicit device pointers leave *slot = -1
 static int resolve_inputs(l3_ctx* c, const void*& video, int& vfmt, const void*& audio, int& afmt, const float*& labels,
-                          int batch, bool need_labels) {
+                          int batch, bool need_labels, int* slot) {
+  *slot = -1;
   if (!video && !audio) {
-    L3_REQUIRE(c->st_batch == batch, "no staged batch of size %d (staged %d)", batch, c->st_batch);
-    video = c->st_video; vfmt = c->st_video_fmt;
-    audio = c->st_audio; afmt = c->st_audio_fmt;
-    if (!labels) labels = c->st_labels;
+    std::lock_guard<std::mutex> lk(c->st_mu);
+    L3_REQUIRE(c->st_count > 0, "no staged batch: call l3_upload_batch_host first");
+    const int sl = c->st_tail;
+    L3_REQUIRE(c->st_batch[sl] == batch, "the staged batch has %d samples, not %d", c->st_batch[sl], batch);
+    L3_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_staged[sl], 0));
+    video = c->st_video[sl]; vfmt = c->st_video_fmt[sl];
+    audio = c->st_audio[sl]; afmt = c->st_audio_fmt[sl];
+    if (!labels) labels = c->st_labels[sl];
+    *slot = sl;
   }
   L3_REQUIRE(video && audio, "video and audio must both be given (or both NULL for the staged batch)");
   L3_REQUIRE(!need_labels || labels, "labels required");
   L3_REQUIRE(c->vision.present && c->audio.present, "context lacks a tower (L3_WS_VISION | L3_WS_AUDIO)");
+  return 0;
+}
+// the forward pass (both towers joined, head launched) has been enqueued on c->stream: everything that reads the slot
+// precedes this point in stream order
+static int release_slot(l3_ctx* c, int slot) {
+  if (slot < 0) return 0;
+  L3_CHECK_CUDA(cudaEventRecord(c->ev_consumed[slot], c->stream));
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->st_consumed_valid[slot] = true;
+  c->st_tail ^= 1;
+  c->st_count--;
   return 0;
 }
 
@@ -978,12 +1048,15 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
   if (check_batch(c, batch)) return -2;
   L3_REQUIRE(c->flags & L3_WS_TRAINING, "context was created without L3_WS_TRAINING");
   L3_REQUIRE(global_batch >= batch, "global_batch %d < batch %d", global_batch, batch);
-  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, true)) return -2;
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  int slot;
+  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, true, &slot)) return -2;
   const float gs = 1.0f / (float)global_batch;
   L3_CHECK_CUDA(cudaMemsetAsync(c->grads, 0, sizeof(float) * c->layout.n_params, c->stream));
   int rc;
   if (c->dtype == L3_DTYPE_BF16) {
     rc = forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
+    if (!rc) rc = release_slot(c, slot);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
     if (!rc) rc = fork_streams(c);
     if (!rc) rc = tower_backward<bf16>(c, c->vision, batch);
@@ -991,6 +1064,7 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
     if (!rc) rc = join_streams(c);
   } else {
     rc = forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
+    if (!rc) rc = release_slot(c, slot);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
     if (!rc) rc = fork_streams(c);
     if (!rc) rc = tower_backward<float>(c, c->vision, batch);
@@ -1018,38 +1092,64 @@ int l3_adam_set_t(l3_ctx* c, int64_t t) {
   return 0;
 }
 
-int l3_get_metrics(l3_ctx* c, float out[4]) {
-  L3_REQUIRE(c != nullptr && out != nullptr, "null argument");
+int64_t l3_adam_get_t(l3_ctx* c) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  return c->adam_t;
+}
+
+// l2 penalty kernel + asynchronous read-back of {ce sum, #correct, l2} into the pinned metrics buffer
+static int enqueue_metrics(l3_ctx* c) {
   if (launch_l2_penalty(c->params, c->layout.n_l2, c->l2_out, c->stream)) return -1;
-  float m[2];
+  L3_CHECK_CUDA(cudaMemcpyAsync(c->metrics_host, c->head.metrics, 8, cudaMemcpyDeviceToHost, c->stream));
+  L3_CHECK_CUDA(cudaMemcpyAsync(c->metrics_host + 2, c->l2_out, 8, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+static void read_metrics(l3_ctx* c, float out[4]) {
   double l2;
-  L3_CHECK_CUDA(cudaMemcpyAsync(m, c->head.metrics, 8, cudaMemcpyDeviceToHost, c->stream));
-  L3_CHECK_CUDA(cudaMemcpyAsync(&l2, c->l2_out, 8, cudaMemcpyDeviceToHost, c->stream));
-  L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
-  out[0] = m[0];
-  out[1] = m[1];
+  memcpy(&l2, c->metrics_host + 2, 8);
+  out[0] = c->metrics_host[0];
+  out[1] = c->metrics_host[1];
   out[2] = (float)(1e-5 * l2);
   out[3] = (float)c->last_batch;
+}
+
+int l3_get_metrics(l3_ctx* c, float out[4]) {
+  L3_REQUIRE(c != nullptr && out != nullptr, "null argument");
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  if (enqueue_metrics(c)) return -1;
+  L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  read_metrics(c, out);
   return 0;
+}
+
+int l3_train_step_staged(l3_ctx* c, int batch, float lr, float out_metrics[4]) {
+  int rc = l3_forward_backward(c, nullptr, 0, nullptr, 0, nullptr, batch, batch);
+  // loss terms of the weights the batch was run with (as keras reports them): read back asynchronously BEFORE the
+  // update is enqueued, one synchronisation at the end of the step
+  if (!rc && out_metrics) rc = enqueue_metrics(c);
+  if (!rc) rc = l3_adam_step(c, lr);
+  if (!rc) L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  if (!rc && out_metrics) read_metrics(c, out_metrics);
+  return rc;
 }
 
 int l3_train_step_host(l3_ctx* c, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
                        const float* labels_host, int batch, float lr, float out_metrics[4]) {
   int rc = l3_upload_batch_host(c, video_host, video_fmt, audio_host, audio_fmt, labels_host, batch);
-  if (!rc) rc = l3_forward_backward(c, nullptr, 0, nullptr, 0, nullptr, batch, batch);
-  if (!rc && out_metrics) rc = l3_get_metrics(c, out_metrics);  // loss terms of the weights the batch was run with
-  if (!rc) rc = l3_adam_step(c, lr);
-  if (!rc) L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  if (!rc) rc = l3_train_step_staged(c, batch, lr, out_metrics);
   return rc;
 }
 
 int l3_predict(l3_ctx* c, const void* video, int video_fmt, const void* audio, int audio_fmt, const float* labels,
                int batch, float* probs_out, float* logits_out) {
   if (check_batch(c, batch)) return -2;
-  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, false)) return -2;
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  int slot;
+  if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, false, &slot)) return -2;
   int rc = c->dtype == L3_DTYPE_BF16
                ? forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, false, 1.0f / batch)
                : forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, false, 1.0f / batch);
+  if (!rc) rc = release_slot(c, slot);
   if (rc) return rc;
   if (probs_out) L3_CHECK_CUDA(cudaMemcpyAsync(probs_out, c->head.probs, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));
   if (logits_out) L3_CHECK_CUDA(cudaMemcpyAsync(logits_out, c->head.logits, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));

@@ -23,7 +23,13 @@ class SingleReplica:
     def slice(self, batch):
         return slice(0, batch)
 
+    def attach(self, engine):
+        return None
+
     def allreduce_grads(self, engine):
+        return None
+
+    def average_bn_state(self, engine):
         return None
 
     def sum_scalars(self, *xs):
@@ -46,9 +52,16 @@ class TorchDistReplicas:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t
 
+    def attach(self, engine):
+        return None
+
     def allreduce_grads(self, engine):
         # one flat fp32 arena (38 MB for cnn_L3_melspec2): a single NCCL ring/NVLS all-reduce
         return self.allreduce_tensor(engine.grads)
+
+    def average_bn_state(self, engine):
+        self.allreduce_tensor(engine.bn_state)
+        engine.bn_state.div_(self.world_size)
 
     def sum_scalars(self, *xs):
         import torch

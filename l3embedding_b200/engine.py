@@ -163,6 +163,41 @@ class Engine:
     def set_adam_t(self, t: int):
         _lib.check(self.lib.l3_adam_set_t(self.ctx, int(t)), "l3_adam_set_t")
 
+    def get_adam_t(self) -> int:
+        return int(_lib.check(self.lib.l3_adam_get_t(self.ctx), "l3_adam_get_t"))
+
+    # ---- optimizer state (keras keeps ONE Adam state for the whole fit; so must every rebuild / resume) -----
+    def get_adam_state(self) -> Dict[str, np.ndarray]:
+        """{'t': step count, 'm': first moments, 'v': second moments} as flat host arrays in arena order."""
+        if not self.training:
+            raise L3Error("inference engine holds no optimizer state")
+        torch.cuda.synchronize(self.device)
+        return {"t": np.int64(self.get_adam_t()), "m": self.adam_m.cpu().numpy(), "v": self.adam_v.cpu().numpy()}
+
+    def set_adam_state(self, state) -> None:
+        if not self.training:
+            raise L3Error("inference engine holds no optimizer state")
+        m, v = np.asarray(state["m"], np.float32).reshape(-1), np.asarray(state["v"], np.float32).reshape(-1)
+        if m.size != self.n_params or v.size != self.n_params:
+            raise ValueError("optimizer state of %d / %d scalars does not fit a %s model (%d parameters)"
+                             % (m.size, v.size, self.model_type, self.n_params))
+        self.adam_m.copy_(torch.from_numpy(m))
+        self.adam_v.copy_(torch.from_numpy(v))
+        self.set_adam_t(int(state["t"]))
+
+    def adopt_state(self, other: "Engine") -> None:
+        """Take over weights, BN statistics and -- when both sides train -- the Adam moments and step count of another
+        engine of the same model (device-to-device), e.g. before replacing it with a larger one."""
+        if other.model_type != self.model_type:
+            raise ValueError("cannot adopt the state of a %s engine" % other.model_type)
+        torch.cuda.synchronize(other.device)
+        self.params.copy_(other.params)
+        self.bn_state.copy_(other.bn_state)
+        if self.training and other.training:
+            self.adam_m.copy_(other.adam_m)
+            self.adam_v.copy_(other.adam_v)
+            self.set_adam_t(other.get_adam_t())
+
     def metrics(self) -> Dict[str, float]:
         """Synchronises.  ce = mean cross-entropy over the local batch; loss = ce + l2 penalty (keras `loss`)."""
         out = (C.c_float * 4)()
@@ -189,6 +224,56 @@ class Engine:
                        "l3_train_step_host")
         n = max(out[3], 1.0)
         return dict(ce=out[0] / n, acc=out[1] / n, l2=out[2], loss=out[0] / n + out[2], batch=out[3])
+
+    def upload_host(self, video: np.ndarray, audio: np.ndarray, labels: Optional[np.ndarray]) -> int:
+        """Asynchronous H2D of one batch from host (ideally pinned) memory into one of the engine's two staging slots, on
+        the library's copy stream.  Returns the batch size.  At most two uploads may be pending; they are consumed in
+        order by train_step_staged / forward_backward_staged.  Safe to call from a prefetch thread while another
+        thread runs a step.  The arrays must stay alive (and unmodified) until the consuming step has returned."""
+        if video.dtype not in (np.uint8, np.float32) or audio.dtype not in (np.int16, np.float32):
+            raise TypeError("video must be uint8|float32 and audio int16|float32")
+        if not (video.flags.c_contiguous and audio.flags.c_contiguous):
+            raise ValueError("upload_host needs C-contiguous arrays")
+        B = video.shape[0]
+        lab = None
+        if labels is not None:
+            if labels.dtype != np.float32 or not labels.flags.c_contiguous:
+                raise ValueError("labels must be a C-contiguous float32 array")
+            lab = labels.ctypes.data_as(C.c_void_p)
+        vf = _lib.VIDEO_U8 if video.dtype == np.uint8 else _lib.VIDEO_F32
+        af = _lib.AUDIO_I16 if audio.dtype == np.int16 else _lib.AUDIO_F32
+        _lib.check(self.lib.l3_upload_batch_host(self.ctx, video.ctypes.data_as(C.c_void_p), vf,
+                                                 audio.ctypes.data_as(C.c_void_p), af, lab, B), "l3_upload_batch_host")
+        return B
+
+    def train_step_staged(self, batch: int, lr: float) -> Dict[str, float]:
+        """keras train_on_batch on the oldest staged batch (forward + backward + Adam; one synchronisation)."""
+        out = (C.c_float * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_train_step_staged(self.ctx, int(batch), float(lr), out), "l3_train_step_staged")
+        n = max(out[3], 1.0)
+        return dict(ce=out[0] / n, acc=out[1] / n, l2=out[2], loss=out[0] / n + out[2], batch=out[3],
+                    ce_sum=out[0], correct=out[1])
+
+    def forward_backward_staged(self, batch: int, global_batch: Optional[int] = None):
+        """forward + backward on the oldest staged batch (the data-parallel step adds the all-reduce and Adam)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_forward_backward(self.ctx, None, 0, None, 0, None, int(batch),
+                                                    int(global_batch or batch)), "l3_forward_backward")
+
+    def train_stream(self, batches, lr: float):
+        """Pipelined training over an iterable of host batches (video, audio, labels): the upload of batch k+1 is in
+        flight on the copy stream while step k computes.  Yields the metrics of every step."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        n_cur = self.upload_host(*cur)
+        while cur is not None:
+            nxt = next(it, None)
+            n_nxt = self.upload_host(*nxt) if nxt is not None else 0
+            yield self.train_step_staged(n_cur, lr)
+            cur, n_cur = nxt, n_nxt
 
     def predict(self, video, audio, labels=None):
         """Inference-mode forward (BN moving statistics): returns (probs, logits) as (B,2) numpy arrays."""

@@ -133,6 +133,8 @@ class L3Model:
         self._seed = seed
         self._host_weights: Optional[Dict[str, np.ndarray]] = None
         self._engine = None
+        self._adam_host = None      # optimizer state waiting for the first training engine (resume)
+        self._pending = 0           # batches staged on the device that no step has consumed yet
         self.dtype = os.environ.get("L3B200_DTYPE", "bf16")
         self.optimizer = None
         self.loss = None
@@ -203,6 +205,14 @@ class L3Model:
         """Order of keras Model.get_weights() on the AVC model (nested towers: trainable then non-trainable)."""
         return [n for l in self.layers for n in l._weight_names]
 
+    def container_weight_names(self) -> List[str]:
+        """Order of keras `Container.weights` of the whole AVC model: ALL trainable weights (layer order, nested towers
+        flattened) and then all non-trainable ones -- the order in which the arrays sit in the single nested-model group
+        of a checkpoint written from a `multi_gpu_model` (model.py:76-77,117-119)."""
+        nt = lambda n: n.startswith("kapre/") or n.endswith(("moving_mean", "moving_variance"))
+        names = self.weight_names()
+        return [n for n in names if not nt(n)] + [n for n in names if nt(n)]
+
     def get_weights(self):
         w = self._weights_dict()
         return [w[n] if not n.startswith("kapre/") else self._kapre(n) for n in self.weight_names()]
@@ -242,15 +252,42 @@ class L3Model:
 
     # ---- device state ------------------------------------------------------------------------------------
     def _get_engine(self, batch: int, training: bool):
+        """The ONE device engine of this model.  It is only ever replaced by a larger or more capable one (never
+        downgraded from training to inference or to a smaller batch), and a replacement adopts weights, BN statistics,
+        Adam moments and the step count device-to-device: keras keeps a single optimizer state for the whole fit
+        (train.py:282,408), so validation with a bigger batch or a predict() between steps must not reset it."""
         from .engine import Engine  # imports torch
         e = self._engine
-        if e is not None and (e.dtype != self.dtype or (training and not e.training) or e.max_batch < batch):
+        if e is not None and e.dtype != self.dtype:
             self._pull()
+            self._adam_host = e.get_adam_state() if e.training else self._adam_host
             self._drop_engine()
-        if self._engine is None:
-            self._engine = Engine(self.model_type, max_batch=max(batch, 1), dtype=self.dtype, training=training,
-                                  weights=self._weights_dict())
-        return self._engine
+            e = None
+        if e is not None and (e.training or not training) and e.max_batch >= batch:
+            return e
+        new = Engine(self.model_type, max_batch=max(batch, e.max_batch if e else 1, 1), dtype=self.dtype,
+                     training=bool(training or (e is not None and e.training)), weights=None if e else self._weights_dict())
+        if e is not None:
+            new.adopt_state(e)
+            e.close()
+        elif new.training and self._adam_host is not None:
+            new.set_adam_state(self._adam_host)      # restored from a checkpoint before the engine existed
+            self._adam_host = None
+        self._engine = new
+        return new
+
+    def get_optimizer_state(self):
+        """Adam step count and moments ({'t','m','v'}, flat arena order) or None before the first training step."""
+        if self._engine is not None and self._engine.training:
+            return self._engine.get_adam_state()
+        return self._adam_host
+
+    def set_optimizer_state(self, state):
+        if self._engine is not None and self._engine.training:
+            self._engine.set_adam_state(state)
+        else:
+            self._adam_host = dict(t=np.int64(state["t"]), m=np.asarray(state["m"], np.float32),
+                                   v=np.asarray(state["v"], np.float32))
 
     # ---- keras training API ------------------------------------------------------------------------------
     def compile(self, optimizer, loss="categorical_crossentropy", metrics=("accuracy",)):
@@ -265,37 +302,92 @@ class L3Model:
         from . import dp
         return dp.current(self.num_gpus)
 
-    def train_on_batch(self, x, y):
-        """x = [video (B,224,224,3), audio (B,1,48000)]; float inputs in [-1,1] as the reference generator yields
-        (train.py:186,189), or raw uint8 / int16 (scaled on the device).  Returns [loss, acc] (global batch)."""
+    # The step is split in two so that fit_generator can overlap the upload of batch k+1 with step k:
+    #   _stage(x, y)  -> asynchronous H2D of this rank's slice into a staging slot (library copy stream)
+    #   _step(ticket) -> forward/backward on the staged slot, gradient all-reduce (N > 1), metrics, Adam
+    def _stage(self, x, y):
         if self.optimizer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
         video, audio = x
         par = self._dp()
         B = len(video)
         sl = par.slice(B)
-        eng = self._get_engine(sl.stop - sl.start, True)
-        eng.forward_backward(video[sl], audio[sl], y[sl], global_batch=B)
+        n = sl.stop - sl.start
+        if self._engine is not None and self._pending and (n > self._engine.max_batch or not self._engine.training):
+            raise RuntimeError("batch of %d samples while a batch staged for a smaller engine is still pending: "
+                               "batch sizes must not grow between consecutive training batches" % n)
+        eng = self._get_engine(n, True)
+        par.attach(eng)
+
+        def host(a, kinds):
+            a = np.asarray(a[sl])
+            if a.dtype not in kinds:
+                raise TypeError("unsupported input dtype %s (want one of %s)" % (a.dtype, [np.dtype(k).name for k in kinds]))
+            return np.ascontiguousarray(a)
+        v, a = host(video, (np.uint8, np.float32)), host(audio, (np.int16, np.float32))
+        lab = np.ascontiguousarray(np.asarray(y[sl], dtype=np.float32))
+        if v.shape[1:] != (224, 224, 3) or a.size != n * 48000 or lab.shape != (n, 2):
+            raise ValueError("expected video (B,224,224,3), audio (B,1,48000), labels (B,2); got %s %s %s"
+                             % (v.shape, a.shape, lab.shape))
+        eng.upload_host(v, a, lab)
+        self._pending += 1
+        return dict(B=B, n=n, keep=(v, a, lab))     # the host arrays must outlive the asynchronous copy
+
+    def _step(self, ticket):
+        par, eng = self._dp(), self._engine
+        B, n = ticket["B"], ticket["n"]
+        self._pending -= 1
+        if par.world_size == 1:
+            m = eng.train_step_staged(n, self.optimizer.lr)
+            return [m["loss"], m["acc"]]
+        eng.forward_backward_staged(n, global_batch=B)
         par.allreduce_grads(eng)
         m = eng.metrics()            # loss of the weights the batch was run with, as keras reports
         eng.adam_step(self.optimizer.lr)
         ce_sum, correct = par.sum_scalars(m["ce_sum"], m["correct"])
         return [ce_sum / B + m["l2"], correct / B]
 
+    def train_on_batch(self, x, y):
+        """x = [video (B,224,224,3), audio (B,1,48000)]; float inputs in [-1,1] as the reference generator yields
+        (train.py:186,189), or raw uint8 / int16 (scaled on the device).  Returns [loss, acc] (global batch)."""
+        return self._step(self._stage(x, y))
+
     def test_on_batch(self, x, y):
+        """keras test_on_batch (inference-mode BN).  Under data parallelism every rank evaluates its slice of the batch
+        (training_utils.py:121-133) and the sums are all-reduced; a batch larger than the engine is run in chunks --
+        the engine is never rebuilt for validation."""
         video, audio = x
-        eng = self._get_engine(len(video), False)
-        eng.predict(video, audio, y)
-        m = eng.metrics()
-        return [m["loss"], m["acc"]]
+        par = self._dp()
+        B = len(video)
+        sl = par.slice(B)
+        n = sl.stop - sl.start
+        eng = self._engine if self._engine is not None else self._get_engine(n, False)
+        ce_sum = correct = 0.0
+        l2 = 0.0
+        for s0 in range(sl.start, sl.stop, eng.max_batch):
+            s1 = min(s0 + eng.max_batch, sl.stop)
+            eng.predict(video[s0:s1], audio[s0:s1], y[s0:s1])
+            m = eng.metrics()
+            ce_sum += m["ce_sum"]; correct += m["correct"]; l2 = m["l2"]
+        ce_sum, correct = par.sum_scalars(ce_sum, correct)
+        return [ce_sum / B + l2, correct / B]
+
+    def sync_replicas(self):
+        """Data parallel only: BN moving statistics are per replica during training (reference semantics: one momentum
+        update per replica, training_utils.py:141-162); before validation / checkpointing they are replaced by their
+        mean over the ranks so that every rank evaluates -- and rank 0 saves -- the same model."""
+        par = self._dp()
+        if par.world_size > 1 and self._engine is not None:
+            par.average_bn_state(self._engine)
 
     def predict(self, x, batch_size=32, verbose=0):
         video, audio = x
         n = len(video)
-        eng = self._get_engine(min(batch_size, max(n, 1)), False)
+        eng = self._engine if self._engine is not None else self._get_engine(min(batch_size, max(n, 1)), False)
+        step = min(batch_size, eng.max_batch)
         out = np.empty((n, 2), np.float32)
-        for s in range(0, n, batch_size):
-            out[s:s + batch_size] = eng.predict(video[s:s + batch_size], audio[s:s + batch_size])[0]
+        for s in range(0, n, step):
+            out[s:s + step] = eng.predict(video[s:s + step], audio[s:s + step])[0]
         return out
 
     def evaluate_generator(self, generator, steps, **_):
@@ -323,15 +415,24 @@ class L3Model:
         for epoch in range(initial_epoch, epochs):
             _call(callbacks, "on_epoch_begin", epoch)
             tot, loss, acc = 0, 0.0, 0.0
+            # software pipeline: the next item is pulled from the generator and its upload enqueued BEFORE the current
+            # step is run, so H2D (and the generator's own work) overlap the device step.  Within an epoch only: the
+            # generator is not advanced past the epoch's last batch before validation, as in keras.
+            item = next(generator)
+            ticket = self._stage(item[0], item[1])
             for step in range(steps_per_epoch):
-                item = next(generator)
-                x, y = item[0], item[1]
-                b = len(y)
+                b = ticket["B"]
+                nxt = None
+                if step + 1 < steps_per_epoch:
+                    item = next(generator)
+                    nxt = self._stage(item[0], item[1])
                 _call(callbacks, "on_batch_begin", step, {"batch": step, "size": b})
-                l, a = self.train_on_batch(x, y)
+                l, a = self._step(ticket)
                 tot += b; loss += l * b; acc += a * b
                 _call(callbacks, "on_batch_end", step, {"batch": step, "size": b, "loss": l, "acc": a})
+                ticket = nxt
             logs = {"loss": loss / max(tot, 1), "acc": acc / max(tot, 1)}
+            self.sync_replicas()
             if validation_data is not None:
                 vl, va = self.evaluate_generator(validation_data, validation_steps)
                 logs["val_loss"], logs["val_acc"] = vl, va

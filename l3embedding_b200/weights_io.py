@@ -116,18 +116,28 @@ def load_weights(path, model):
         model.set_weights([z[n] for n in names])
 
 
+def _keras_name(cn: str) -> str:
+    """canonical 'vision/conv1a/kernel' -> keras variable-style 'vision_conv1a/kernel:0' (the slash nests a sub-group)"""
+    parts = cn.split("/")
+    return "%s/%s:0" % ("_".join(parts[:-1]), parts[-1])
+
+
 def _keras_groups(model):
     """[(top-level layer name, [(keras weight name, canonical name)])] as keras 2.0.9 save_weights groups them: EVERY
     layer of `model.layers` gets a group (weight-less ones with an empty `weight_names`), datasets are named after the
-    backend variables ('<layer>/<weight>:0'; the slash makes h5py nest a sub-group)."""
-    groups = []
-    for layer in model.layers:
-        entries = []
-        for cn in layer._weight_names:
-            parts = cn.split("/")
-            entries.append(("%s/%s:0" % ("_".join(parts[:-1]), parts[-1]), cn))
-        groups.append((layer.name, entries))
-    return groups
+    backend variables ('<layer>/<weight>:0').
+
+    A model wrapped by multi_gpu_model (num_gpus > 1) is saved the way keras saves the reference's wrapper
+    (training_utils.py:121-170): inputs, one Lambda slice per input and replica, the WHOLE template model as one nested
+    layer holding every array in Container order (all trainable, then all non-trainable), and the output
+    concatenation -- the layout `load_model(..., src_num_gpus=N)` expects (model.py:117-119)."""
+    if getattr(model, "num_gpus", 0) > 1:
+        groups = [("input_1", []), ("input_2", [])]
+        groups += [("lambda_%d" % (i + 1), []) for i in range(2 * model.num_gpus)]
+        groups.append((model.name, [(_keras_name(cn), cn) for cn in model.container_weight_names()]))
+        groups.append(("dense_2", []))     # training_utils.py:168-170: the merged output carries the output's name
+        return groups
+    return [(layer.name, [(_keras_name(cn), cn) for cn in layer._weight_names]) for layer in model.layers]
 
 
 def _save_h5(path, model, names, arrays):
@@ -176,15 +186,35 @@ def _load_h5(path, model):
         f = minihdf5.File(path)
     dec = lambda n: n.decode("utf8") if isinstance(n, bytes) else str(n)
     root = f["model_weights"] if ("layer_names" not in f.attrs and "model_weights" in f) else f   # Model.save() files
-    arrays = []
+    groups = []
     for ln in [dec(n) for n in root.attrs["layer_names"]]:
         g = root[ln]
-        for wn in g.attrs["weight_names"]:
-            arrays.append(np.asarray(g[dec(wn)]))
+        arrs = [np.asarray(g[dec(wn)]) for wn in g.attrs["weight_names"]]
+        if arrs:
+            groups.append((ln, arrs))
+    if hasattr(f, "close"):
+        f.close()
+    arrays = [a for _, arrs in groups for a in arrs]
     expected = model.weight_names()
     if len(arrays) != len(expected):
         raise ValueError("checkpoint %s holds the weights of a different model layout (%d arrays, the %s model has %d)"
                          % (path, len(arrays), model.model_type, len(expected)))
-    model.set_weights(arrays)
-    if hasattr(f, "close"):
-        f.close()
+    # Which layout?  single-GPU files have one group per weighted top-level layer (vision_model, audio_model, dense_1,
+    # dense_2); a file saved from a multi_gpu_model has ONE weight-bearing group -- the nested template model -- with
+    # every array in Container order (all trainable, then all non-trainable).  Decided by structure and confirmed by
+    # shapes, so a wrong src_num_gpus cannot load arrays into the wrong tensors silently.
+    shapes = dict(weight_shapes(model.model_type))
+    shapes.update({k: v.shape for k, v in kapre_constants(model.model_type).items()})
+
+    def fits(order):
+        return all(tuple(a.shape) == tuple(shapes[n]) for a, n in zip(arrays, order))
+    nested = len(groups) == 1
+    order = model.container_weight_names() if nested else expected
+    if not fits(order):
+        other = expected if nested else model.container_weight_names()
+        if not fits(other):
+            raise ValueError("checkpoint %s: array shapes match neither the single-model layout nor the multi-GPU "
+                             "(nested template model) layout of %s" % (path, model.model_type))
+        order = other
+    by_name = dict(zip(order, arrays))
+    model.set_weights([by_name[n] for n in expected])

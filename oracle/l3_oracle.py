@@ -314,13 +314,37 @@ def _bn(x, w, prefix, training, cfg, stats):
     return (x - mean[None, :, None, None]) * (inv * g)[None, :, None, None] + b[None, :, None, None]
 
 
-def _conv(x, w, prefix, cfg=None):
+class _InputBnThroughputMode(torch.autograd.Function):
+    """Input BatchNormalization of the bf16 throughput mode, forward AND the device's backward arithmetic.
+    forward: y = bf16(scale*x + shift) -- the stored conv input.  backward: the device never materialises the data
+    gradient da of the first convolution (csrc/conv_simt.cu k_bn0_from_dw): with xin = the STORED bf16 input it forms
+        sum(da)      = sum_{tap,co} w * d1                     (exact, da is not rounded to bf16)
+        sum(da*xhat) = (sum_{tap,co} w * dW - beta*sum(da)) / gamma = sum(da * (xin - beta) / gamma)
+    i.e. the normalised input is re-derived from the bf16-rounded xin, not from the fp32 x."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, inv):
+        sh = (1, -1, 1, 1)
+        y = (x - mean.view(sh)) * (inv * gamma).view(sh) + beta.view(sh)
+        yq = y.to(torch.bfloat16).to(y.dtype)
+        ctx.save_for_backward(yq, gamma, beta)
+        return yq
+
+    @staticmethod
+    def backward(ctx, g):
+        yq, gamma, beta = ctx.saved_tensors
+        s1 = g.sum(dim=(0, 2, 3))
+        s2 = ((g * yq).sum(dim=(0, 2, 3)) - beta * s1) / gamma
+        return None, s2, s1, None, None
+
+
+def _conv(x, w, prefix, cfg=None, round_input_grad=True):
     k = w[prefix + "/kernel"].permute(3, 2, 0, 1)     # HWIO -> OIHW
     if cfg is not None and cfg.emulate_bf16:
         # device: bf16 conv input (gradient da stored as bf16), bf16 weight operands on every tcgen05 layer (the first
         # layer included unless first_layer_bf16_weights is off), fp32 accumulate, output z and its gradient dz
         # stored as bf16
-        x = _RoundGrad.apply(_q(x))
+        x = _RoundGrad.apply(_q(x)) if round_input_grad else _q(x)
         if k.shape[1] >= 64 or cfg.first_layer_bf16_weights:
             k = _q(k)
         return _RoundGrad.apply(_q(F.conv2d(x, k, w[prefix + "/bias"], padding=1)))
@@ -390,7 +414,7 @@ def _windows(t_nhwc, OH, OW):
             .reshape(B, OH, OW, 4, C))
 
 
-def tower_forward_frozen(x_nhwc, w, tower, model_type, cfg, routing, stats=None):
+def tower_forward_frozen(x_nhwc, w, tower, model_type, cfg, routing, stats=None, taps=None):
     """Training-mode tower forward whose DECISIONS (ReLU masks, max-pool routing) are not taken from its own values
     but from `routing`, recorded on the device: arithmetic differences of one bf16 ulp then stay one-ulp differences
     instead of re-routing whole gradient paths, so gradients become comparable tensor by tensor.
@@ -399,20 +423,38 @@ def tower_forward_frozen(x_nhwc, w, tower, model_type, cfg, routing, stats=None)
       routing["pos"][i]    int64 (B,OH,OW,C) pooled layer i: winning window position 0..3 (order of _windows)
       routing["sign"][i]   bool (B,OH,OW,C)  pooled layer i: window maximum > 0
       routing["argmax"]    int64 (B,512)     global max-pool: winning pixel (row-major) ; routing["gmask"] bool: > 0
-    Same layer sequence as tower_forward (audio_model.py:370-437, vision_model.py:124-190)."""
+    Same layer sequence as tower_forward (audio_model.py:370-437, vision_model.py:124-190).  With emulate_bf16 the input
+    BN follows the device's throughput-mode arithmetic (_InputBnThroughputMode).  `taps` (optional dict) receives the
+    conv outputs z ("<tower>/convNx") and BN outputs ("<tower>/bnNx") so that a caller can ask autograd for the
+    gradients AT those tensors (the terms the bias / beta / gamma gradients are sums of)."""
     if stats is None:
         stats = {}
     spec = (AUDIO_SPECS if tower == "audio" else VISION_SPECS)[model_type]
     x = x_nhwc.permute(0, 3, 1, 2).to(cfg.dtype)
+    device_bn0 = False
     if spec["input_bn"]:
-        x = _bn(x, w, f"{tower}/bn0", True, cfg, stats)
+        if cfg.emulate_bf16:
+            mean = x.mean(dim=(0, 2, 3))
+            inv = torch.rsqrt(x.var(dim=(0, 2, 3), unbiased=False) + cfg.bn_eps)
+            stats[f"{tower}/bn0"] = (mean.detach(), x.var(dim=(0, 2, 3), unbiased=False).detach(), x.numel() // x.shape[1])
+            x = _InputBnThroughputMode.apply(x, w[f"{tower}/bn0/gamma"], w[f"{tower}/bn0/beta"], mean, inv)
+            device_bn0 = True
+        else:
+            x = _bn(x, w, f"{tower}/bn0", True, cfg, stats)
+        if taps is not None:
+            taps[f"{tower}/bn0"] = x
     for i, nm in enumerate(CONV_NAMES):
-        z = _conv(x, w, f"{tower}/{nm}", cfg)
+        z = _conv(x, w, f"{tower}/{nm}", cfg, round_input_grad=not (i == 0 and device_bn0))
+        if taps is not None:
+            taps[f"{tower}/{nm}"] = z
         bnn = f"{tower}/bn{nm[4:]}"
         relu_first = tower == "vision" and nm == "conv1b"
         if relu_first:
             z = z * routing["relu"][i].permute(0, 3, 1, 2).contiguous().to(z.dtype)
-        y = _bn(z, w, bnn, True, cfg, stats).permute(0, 2, 3, 1)             # NHWC
+        yb = _bn(z, w, bnn, True, cfg, stats)
+        if taps is not None:
+            taps[bnn] = yb
+        y = yb.permute(0, 2, 3, 1)                                           # NHWC
         if nm == "conv4b":
             B, H, W, C = y.shape
             v = torch.gather(y.reshape(B, H * W, C), 1, routing["argmax"].unsqueeze(1)).squeeze(1)
@@ -428,16 +470,36 @@ def tower_forward_frozen(x_nhwc, w, tower, model_type, cfg, routing, stats=None)
     raise AssertionError("unreachable")
 
 
-def compute_grads_frozen(video_f, audio_f, label, w, model_type, cfg, routing):
-    """compute_grads with the device's routing decisions (routing = {"vision": ..., "audio": ...})."""
+def compute_grads_frozen(video_f, audio_f, label, w, model_type, cfg, routing, with_noise_scales=False):
+    """compute_grads with the device's routing decisions (routing = {"vision": ..., "audio": ...}).
+    with_noise_scales: also returns, for every bias / BN beta / BN gamma gradient, the per-channel root-sum-square of the
+    terms it is a sum of (sqrt(sum dz^2), sqrt(sum dy^2), sqrt(sum (dy*xhat)^2)): a sum of N bf16-stored terms cannot be
+    reproduced more closely than a fraction of one bf16 ulp of each term, added in quadrature."""
     st: dict = {}
-    v = tower_forward_frozen(video_f, w, "vision", model_type, cfg, routing["vision"], st)
-    a = tower_forward_frozen(frontend(audio_f, model_type, cfg), w, "audio", model_type, cfg, routing["audio"], st)
+    taps: dict = {}
+    v = tower_forward_frozen(video_f, w, "vision", model_type, cfg, routing["vision"], st, taps)
+    a = tower_forward_frozen(frontend(audio_f, model_type, cfg), w, "audio", model_type, cfg, routing["audio"], st, taps)
     logits = head_forward(v, a, w)
     loss, ce, acc = avc_loss(logits, label, w, cfg)
     names = [k for k, t in w.items() if t.requires_grad]
-    grads = torch.autograd.grad(loss, [w[k] for k in names])
-    return dict(zip(names, grads)), dict(loss=loss.detach(), ce=ce.detach(), acc=acc.detach(), logits=logits.detach())
+    tap_names = [k for k, t in taps.items() if t.requires_grad] if with_noise_scales else []
+    grads = torch.autograd.grad(loss, [w[k] for k in names] + [taps[k] for k in tap_names])
+    out = dict(loss=loss.detach(), ce=ce.detach(), acc=acc.detach(), logits=logits.detach())
+    gd = dict(zip(names, grads[:len(names)]))
+    if not with_noise_scales:
+        return gd, out
+    scales = {}
+    for k, g in zip(tap_names, grads[len(names):]):
+        g = g.detach()
+        rss = torch.sqrt((g * g).sum(dim=(0, 2, 3)))
+        if "/conv" in k:
+            scales[k + "/bias"] = rss
+        else:
+            y = taps[k].detach()
+            xhat = (y - w[k + "/beta"].detach().view(1, -1, 1, 1)) / w[k + "/gamma"].detach().view(1, -1, 1, 1)
+            scales[k + "/beta"] = rss
+            scales[k + "/gamma"] = torch.sqrt(((g * xhat) ** 2).sum(dim=(0, 2, 3)))
+    return gd, out, scales
 
 
 def head_forward(v, a, w):

@@ -126,9 +126,17 @@ def test_bf16_training_step_gradients_with_frozen_routing(model_type):
     bf16 gradients only agree in direction (cosine 0.89-0.96, round 1).  Here the bf16-emulating oracle REPLAYS the
     device's own decisions (ReLU masks from the stored activations, pool winners from the recorded routing bytes, the
     global max-pool's argmax), so both sides differentiate the same piecewise-linear function and differ only by
-    accumulation order and the 1-ulp bf16 rounding flips that follow from it.  Every gradient tensor of the step must
-    then agree to 2e-2 relative L2 (the near-zero ones -- biases of convolutions feeding a training-mode BN, whose
-    gradient is analytically 0 -- to 2e-2 of the largest gradient magnitude of their layer's kernel instead)."""
+    accumulation order and the 1-ulp bf16 rounding flips that follow from it.  Bars:
+      * every convolution / dense kernel gradient: <= 2e-2 relative L2;
+      * every bias / BN beta / BN gamma gradient (per-channel SUMS of bf16-stored terms): <= 2e-2 relative L2, or --
+        for the sums that cancel -- every channel within 8 * 2^-9 * sqrt(sum of squared terms), i.e. a few half-ulps
+        of the terms added in quadrature.  The cancelling ones are known analytically: the bias of a convolution
+        feeding a training-mode BN (exactly 0; the device does not even compute it), and beta / gamma of a BN whose
+        output enters the next convolution without a ReLU mask in between (the input BN; vision bn1b, the
+        Conv->ReLU->BN layer) -- their terms are data gradients of a batch-normalised signal and sum to border effects.
+        Calibration (CPU, the same emulation evaluated in fp32 and in fp64 arithmetic with identical routing): kernels
+        <= 1.1e-2, well-conditioned sums <= 1.2e-2, cancelling sums 3e-2 .. 0.9 relative but <= 3.8 * 2^-9 * rss.
+    The input BN is emulated with the device's throughput-mode arithmetic (oracle._InputBnThroughputMode)."""
     B = 4
     w_np = O.init_weights(model_type, seed=3, randomize_bn=True)
     video, audio, label = O.synthetic_batch(B, seed=515)
@@ -142,21 +150,28 @@ def test_bf16_training_step_gradients_with_frozen_routing(model_type):
     w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
     vf = torch.from_numpy(O.scale_video(video)).double()
     af = torch.from_numpy(O.pcm2float(audio, "float64"))
-    grads, out = O.compute_grads_frozen(vf, af, torch.from_numpy(label), w, model_type, cfg, routing)
+    grads, out, scales = O.compute_grads_frozen(vf, af, torch.from_numpy(label), w, model_type, cfg, routing,
+                                                with_noise_scales=True)
     rows, bad = [], []
     for name, g_ref in grads.items():
         g_ref = g_ref.numpy()
         if name.endswith("/kernel"):
             g_ref = g_ref - 2e-5 * w_np[name]
         err = rel_l2(got[name], g_ref)
-        max_abs = float(np.abs(got[name] - g_ref).max())
-        layer_kernel = name.rsplit("/", 1)[0] + "/kernel"
-        scale = float(np.abs(grads[layer_kernel].numpy()).max()) if layer_kernel in grads else float(np.abs(g_ref).max())
-        rows.append((name, round(err, 4), "%.2e" % max_abs))
-        if not (err <= 2e-2 or max_abs <= 2e-2 * scale):
-            bad.append((name, round(err, 4), max_abs, scale))
-    worst = sorted(rows, key=lambda r: -r[1])[:8]
-    print(model_type, "frozen-routing bf16 gradients: loss dev %.5f oracle %.5f; worst rel-L2:" % (loss_dev, float(out["loss"])), worst)
+        ok = err <= 2e-2
+        ratio = None
+        if not ok and name in scales:
+            ratio = float((np.abs(got[name] - g_ref) / (2.0 ** -9 * scales[name].numpy() + 1e-30)).max())
+            ok = ratio <= 8.0
+        rows.append((name, round(err, 4), None if ratio is None else round(ratio, 2)))
+        if not ok:
+            bad.append(rows[-1])
+    kern = [r for r in rows if r[0].endswith("/kernel")]
+    sums = [r for r in rows if not r[0].endswith("/kernel")]
+    print(model_type, "frozen-routing bf16 gradients: loss dev %.5f oracle %.5f; kernels worst rel-L2 %s; sums passing "
+          "on rel-L2: %d of %d, the others (name, rel-L2, max |err| / (2^-9 rss)): %s"
+          % (loss_dev, float(out["loss"]), sorted(kern, key=lambda r: -r[1])[:3], sum(r[2] is None for r in sums), len(sums),
+             [r for r in sums if r[2] is not None and not r[0].endswith("/bias")]))
     assert abs(loss_dev - float(out["loss"])) <= 2e-2 * max(1.0, abs(float(out["loss"])))
     assert not bad, bad
 

@@ -176,7 +176,8 @@ def test_data_generator_and_restart_info(tmp_path):
     d = str(tmp_path / "subset_train")
     _write_batches(d)
     g = T.data_generator(d, batch_size=4, random_state=1)
-    b0, b1, b2 = next(g), next(g), next(g)
+    cp = lambda b: {k: v.copy() for k, v in b.items()}     # ring slots are recycled after two further batches
+    b0, b1, b2 = cp(next(g)), cp(next(g)), cp(next(g))
     assert b0["video"].shape == (4, 224, 224, 3) and b0["video"].dtype == np.uint8 and b0["audio"].dtype == np.int16
     assert b1["label"].shape == (4, 2) and b1["label"].dtype == np.float32
     g2 = T.data_generator(d, batch_size=4, random_state=1, start_batch_idx=1)
@@ -188,7 +189,7 @@ def test_data_generator_and_restart_info(tmp_path):
     x, y = next(T.keras_tuples(T.data_generator(d, batch_size=2), ["video", "audio"], "label"))
     assert len(x) == 2 and x[0].shape == (2, 224, 224, 3) and y.shape == (2, 2)
     ev = T.single_epoch_data_generator(d, 2, batch_size=4, random_state=1)
-    e = [next(ev) for _ in range(4)]
+    e = [cp(next(ev)) for _ in range(4)]
     assert np.array_equal(e[0]["audio"], e[2]["audio"]) and np.array_equal(e[1]["audio"], e[3]["audio"])
     p = tmp_path / "history_csvlog.csv"
     p.write_text("epoch,acc,loss,val_acc,val_loss\n0,0.5,0.9,0.55,0.8\n1,0.6,0.7,0.65,0.6\n")
@@ -283,3 +284,138 @@ def test_data_parallel_glue_over_gloo():
     assert res[0][1] == slice(0, 5) and res[1][1] == slice(5, 10)
     assert all(r[2] == 3.0 and r[3] == 3.0 for r in res)          # 1 + 2 summed over ranks
     assert all(r[4] == (1.0, 2.0) for r in res)
+
+
+def test_batch_plan_reproduces_the_reference_sequence(tmp_path):
+    """pipeline.BatchPlan against a literal simulation of train.py:134-195 (cycle_shuffle over the listing, one global
+    `random` seeded once, samples cut into consecutive runs of batch_size across file and pass boundaries), including
+    the resume seek; and the prefetching reader against the thread-less path."""
+    import random
+    from l3embedding_b200 import pipeline as P
+    d = str(tmp_path / "subset_train")
+    os.makedirs(d)
+    sizes = {"b0.npz": 5, "b1.npz": 3, "b2.npz": 7, "b3.npz": 2}
+    rng = np.random.default_rng(0)
+    for name, n in sizes.items():
+        np.savez(os.path.join(d, name), video=rng.integers(0, 256, (n, 224, 224, 3), dtype=np.uint8),
+                 audio=rng.integers(-9, 9, (n, 1, 48000)).astype(np.int16),
+                 label=np.eye(2, dtype=np.float32)[rng.integers(0, 2, n)])
+
+    def reference_stream(batch_size, seed, n_batches):
+        random.seed(seed)                                   # train.py:144
+        lst = sorted(sizes)
+        out, cur = [], []
+        need = batch_size
+        while len(out) < n_batches:
+            for f in list(lst):                             # cycle_shuffle: one pass, then shuffle in place
+                pos = 0
+                while pos < sizes[f]:
+                    take = min(need, sizes[f] - pos)
+                    cur.append((f, pos, pos + take))
+                    pos += take
+                    need -= take
+                    if need == 0:
+                        out.append(cur)
+                        cur, need = [], batch_size
+            random.shuffle(lst)
+        return out[:n_batches]
+    for bs, seed in ((4, 1), (6, 20180123), (17, 3)):
+        plan = P.BatchPlan(d, bs, random_state=seed)
+        want = reference_stream(bs, seed, 12)
+        got = [[(os.path.basename(p), s, e) for p, s, e in segs] for segs, _ in zip(plan.segments(0), range(12))]
+        assert got == want
+        seek = [[(os.path.basename(p), s, e) for p, s, e in segs] for segs, _ in zip(plan.segments(7), range(3))]
+        assert seek == want[7:10]
+    plan = P.BatchPlan(d, 4, random_state=1)
+    reader = P.PinnedBatchReader(plan, start_batch=2, max_batches=7, pinned=False)
+    ref = P.read_batches(plan, start_batch=2)
+    n, held = 0, []
+    for b in reader:
+        r = next(ref)
+        assert all(np.array_equal(b[k], r[k]) and b[k].dtype == r[k].dtype for k in P.KEYS)
+        held = (held + [(b, r)])[-2:]          # the batch just taken and the one before it are still intact
+        assert all(np.array_equal(hb["video"], hr["video"]) for hb, hr in held)
+        n += 1
+    assert n == 7
+    reader.close()
+
+
+def test_engine_is_created_once_across_train_validate_train(monkeypatch):
+    """validation with a bigger batch (or any predict) between steps must not rebuild the engine and thereby
+    reset Adam's moments / step count; a genuinely larger training batch rebuilds ONCE and adopts the state."""
+    from l3embedding_b200 import model as M, engine as E
+
+    created = []
+
+    class StubEngine:
+        def __init__(self, model_type, max_batch, dtype="f32", training=True, weights=None, **_):
+            self.model_type, self.max_batch, self.dtype, self.training = model_type, max_batch, dtype, training
+            self.adam_t, self.adopted, self.closed, self.staged = 0, None, False, []
+            created.append(self)
+
+        def adopt_state(self, other):
+            self.adopted, self.adam_t = other, other.adam_t
+
+        def close(self):
+            self.closed = True
+
+        def upload_host(self, v, a, l):
+            self.staged.append(len(v))
+            return len(v)
+
+        def train_step_staged(self, n, lr):
+            assert self.staged.pop(0) == n
+            self.adam_t += 1
+            return dict(loss=1.0, acc=0.5)
+
+        def predict(self, v, a, y=None):
+            assert len(v) <= self.max_batch
+            return np.zeros((len(v), 2), np.float32), np.zeros((len(v), 2), np.float32)
+
+        def metrics(self):
+            return dict(ce_sum=1.0, correct=1.0, l2=0.0)
+
+        def get_weights(self):
+            return {}
+    monkeypatch.setattr(E, "Engine", StubEngine)
+    m, _, _ = M.MODELS["cnn_L3_orig"]()
+    m.compile(M.Adam(lr=1e-4))
+    x = lambda n: [np.zeros((n, 224, 224, 3), np.uint8), np.zeros((n, 1, 48000), np.int16)]
+    y = lambda n: np.tile(np.array([[1, 0]], np.float32), (n, 1))
+    for _ in range(2):
+        m.train_on_batch(x(32), y(32))
+        m.test_on_batch(x(64), y(64))           # validation batch twice the training batch: chunked, not rebuilt
+        m.predict(x(8))
+    assert len(created) == 1 and created[0].training and created[0].adam_t == 2
+    m.train_on_batch(x(48), y(48))              # a larger TRAINING batch: one rebuild that adopts the optimizer state
+    assert len(created) == 2 and created[1].adopted is created[0] and created[0].closed
+    assert created[1].training and created[1].max_batch == 48 and created[1].adam_t == 3
+
+
+def test_multi_gpu_checkpoint_layout_round_trip(tmp_path):
+    """model.py:76-77,117-119: a checkpoint saved from a multi_gpu_model keeps the whole template model as ONE nested
+    layer with its arrays in Container order (all trainable, then all non-trainable) -- a different array order than
+    the single-model file.  Both layouts load into the right tensors whatever src_num_gpus says; a file of another
+    model type is refused."""
+    from l3embedding_b200 import model as M, minihdf5
+    m, _, _ = M.MODELS["cnn_L3_kapredbinputbn"]()
+    rng = np.random.default_rng(1)
+    w = {k: (v + 0.01 * rng.standard_normal(v.shape)).astype(np.float32) for k, v in m.named_weights().items()}
+    m.set_named_weights(w)
+    single, multi = str(tmp_path / "single.h5"), str(tmp_path / "multi.h5")
+    m.save_weights(single)
+    M.multi_gpu_model(m, gpus=4).save_weights(multi)
+    f = minihdf5.File(multi)
+    names = [n.decode() for n in f.attrs["layer_names"]]
+    assert names == ["input_1", "input_2"] + ["lambda_%d" % i for i in range(1, 9)] + ["cnn_L3_kapredbinputbn", "dense_2"]
+    wn = [n.decode() for n in f["cnn_L3_kapredbinputbn"].attrs["weight_names"]]
+    assert len(wn) == len(m.weight_names())
+    first_nt = next(i for i, n in enumerate(wn) if "moving" in n or "kapre" in n)
+    assert all(("moving" in n or "kapre" in n) for n in wn[first_nt:])          # trainable block, then non-trainable
+    assert m.container_weight_names() != m.weight_names()
+    for path in (single, multi):
+        for src in (0, 4):
+            got = M.load_model(path, "cnn_L3_kapredbinputbn", src_num_gpus=src, tgt_num_gpus=1).named_weights()
+            assert all(np.array_equal(got[k], w[k]) for k in w), (path, src)
+    with pytest.raises(ValueError):
+        M.load_model(multi, "cnn_L3_orig", src_num_gpus=4)
