@@ -9,10 +9,15 @@
 A "step" is one keras `train_on_batch` of `cnn_L3_melspec2` (BASELINE.json configs[1]): forward, backward, gradient
 all-reduce (N>1) and the Adam update on a batch of synthetic AVC pairs (224x224x3 uint8 frame + 1 s 48 kHz int16
 audio), bf16 activations / tcgen05 convolutions with fp32 accumulation, per-GPU batch 64 (weak scaling).
-`value` is timed with the inputs resident in HBM; `e2e` goes through the host-buffer call
-(`Engine.train_step_host` -> `l3_train_step_host`) with the H2D copies and the metric read-back inside the
-timed region.  The reference's own Keras/TF path cannot run, so `--impl reference` and `cpu_baseline`
-time the PyTorch-CPU restatement in oracle/ ("port") on the box's host cores.
+`value` is timed with the inputs resident in HBM; `e2e` goes through the host-buffer calls a user's fit loop makes
+(`Engine.upload_host` -> `l3_upload_batch_host` from pinned buffers, then `l3_train_step_staged` /
+`l3_dp_train_step_staged`) with the H2D copies and the metric read-back inside the timed region; the upload of
+batch k+1 is enqueued on the library's copy stream before step k is run, as `L3Model.fit_generator` does.
+At N > 1 the gradient exchange is the library's own (l3_dp_*: NCCL all-reduce in buckets overlapped with backward).
+The reference's own Keras/TF path cannot run, so `--impl reference` and `cpu_baseline` time the
+PyTorch-CPU restatement in oracle/ ("port") on the box's host cores, at the same per-GPU batch.
+Extra records under `configs`: BASELINE configs[2] (audio-embedding inference, 10k clips) at N=1, configs[3]
+(cnn_L3_kapredbinputbn, 4x64) when --gpus 4, configs[4] (cnn_L3_melspec2, 8x128) when --gpus 8.
 """
 import argparse
 import json
@@ -50,14 +55,18 @@ def conv_class_gflop_per_pair():
 
 
 # DRAM bytes (read + write) per training step at B=64 and the time-weighted tensor-pipe activity, summed over the
-# launches of each convolution class, from ONE `ncu --clock-control none` capture of a whole step
-# (profiles/r1_ncu_full_conv_step.txt, reduced to profiles/r1_ncu_conv_classes.json by tools/ncu_conv_step.py)
+# launches of each convolution class, from ONE `ncu --clock-control none` capture of a whole step, reduced by
+# tools/ncu_conv_step.py.  STATIC: read from the committed profile, not measured in the run that prints the line.
+NCU_CLASSES_FILES = ["profiles/r2_ncu_conv_classes.json", "profiles/r1_ncu_conv_classes.json"]
+
+
 def ncu_conv_classes():
-    p = os.path.join(ROOT, "profiles", "r1_ncu_conv_classes.json")
-    try:
-        return json.load(open(p))
-    except Exception:
-        return {}
+    for rel in NCU_CLASSES_FILES:
+        try:
+            return json.load(open(os.path.join(ROOT, rel))), rel
+        except Exception:
+            continue
+    return {}, None
 
 
 class ClockSampler(threading.Thread):
@@ -128,8 +137,19 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def run_cpu_port(batch, steps, warmup, threads=None):
-    """Times oracle.train_step (PyTorch CPU fp32 restatement of the reference graph) -> pairs/s."""
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return None
+
+
+def run_cpu_port(batch, steps, warmup, threads=None, budget_s=None):
+    """Times oracle.train_step (PyTorch CPU fp32 restatement of the reference graph) -> pairs/s.  With budget_s the
+    number of steps (never the batch) is cut so that the whole run stays inside the budget; returns what was run."""
     import torch
     from oracle import l3_oracle as O
     threads = threads or os.cpu_count() or 1
@@ -137,55 +157,78 @@ def run_cpu_port(batch, steps, warmup, threads=None):
     w = O.to_torch(O.init_weights(MODEL_TYPE, seed=20180123), requires_grad=True)
     st = O.AdamState()
     video, audio, label = O.synthetic_batch(batch, seed=1)
-    for _ in range(warmup):
+    t0 = time.perf_counter()
+    done_warm = 0
+    for _ in range(max(warmup, 1)):
         O.train_step(video, audio, label, w, st, MODEL_TYPE, 1e-5)
+        done_warm += 1
+        if budget_s is not None and (time.perf_counter() - t0) * (done_warm + 1) / done_warm > 0.3 * budget_s:
+            break
+    per = (time.perf_counter() - t0) / done_warm
+    if budget_s is not None:
+        steps = max(1, min(steps, int((budget_s - (time.perf_counter() - t0)) / max(per, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         O.train_step(video, audio, label, w, st, MODEL_TYPE, 1e-5)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, threads
+    return batch * steps / dt, dt / steps, threads, steps, done_warm
 
 
-def embedding_delta_vs_port():
-    """The second half of BASELINE.json's metric ("embedding max|delta| vs the reference"): the fp32 parity mode's audio
-    embedding and AVC logits on two synthetic pairs against the fp64 CPU restatement (the reference's Keras path cannot
-    run).  Part of the cpu_baseline leg: the only place bench.py touches oracle/."""
+def parity_vs_port():
+    """The second half of BASELINE.json's metric ("embedding max|delta| vs the reference"): audio embedding (6144-d) and
+    AVC logits on two synthetic pairs against the fp64 CPU restatement (the reference's Keras path cannot run) -- for the
+    fp32 parity mode (north_star's 1e-3 bar) AND for the bf16 throughput mode that the line's throughput is measured in.
+    Part of the cpu_baseline leg: the only place bench.py touches oracle/."""
     import numpy as np
     import torch
     from l3embedding_b200.engine import Engine
     from oracle import l3_oracle as O
     w_np = O.init_weights(MODEL_TYPE, seed=20180123, randomize_bn=True)
     video, audio, _ = O.synthetic_batch(2, seed=42)
-    eng = Engine(MODEL_TYPE, 2, "f32", training=True, weights=w_np)   # the configuration smoke() validates
-    try:
-        cfg = O.OracleConfig(dtype=torch.float64)
-        w = O.to_torch(w_np, dtype=torch.float64)
-        af = torch.from_numpy(O.pcm2float(audio, "float64"))
-        vf = torch.from_numpy(O.scale_video(video)).double()
-        emb = eng.embed_audio(audio, "original").cpu().numpy()
-        ref = O.audio_embedding(af, w, MODEL_TYPE, "original", cfg).numpy()
-        _, logits = eng.predict(video, audio)
-        ref_logits = O.avc_forward(vf, af, w, MODEL_TYPE, False, cfg).numpy()
-        return {"embedding_max_abs_delta": float(np.abs(emb - ref).max()), "embedding_abs_max": float(np.abs(ref).max()),
-                "logits_max_abs_delta": float(np.abs(logits - ref_logits).max()),
-                "mode": "f32 parity mode vs the fp64 CPU restatement, 2 synthetic pairs, 6144-d audio embedding"}
-    finally:
-        eng.close()
+    cfg = O.OracleConfig(dtype=torch.float64)
+    w = O.to_torch(w_np, dtype=torch.float64)
+    af = torch.from_numpy(O.pcm2float(audio, "float64"))
+    vf = torch.from_numpy(O.scale_video(video)).double()
+    ref = O.audio_embedding(af, w, MODEL_TYPE, "original", cfg).numpy()
+    ref_logits = O.avc_forward(vf, af, w, MODEL_TYPE, False, cfg).numpy()
+    out = {"reference": "fp64 CPU restatement (oracle/), 2 synthetic pairs, 6144-d audio embedding",
+           "embedding_abs_max": float(np.abs(ref).max())}
+    for mode in ("f32", "bf16"):
+        eng = Engine(MODEL_TYPE, 2, mode, training=True, weights=w_np)
+        try:
+            emb = eng.embed_audio(audio, "original").cpu().numpy()
+            _, logits = eng.predict(video, audio)
+            out[mode] = {"embedding_max_abs_delta": float(np.abs(emb - ref).max()),
+                         "logits_max_abs_delta": float(np.abs(logits - ref_logits).max())}
+        finally:
+            eng.close()
+    out["note"] = "f32 = parity mode (bar 1e-3); bf16 = the throughput mode this line's value / e2e are measured in"
+    return out
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 4
-    value, sec, threads = run_cpu_port(batch, args.steps, args.warmup)
-    sample = "%d pairs per step x %d steps (bounded sample of the batch-%d workload)" % (batch, args.steps, PER_GPU_BATCH)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    batch = args.batch
+    avail = _mem_available_gb()
+    note = ""
+    if avail is not None and avail < 0.45 * batch + 8:          # ~0.33 GB of autograd state per pair (measured)
+        batch = max(4, int((avail - 8) / 0.45))
+        note = " (host memory %.0f GB: batch cut from %d)" % (avail, args.batch)
+    value, sec, threads, steps, warm = run_cpu_port(batch, args.steps, args.warmup, budget_s=240.0)
+    sample = "%d-pair batch (the per-GPU batch of the GPU arm)%s, %d warm-up + %d timed train_step, %.1f s/step" % (
+        batch, note, warm, steps, sec)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cnn_L3_melspec2 train_on_batch (fwd+bwd+Adam), synthetic AVC pairs",
-                       "per_gpu_batch": PER_GPU_BATCH, "note": "PyTorch-CPU restatement of the Keras/TF graph (the "
-                       "reference itself needs keras 2.0.9 / TF 1.4 / kapre, not installable here)"},
+            "config": {"workload": "cnn_L3_melspec2 train_on_batch (fwd+bwd+Adam), synthetic AVC pairs "
+                                   "(224x224x3 u8 frame + 48000-sample i16 audio)",
+                       "per_gpu_batch": batch, "global_batch": batch, "parallelism": "cpu",
+                       "requested_steps": args.steps, "requested_warmup": args.warmup,
+                       "note": "PyTorch-CPU restatement of the Keras/TF graph (the reference itself needs keras 2.0.9 / "
+                               "TF 1.4 / kapre, not installable here); one process on all host cores; steps cut (never "
+                               "the batch) to keep the run inside 4 minutes"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -193,13 +236,155 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def main_gpu(args):
-    import numpy as np
+class TrainBench:
+    """One training configuration (model type, per-GPU batch) on this rank: resident and end-to-end timings."""
+
+    def __init__(self, model_type, B, dtype, world, rank, dev, par, pool_n, lr=1e-5):
+        import torch
+        from l3embedding_b200 import _lib
+        from l3embedding_b200.engine import Engine
+        from l3embedding_b200.synthetic import synthetic_batch
+        self.torch, self.lib = torch, _lib.load()
+        self.B, self.G, self.world, self.rank, self.dev, self.lr, self.pool_n = B, B * world, world, rank, dev, lr, pool_n
+        self.eng = Engine(model_type, B, dtype, training=True, device=dev, seed=20180123)
+        par.attach(self.eng)          # N > 1: joins the library's NCCL communicator (collective)
+        # a pool of distinct synthetic batches, resident in HBM and pinned on the host for the e2e arm
+        self.pool_dev, self.pool_host = [], []
+        for i in range(pool_n):
+            v, a, l = synthetic_batch(B, seed=20180123 + 1000 * rank + i)
+            hv, ha, hl = (torch.from_numpy(x).pin_memory() for x in (v, a, l))
+            self.pool_host.append((hv.numpy(), ha.numpy(), hl.numpy(), (hv, ha, hl)))
+            self.pool_dev.append((hv.to(dev), ha.to(dev), hl.to(dev)))
+        torch.cuda.synchronize()
+
+    def step_resident(self, i):
+        v, a, l = self.pool_dev[i % self.pool_n]
+        self.eng.forward_backward(v, a, l, global_batch=self.G)     # N > 1: gradient buckets leave during backward
+        self.eng.adam_step(self.lr)                                 # waits for them
+
+    def _upload(self, i):
+        hv, ha, hl, _ = self.pool_host[i % self.pool_n]
+        self.eng.upload_host(hv, ha, hl)
+
+    def step_e2e(self, i):
+        # the fit loop's software pipeline: batch i was uploaded during step i-1; enqueue batch i+1, run step i
+        self._upload(i + 1)
+        if self.world == 1:
+            return self.eng.train_step_staged(self.B, self.lr)
+        return self.eng.dp_train_step_staged(self.B, self.G, self.lr)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, profile=False, local=0, prime=None):
+        torch = self.torch
+        if prime is not None:
+            prime(0)
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        if profile:
+            self.eng.profile(True)
+        l0 = self.lib.l3_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        self.barrier()
+        clocks = sampler.finish()
+        ms = e0.elapsed_time(e1)
+        prof = self.eng.profile_read() if profile else None
+        if profile:
+            self.eng.profile(False)
+        launches = self.lib.l3_launch_count() - l0
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks, prof, launches
+
+    def drain_staged(self):
+        """the e2e loop leaves one uploaded batch pending: consume it so the next phase starts clean"""
+        if self.world == 1:
+            self.eng.train_step_staged(self.B, self.lr)
+        else:
+            self.eng.dp_train_step_staged(self.B, self.G, self.lr)
+
+    def run(self, steps, warmup, local, with_profile):
+        ms, clocks, _, launches = self.timed(self.step_resident, steps, warmup, local=local)
+        out = {"value": self.G * steps / (ms / 1e3), "ms_per_step": ms / steps, "clocks": clocks, "launches": int(launches)}
+        if with_profile:
+            # per-kernel-class durations: a separate pass with the two towers serialised on one stream (in the timed
+            # runs they overlap on two streams, which makes per-class CUDA-event intervals overlap too)
+            self.eng.set_two_streams(False)
+            ps = max(3, min(steps, 10))
+            ms_serial, _, prof, _ = self.timed(self.step_resident, ps, 2, profile=True, local=local)
+            self.eng.set_two_streams(True)
+            out.update(prof=prof, prof_steps=ps, ms_serial=ms_serial)
+        es = max(3, min(steps, 10))
+        ms2, _, _, _ = self.timed(self.step_e2e, es, 2, local=local, prime=self._upload)
+        self.drain_staged()
+        out.update(e2e_value=self.G * es / (ms2 / 1e3), e2e_ms=ms2 / es, e2e_steps=es)
+        return out
+
+    def close(self):
+        self.eng.close()
+
+
+def embedding_inference_record(dev):
+    """BASELINE configs[2]: audio-tower embedding inference (the 05_generate_embedding_samples.py path), 10 000 x 1 s
+    clips on one B200: clips/s with the clips resident in HBM and host -> host (pinned int16 in, pinned float32 out)."""
     import torch
-    import torch.distributed as dist
-    from l3embedding_b200 import _lib, dp
     from l3embedding_b200.engine import Engine
     from l3embedding_b200.synthetic import synthetic_batch
+    N, BATCH = 10000, 500
+    _, audio, _ = synthetic_batch(BATCH, seed=7)
+    host = torch.from_numpy(audio).pin_memory()
+    rec = {"workload": "cnn_L3_melspec2 audio embedding, %d clips of 1 s / 48 kHz int16, batch %d" % (N, BATCH)}
+    for dtype, n_iter in (("bf16", N // BATCH), ("f32", 2)):
+        eng = Engine(MODEL_TYPE, BATCH, dtype, training=False, towers=("audio",), host_staging=False, device=dev)
+        try:
+            d = host.to(dev)
+            for pooling, dim in (("original", 6144), ("short", 512)):
+                res = torch.empty(BATCH, dim, device=dev)
+                for _ in range(2):
+                    eng.embed_audio(d, pooling, out=res)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n_iter):
+                    eng.embed_audio(d, pooling, out=res)
+                e1.record()
+                torch.cuda.synchronize()
+                r = {"clips_per_s_resident": n_iter * BATCH / (e0.elapsed_time(e1) / 1e3), "clips": n_iter * BATCH,
+                     "conv_tflops": n_iter * BATCH / (e0.elapsed_time(e1) / 1e3) * 20.405 / 1e3}
+                if dtype == "bf16":
+                    hres = torch.empty(BATCH, dim).pin_memory()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(n_iter):
+                        dd = host.to(dev, non_blocking=True)
+                        eng.embed_audio(dd, pooling, out=res)
+                        hres.copy_(res, non_blocking=True)
+                    torch.cuda.synchronize()
+                    r["clips_per_s_host_to_host"] = n_iter * BATCH / (time.perf_counter() - t0)
+                rec["%s_%s" % (dtype, pooling)] = r
+        finally:
+            eng.close()
+    return rec
+
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from l3embedding_b200 import dp
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,149 +399,113 @@ def main_gpu(args):
         sys.stdout.flush()
         saved_fd = os.dup(1)
         os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
+    try:
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)     # bootstrap + the timing barrier / max only
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()
-        finally:
+        par = dp.LibraryReplicas() if world > 1 else dp.SingleReplica()
+        B = args.batch
+        tb = TrainBench(MODEL_TYPE, B, args.dtype, world, rank, dev, par, args.pool)
+    finally:
+        if world > 1:
+            sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    par = dp.TorchDistReplicas() if world > 1 else dp.SingleReplica()
-    B = args.batch
     G = B * world
-    lr = 1e-5   # jobs/l3embedding-train-melspec2-09192018.sbatch
-    eng = Engine(MODEL_TYPE, B, args.dtype, training=True, device=dev, seed=20180123)
-    lib = _lib.load()
+    r = tb.run(args.steps, args.warmup, local, with_profile=True)
+    uses_tc = bool(tb.eng.uses_tensor_cores)
+    tb.close()
 
-    # a pool of distinct synthetic batches, resident in HBM (and pinned on the host for the e2e arm)
-    pool_n = args.pool
-    pool_dev, pool_host = [], []
-    for i in range(pool_n):
-        v, a, l = synthetic_batch(B, seed=20180123 + 1000 * rank + i)
-        hv, ha, hl = (torch.from_numpy(x).pin_memory() for x in (v, a, l))
-        pool_host.append((hv, ha, hl))
-        pool_dev.append((hv.to(dev), ha.to(dev), hl.to(dev)))
-    torch.cuda.synchronize()
-
-    def step_resident(i):
-        v, a, l = pool_dev[i % pool_n]
-        eng.forward_backward(v, a, l, global_batch=G)
-        par.allreduce_grads(eng)
-        eng.adam_step(lr)
-
-    def step_e2e(i):
-        hv, ha, hl = pool_host[i % pool_n]
-        if world == 1:
-            return eng.train_step_host(hv.numpy(), ha.numpy(), hl.numpy(), lr)
-        # N>1: H2D upload, forward/backward, NCCL all-reduce, Adam, metric read-back
-        v, a, l = hv.to(dev, non_blocking=True), ha.to(dev, non_blocking=True), hl.to(dev, non_blocking=True)
-        eng.forward_backward(v, a, l, global_batch=G)
-        par.allreduce_grads(eng)
-        m = eng.metrics()
-        eng.adam_step(lr)
-        return m
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, profile=False):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        if profile:
-            eng.profile(True)
-        l0 = lib.l3_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local)
-        sampler.start()
-        e0.record()
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record()
-        barrier()
-        clocks = sampler.finish()
-        ms = e0.elapsed_time(e1)
-        prof = eng.profile_read() if profile else None
-        if profile:
-            eng.profile(False)
-        launches = lib.l3_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, clocks, prof, launches
-
-    ms, clocks, _, launches = timed(step_resident, args.steps, args.warmup)
-    value = G * args.steps / (ms / 1e3)
-    # per-kernel-class durations: a separate pass with the two towers serialised on one stream (in the timed runs
-    # they overlap on two streams, which makes per-class CUDA-event intervals overlap too)
-    eng.set_two_streams(False)
-    prof_steps = max(3, min(args.steps, 10))
-    ms_serial, _, prof, _ = timed(step_resident, prof_steps, 2, profile=True)
-    eng.set_two_streams(True)
-    e2e_steps = max(3, min(args.steps, 10))
-    ms2, _, _, _ = timed(step_e2e, e2e_steps, 2)
-    e2e_value = G * e2e_steps / (ms2 / 1e3)
+    # the other BASELINE configurations this launch can cover
+    configs = {}
+    if world == 4 or args.all_configs:
+        t4 = TrainBench("cnn_L3_kapredbinputbn", 64, args.dtype, world, rank, dev, par, args.pool)
+        r4 = t4.run(max(5, args.steps // 2), 3, local, with_profile=False)
+        t4.close()
+        configs["config4_kapredbinputbn_dp%d_x64" % world] = {
+            "pairs_per_s": r4["value"], "ms_per_step": r4["ms_per_step"], "e2e_pairs_per_s": r4["e2e_value"],
+            "global_batch": 64 * world, "whole_step_frac": r4["value"] * 122.54 / 1e3 / world / measured_peaks()[0]}
+    if world == 8 or args.all_configs:
+        t5 = TrainBench(MODEL_TYPE, 128, args.dtype, world, rank, dev, par, max(2, args.pool // 2))
+        r5 = t5.run(max(5, args.steps // 2), 3, local, with_profile=False)
+        t5.close()
+        configs["config5_melspec2_dp%d_x128" % world] = {
+            "pairs_per_s": r5["value"], "ms_per_step": r5["ms_per_step"], "e2e_pairs_per_s": r5["e2e_value"],
+            "global_batch": 128 * world, "whole_step_frac": r5["value"] * TRAIN_GFLOP / 1e3 / world / measured_peaks()[0]}
+    if world == 1 and rank == 0 and not args.no_configs:
+        try:
+            configs["config3_embedding_inference"] = embedding_inference_record(dev)
+        except Exception as e:   # a reporting extra must never cost the bench line
+            configs["config3_embedding_inference"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
         gf = conv_class_gflop_per_pair()
+        prof, prof_steps, ms_serial = r["prof"], r["prof_steps"], r["ms_serial"]
         kernels = {}
         for k, (kms, n) in prof.items():
-            if k in gf and kms > 0:
-                kernels[k] = {"ms_per_step": kms / prof_steps, "launches_per_step": n / prof_steps,
-                              "tflops": gf[k] * B * prof_steps / kms, "frac_of_serial_step": kms / ms_serial}
-            elif kms > 0:
-                kernels[k] = {"ms_per_step": kms / prof_steps, "launches_per_step": n / prof_steps,
-                              "frac_of_serial_step": kms / ms_serial}
+            if kms <= 0:
+                continue
+            kernels[k] = {"ms_per_step": kms / prof_steps, "launches_per_step": n / prof_steps,
+                          "frac_of_serial_step": kms / ms_serial}
+            if k in gf:
+                kernels[k]["tflops"] = gf[k] * B * prof_steps / kms
         dom = max((k for k in kernels if k in gf), key=lambda k: kernels[k]["ms_per_step"])
-        ncu = ncu_conv_classes()
+        ncu, ncu_src = ncu_conv_classes()
         achieved = kernels[dom]["tflops"]
+        static_ok = B == 64 and args.dtype == "bf16" and ncu_src is not None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "cnn_L3_melspec2 train_on_batch (fwd+bwd+Adam), synthetic AVC pairs "
                                    "(224x224x3 u8 frame + 48000-sample i16 audio)",
                        "per_gpu_batch": B, "global_batch": G, "parallelism": "dp%d" % world,
-                       "tensor_cores": bool(eng.uses_tensor_cores), "tower_streams": 2,
+                       "tensor_cores": uses_tc, "tower_streams": 2,
+                       "gradient_exchange": ("none" if world == 1 else "libl3b200 l3_dp_*: NCCL all-reduce in buckets on a "
+                                             "communication stream, overlapped with backward"),
                        "l2": "inputs rotate over a %d-batch pool; each step streams >5 GB of activations through the "
-                             "126 MB L2, so no step sees a warm L2" % pool_n},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (224 * 224 * 3 + 48000 * 2 + 8),
-                    "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": ms2 / e2e_steps,
-                    "api": ("Engine.train_step_host -> l3_train_step_host (pinned host buffers)" if world == 1 else
-                            "pinned host batch -> H2D -> Engine.forward_backward -> NCCL all-reduce -> metrics D2H -> adam")},
-            "gpu_launches": int(launches),
+                             "126 MB L2, so no step sees a warm L2" % args.pool},
+            "clocks": r["clocks"],
+            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * (224 * 224 * 3 + 48000 * 2 + 8),
+                    "d2h_bytes_per_step": 16, "steps": r["e2e_steps"], "ms_per_step": r["e2e_ms"],
+                    "api": ("Engine.upload_host (pinned u8/i16 -> l3_upload_batch_host, copy stream) of batch k+1, then "
+                            + ("l3_train_step_staged" if world == 1 else "l3_dp_train_step_staged")
+                            + " of batch k (metrics read back every step)")},
+            "gpu_launches": r["launches"],
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         "traffic": (ncu.get(dom, {}).get("dram_bytes") if (B == 64 and args.dtype == "bf16") else None),
-                         "traffic_unit": "DRAM bytes per step for the class (ncu, profiles/r1_ncu_full_conv_step.txt)",
-                         "tensor_pipe_active_pct_ncu": {k: round(v["tensor_pipe_active_pct_time_weighted"], 1)
-                                                        for k, v in ncu.items()},
+                         "traffic": (ncu.get(dom, {}).get("dram_bytes") if static_ok else None),
+                         "traffic_unit": "DRAM bytes per step for the class",
+                         "traffic_source": ("static: %s (one ncu capture of a B=64 step, not this run)" % ncu_src) if static_ok else None,
+                         "tensor_pipe_active_pct_ncu": ({"source": "static: %s (not measured in this run)" % ncu_src,
+                                                         **{k: round(v["tensor_pipe_active_pct_time_weighted"], 1)
+                                                            for k, v in ncu.items()}} if ncu_src else None),
                          "peak_source": peak_src,
-                         "whole_step_frac": value * TRAIN_GFLOP / 1e3 / world / peak_tf,
+                         "whole_step_frac": r["value"] * TRAIN_GFLOP / 1e3 / world / peak_tf,
                          "serial_ms_per_step": ms_serial / prof_steps,
-                         "note": "kernel classes timed with CUDA events on the library stream in a pass with the two "
+                         "note": "kernel classes timed live with CUDA events on the library stream in a pass with the two "
                                  "towers serialised; the headline step overlaps them on two streams",
                          "kernels": kernels},
         }
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            cb, csteps = 8, 1
-            v, sec, threads = run_cpu_port(cb, csteps, 1)
+            cb = 8
+            v, sec, threads, csteps, cwarm = run_cpu_port(cb, 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d-pair batch, 1 warm-up + %d timed train_step of the PyTorch-CPU "
-                                              "restatement (oracle/), %.1f s/step" % (cb, csteps, sec)}
+                                    "sample": "%d-pair batch, %d warm-up + %d timed train_step of the PyTorch-CPU "
+                                              "restatement (oracle/), %.1f s/step; `--impl reference` runs the full "
+                                              "%d-pair batch" % (cb, cwarm, csteps, sec, B)}
             try:
-                line["cpu_baseline"]["parity"] = embedding_delta_vs_port()
+                line["cpu_baseline"]["parity"] = parity_vs_port()
             except Exception as e:   # a reporting extra must never cost the bench line
                 line["cpu_baseline"]["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -370,6 +519,8 @@ if __name__ == "__main__":
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--pool", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE-config records")
+    ap.add_argument("--all-configs", action="store_true", help="run the config 4 / 5 records at any --gpus")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = 3

@@ -102,6 +102,27 @@ int l3_embed_audio_frames(l3_ctx* ctx, const void* signal, int audio_fmt, int64_
 /* load_embedding(...,'vision',...) (vision_model.py:198-218): video (n,224,224,3) -> (n, 8192) */
 int l3_embed_vision(l3_ctx* ctx, const void* video, int video_fmt, int n, float* out);
 
+/* ---- data parallelism inside the library ------------------------------------------------------------------------
+ * Replaces l3embedding/training_utils.py:21-170 (multi_gpu_model: batch slices, one replica per GPU, gradients summed
+ * into shared variables).  One process / context per GPU; the host slices the batch (training_utils.py:121-133) and
+ * every rank runs the same step on its slice with its own BN batch statistics (reference semantics: no sync-BN).
+ * After l3_dp_init, l3_forward_backward sums the gradient arena over the ranks ITSELF: NCCL all-reduces on the
+ * context's communication stream, in buckets that leave while the backward pass is still running (conv4b / conv4a /
+ * conv3 of each tower as soon as their weight gradients are enqueued; a last grouped launch for the small rest).
+ * l3_adam_step and l3_get_metrics wait for them; l3_get_metrics then reports the sums over the GLOBAL batch.
+ * NCCL (libnccl.so.2) is bound at run time; bootstrap: rank 0 calls l3_dp_unique_id and hands the 128 bytes to the
+ * other ranks by any means (the Python host uses torch.distributed / a file; a C host may use MPI or a socket). */
+int l3_dp_unique_id(char out[128]);
+int l3_dp_init(l3_ctx* ctx, const char id[128], int rank, int nranks);   /* collective: every rank must call it */
+int l3_dp_info(l3_ctx* ctx, int* rank, int* nranks);                     /* returns 1 when initialised, else 0 */
+int l3_dp_nccl_version(void);                                            /* e.g. 22809; 0 when NCCL is not loadable */
+/* one keras train_on_batch of the GLOBAL batch on this rank's staged slice: forward_backward (+ overlapped gradient
+ * exchange) + metrics + adam; synchronises once.  out_metrics = sums over the global batch. */
+int l3_dp_train_step_staged(l3_ctx* ctx, int batch, int global_batch, float lr, float out_metrics[4]);
+/* BN moving statistics are per replica during training (reference: one momentum update per replica); replaces them
+ * by their mean over the ranks, so that every rank evaluates -- and rank 0 saves -- the same model. */
+int l3_dp_average_bn_state(l3_ctx* ctx);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------- */
 /* kernel launches issued by this library in the calling process since it was loaded */
 uint64_t l3_launch_count(void);

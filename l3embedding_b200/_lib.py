@@ -46,6 +46,12 @@ SIGNATURES = {
     "l3_get_metrics": (_i, [_vp, _fp]),
     "l3_train_step_staged": (_i, [_vp, _i, _f, _fp]),
     "l3_train_step_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _f, _fp]),
+    "l3_dp_unique_id": (_i, [C.c_char_p]),
+    "l3_dp_init": (_i, [_vp, C.c_char_p, _i, _i]),
+    "l3_dp_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "l3_dp_nccl_version": (_i, []),
+    "l3_dp_train_step_staged": (_i, [_vp, _i, _i, _f, _fp]),
+    "l3_dp_average_bn_state": (_i, [_vp]),
     "l3_predict": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "l3_embed_audio": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "l3_embed_audio_frames": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),

@@ -225,6 +225,10 @@ struct l3_ctx {
   cudaEvent_t ev_staged[2], ev_consumed[2];
   std::mutex st_mu;
   float* metrics_host;   // pinned: {ce sum, #correct} + l2 (double) of the last enqueue_metrics
+  // data parallelism (l3_dp_init): NCCL communicator + communication stream; the gradient buckets of a step are
+  // all-reduced while the backward pass is still running (tower_backward_layer, dp_fire_tail)
+  DpState* dp;
+  int last_global_batch;
   long long adam_t;
   int use_tc;
   int last_batch;
@@ -512,40 +516,59 @@ static bool first_wgrad_tc_enabled() {
   return v != 0;
 }
 
+// Backward of one tower, cut into begin / per-layer / end so that the host can interleave the two towers layer by
+// layer (their kernels run concurrently on the towers' streams) and fire the data-parallel gradient buckets as soon as a
+// layer's weight gradient is enqueued.
+// dz(l) lives in dzbuf[l & 1]; with `defer` the weight gradient of layer l runs on the tower's side stream, ordered by
+// two events per buffer: ev_dz (dz(l) complete -> wgrad(l) may read it) and ev_wg (wgrad(l) done -> the BN/ReLU
+// backward of layer l-2 may overwrite the buffer)
+static bool tower_defers_wgrad(l3_ctx* c, Tower& tw) {
+  return tw.wstream != nullptr && c->wgrad_streams && c->two_streams && tw.stream != c->stream;
+}
+
 template <typename T>
-static int tower_backward(l3_ctx* c, Tower& tw, int B) {
+static int tower_backward_begin(l3_ctx* c, Tower& tw, int B) {
   cudaStream_t s = tw.stream;
-  // dz(l) lives in dzbuf[l & 1]; with `defer` the weight gradient of layer l runs on the tower's side stream, ordered by
-  // two events per buffer: ev_dz (dz(l) complete -> wgrad(l) may read it) and ev_wg (wgrad(l) done -> the BN/ReLU
-  // backward of layer l-2 may overwrite the buffer)
-  T* dzbuf[2] = {(T*)tw.g0, (T*)tw.g0b};
-  const bool defer = tw.wstream != nullptr && c->wgrad_streams && c->two_streams && s != c->stream;
-  cudaStream_t ws = defer ? tw.wstream : s;
   tw.wg_pending[0] = tw.wg_pending[1] = 0;
+  ConvLayer& L = tw.L[7];
+  return launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, (T*)tw.g0b, L.bn, B, L.H, L.W,
+                                L.Cout, s);
+}
+
+// data-parallel bucket of this tower's conv-kernel gradients [l_lo, l_hi] (contiguous in the arena), ordered after
+// everything enqueued so far on `producer`
+static int dp_fire_kernels(l3_ctx* c, Tower& tw, int l_lo, int l_hi, cudaStream_t producer) {
+  if (!c->dp) return 0;
+  long long n = 0;
+  for (int l = l_lo; l <= l_hi; ++l) n += 9LL * tw.L[l].Cin * tw.L[l].Cout;
+  void* p = tw.L[l_lo].dw;
+  return dp_allreduce_ranges(c->dp, producer, &p, &n, 1, 0);
+}
+
+template <typename T>
+static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
+  cudaStream_t s = tw.stream;
+  T* dzbuf[2] = {(T*)tw.g0, (T*)tw.g0b};
+  const bool defer = tower_defers_wgrad(c, tw);
+  cudaStream_t ws = defer ? tw.wstream : s;
   T* da = (T*)tw.g1;
-  {
-    ConvLayer& L = tw.L[7];
-    if (launch_gmaxpool_bwd<T>(c->head.dconcat + tw.concat_off, 1024, tw.argmax, (const T*)L.z, dzbuf[1], L.bn, B, L.H, L.W,
-                               L.Cout, s))
-      return -1;
+  ConvLayer& L = tw.L[l];
+  T* dz = dzbuf[l & 1];
+  long long rows = (long long)B * L.H * L.W;
+  if (l == 7) {
+    // dz holds the scattered dy of the global max-pool and bn.sum its sums: finish BN backward in place
+    if (launch_bn_bwd_finalize(L.bn, rows, 0, s)) return -1;
+    if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
   }
-  for (int l = 7; l >= 0; --l) {
-    ConvLayer& L = tw.L[l];
-    T* dz = dzbuf[l & 1];
-    long long rows = (long long)B * L.H * L.W;
-    if (l == 7) {
-      // dz holds the scattered dy of the global max-pool and bn.sum its sums: finish BN backward in place
-      if (launch_bn_bwd_finalize(L.bn, rows, 0, s)) return -1;
-      if (launch_bn_bwd_apply<T>(dz, (const T*)L.z, B, L.H, L.W, L.Cout, L.bn, L.relu_first, s)) return -1;
+  // weight / bias gradient (layer 0 stays on the main stream: the input-BN gradient is derived from its result)
+  {
+    const bool side = defer && l > 0;
+    cudaStream_t sw = side ? ws : s;
+    if (side) {
+      L3_CHECK_CUDA(cudaEventRecord(tw.ev_dz[l & 1], s));
+      L3_CHECK_CUDA(cudaStreamWaitEvent(ws, tw.ev_dz[l & 1], 0));
     }
-    // weight / bias gradient (layer 0 stays on the main stream: the input-BN gradient is derived from its result)
     {
-      const bool side = defer && l > 0;
-      cudaStream_t sw = side ? ws : s;
-      if (side) {
-        L3_CHECK_CUDA(cudaEventRecord(tw.ev_dz[l & 1], s));
-        L3_CHECK_CUDA(cudaStreamWaitEvent(ws, tw.ev_dz[l & 1], 0));
-      }
       ProfScope ps(c, PROF_CONV_WGRAD, sw);
       if (L.tc && c->use_tc) {
         // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
@@ -565,69 +588,120 @@ static int tower_backward(l3_ctx* c, Tower& tw, int B) {
       } else {
         if (launch_wgrad3x3_simt<T>((const T*)L.in, (const T*)dz, L.dw, L.db, B, L.H, L.W, L.Cin, L.Cout, sw, tw.wg64)) return -1;
       }
-      if (side) {
-        L3_CHECK_CUDA(cudaEventRecord(tw.ev_wg[l & 1], ws));
-        tw.wg_pending[l & 1] = 1;
-      }
     }
-    if (l == 0) {
-      if (tw.has_bn0) {
-        // input BN: d_gamma / d_beta need only sum(da), sum(da*xhat) -- computed without storing da
-        ProfScope ps(c, PROF_CONV_DGRAD, s);
-        if (sizeof(T) == 4) {
-          // parity mode: sum(da), sum(da*xhat) straight from dz with fp64 accumulation.  (The algebraic route below
-          // forms them as a residual of cancelling sums of the weight gradient: fine at bf16 accuracy, but it amplified
-          // the weight gradient's rounding noise past the 1e-2 parity bar.)
-          if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, nullptr, s)) return -1;
-        } else {
-          int* fallback = reinterpret_cast<int*>(tw.d1 + 9 * 64);
-          if (launch_bn0_from_dw(L.w, L.dw, tw.d1, tw.bn0, L.Cin, fallback, s)) return -1;
-          if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, fallback, s)) return -1;
-        }
-        if (launch_bn_bwd_finalize(tw.bn0, rows, 0, s)) return -1;
-      }
-      break;
+    if (side) {
+      L3_CHECK_CUDA(cudaEventRecord(tw.ev_wg[l & 1], ws));
+      tw.wg_pending[l & 1] = 1;
     }
-    // data gradient: da = conv(dz, flip/transpose(w))
-    ConvLayer& Lp = tw.L[l - 1];
-    // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) can ride in the dgrad
-    // epilogue (L3_DGRAD_FUSE_STATS=1; measured neutral, off by default)
-    const bool fuse_stats = L.tc && c->use_tc && !Lp.pool && !Lp.relu_first && conv_tc_fuses_bwd_stats();
-    {
-      ProfScope ps(c, PROF_CONV_DGRAD, s);
-      if (fuse_stats) {
-        if (launch_dgrad3x3_tc_bwdstats((const bf16*)dz, L.wt_pk, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, (const bf16*)Lp.z,
-                                        Lp.bn.scale, Lp.bn.shift, Lp.bn.sum, s))
-          return -1;
-      } else if (L.tc && c->use_tc) {
-        if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
-      } else {
-        if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
-        if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
-      }
-    }
-    // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
-    long long rows_p = (long long)B * Lp.H * Lp.W;
-    if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s,
-                                           (const T*)Lp.zsel, Lp.sel))
-      return -1;
-    if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
-    // dz(l-1) goes into the buffer the weight gradient of layer l+1 read
-    const int nb = (l - 1) & 1;
-    if (tw.wg_pending[nb]) {
-      L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[nb], 0));
-      tw.wg_pending[nb] = 0;
-    }
-    if (launch_bwd_apply<T>(da, (const T*)Lp.z, dzbuf[nb], B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s, Lp.sel))
-      return -1;
+    // gradient buckets of the big layers leave as soon as their weight gradient is enqueued: conv4b, conv4a, conv3a+3b
+    // hold 74 % + 18 % of the bytes and are complete after ~27 % / ~45 % of the backward FLOPs; the small
+    // rest of the tower goes in the final grouped launch (l3_forward_backward).  Layers 7..1 share the stream `sw`.
+    if (l == 7 || l == 6) { if (dp_fire_kernels(c, tw, l, l, sw)) return -1; }
+    else if (l == 4) { if (dp_fire_kernels(c, tw, 4, 5, sw)) return -1; }
   }
-  // the tower is complete only when its side stream is
+  if (l == 0) {
+    if (tw.has_bn0) {
+      // input BN: d_gamma / d_beta need only sum(da), sum(da*xhat) -- computed without storing da
+      ProfScope ps(c, PROF_CONV_DGRAD, s);
+      if (sizeof(T) == 4) {
+        // parity mode: sum(da), sum(da*xhat) straight from dz with fp64 accumulation.  (The algebraic route below
+        // forms them as a residual of cancelling sums of the weight gradient: fine at bf16 accuracy, but it amplified
+        // the weight gradient's rounding noise past the 1e-2 parity bar.)
+        if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, nullptr, s)) return -1;
+      } else {
+        int* fallback = reinterpret_cast<int*>(tw.d1 + 9 * 64);
+        if (launch_bn0_from_dw(L.w, L.dw, tw.d1, tw.bn0, L.Cin, fallback, s)) return -1;
+        if (launch_first_dgrad_bnstats<T>((const T*)dz, L.w, tw.x0, tw.bn0, B, L.H, L.W, L.Cin, L.Cout, fallback, s)) return -1;
+      }
+      if (launch_bn_bwd_finalize(tw.bn0, rows, 0, s)) return -1;
+    }
+    return 0;
+  }
+  // data gradient: da = conv(dz, flip/transpose(w))
+  ConvLayer& Lp = tw.L[l - 1];
+  // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) can ride in the dgrad
+  // epilogue (L3_DGRAD_FUSE_STATS=1; measured neutral, off by default)
+  const bool fuse_stats = L.tc && c->use_tc && !Lp.pool && !Lp.relu_first && conv_tc_fuses_bwd_stats();
+  {
+    ProfScope ps(c, PROF_CONV_DGRAD, s);
+    if (fuse_stats) {
+      if (launch_dgrad3x3_tc_bwdstats((const bf16*)dz, L.wt_pk, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, (const bf16*)Lp.z,
+                                      Lp.bn.scale, Lp.bn.shift, Lp.bn.sum, s))
+        return -1;
+    } else if (L.tc && c->use_tc) {
+      if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
+    } else {
+      if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
+      if (launch_conv3x3_simt<T>((const T*)dz, L.w_t, nullptr, da, B, L.H, L.W, L.Cout, L.Cin, s)) return -1;
+    }
+  }
+  // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
+  long long rows_p = (long long)B * Lp.H * Lp.W;
+  if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s,
+                                         (const T*)Lp.zsel, Lp.sel))
+    return -1;
+  if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
+  // dz(l-1) goes into the buffer the weight gradient of layer l+1 read
+  const int nb = (l - 1) & 1;
+  if (tw.wg_pending[nb]) {
+    L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[nb], 0));
+    tw.wg_pending[nb] = 0;
+  }
+  return launch_bwd_apply<T>(da, (const T*)Lp.z, dzbuf[nb], B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s, Lp.sel);
+}
+
+// the tower is complete only when its side stream is
+static int tower_backward_end(l3_ctx* c, Tower& tw) {
   for (int b2 = 0; b2 < 2; ++b2)
     if (tw.wg_pending[b2]) {
-      L3_CHECK_CUDA(cudaStreamWaitEvent(s, tw.ev_wg[b2], 0));
+      L3_CHECK_CUDA(cudaStreamWaitEvent(tw.stream, tw.ev_wg[b2], 0));
       tw.wg_pending[b2] = 0;
     }
   return 0;
+}
+
+// both towers, interleaved layer by layer on the host (on the device they overlap on their own streams)
+template <typename T>
+static int towers_backward(l3_ctx* c, int B) {
+  Tower* tws[2] = {&c->vision, &c->audio};
+  for (Tower* tw : tws)
+    if (tower_backward_begin<T>(c, *tw, B)) return -1;
+  for (int l = 7; l >= 0; --l)
+    for (Tower* tw : tws)
+      if (tower_backward_layer<T>(c, *tw, B, l)) return -1;
+  for (Tower* tw : tws)
+    if (tower_backward_end(c, *tw)) return -1;
+  return 0;
+}
+
+// loss sum and #correct of the GLOBAL batch: the two scalars are copied aside (head.metrics[8..9]) and summed over the
+// ranks right after the forward pass; l3_get_metrics reports them when data parallelism is on
+static int dp_fire_metrics(l3_ctx* c) {
+  float* g = c->head.metrics + 8;
+  L3_CHECK_CUDA(cudaMemcpyAsync(g, c->head.metrics, 8, cudaMemcpyDeviceToDevice, c->stream));
+  void* p = g;
+  long long n = 2;
+  return dp_allreduce_ranges(c->dp, c->stream, &p, &n, 1, 0);
+}
+
+// The rest of the gradient arena in ONE grouped launch once both towers have joined the context stream: the small
+// conv kernels of each tower (conv1a..conv2b), the dense kernels, and everything that is not a kernel (biases, BN
+// gamma / beta).  ~2.6 MB of 38 MB: this is the only part of the exchange that the backward pass cannot hide.
+static int dp_fire_tail(l3_ctx* c) {
+  void* ptrs[4];
+  long long counts[4];
+  int n = 0;
+  for (Tower* tw : {&c->vision, &c->audio}) {
+    long long k = 0;
+    for (int l = 0; l <= 3; ++l) k += 9LL * tw->L[l].Cin * tw->L[l].Cout;
+    ptrs[n] = tw->L[0].dw;
+    counts[n++] = k;
+  }
+  ptrs[n] = c->head.dw1;                                  // dense_1 and dense_2 kernels are adjacent (build_layout)
+  counts[n++] = 1024LL * 128 + 128 * 2;
+  ptrs[n] = c->grads + c->layout.n_l2;
+  counts[n++] = c->layout.n_params - c->layout.n_l2;
+  return dp_allreduce_ranges(c->dp, c->stream, ptrs, counts, n, 0);
 }
 
 // bf16 tensor-core operand packs of every layer (forward, and dgrad when training), one launch
@@ -852,6 +926,8 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->st_consumed_valid[0] = c->st_consumed_valid[1] = false;
   c->copy_stream = nullptr;
   c->metrics_host = nullptr;
+  c->dp = nullptr;
+  c->last_global_batch = 0;
   if (cudaMallocHost((void**)&c->metrics_host, 64) != cudaSuccess) {
     set_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
@@ -915,6 +991,7 @@ void l3_ctx_destroy(l3_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
   }
   if (ctx->metrics_host) cudaFreeHost(ctx->metrics_host);
+  if (ctx->dp) dp_destroy(ctx->dp);
   if (ctx->stream2) {
     cudaStreamSynchronize(ctx->stream2);
     cudaEventDestroy(ctx->ev_fork);
@@ -1052,32 +1129,42 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
   int slot;
   if (resolve_inputs(c, video, video_fmt, audio, audio_fmt, labels, batch, true, &slot)) return -2;
   const float gs = 1.0f / (float)global_batch;
+  if (c->dp) {
+    // the previous step's collectives (and its Adam update, which waited for them) precede this memset in stream order
+    // only if the caller ran l3_adam_step; make the dependency explicit either way
+    if (dp_join(c->dp, c->stream)) return -1;
+    dp_begin_step(c->dp);
+  }
   L3_CHECK_CUDA(cudaMemsetAsync(c->grads, 0, sizeof(float) * c->layout.n_params, c->stream));
   int rc;
   if (c->dtype == L3_DTYPE_BF16) {
     rc = forward_all<bf16>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
     if (!rc) rc = release_slot(c, slot);
+    if (!rc && c->dp) rc = dp_fire_metrics(c);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
     if (!rc) rc = fork_streams(c);
-    if (!rc) rc = tower_backward<bf16>(c, c->vision, batch);
-    if (!rc) rc = tower_backward<bf16>(c, c->audio, batch);
+    if (!rc) rc = towers_backward<bf16>(c, batch);
     if (!rc) rc = join_streams(c);
   } else {
     rc = forward_all<float>(c, video, video_fmt, audio, audio_fmt, labels, batch, true, gs);
     if (!rc) rc = release_slot(c, slot);
+    if (!rc && c->dp) rc = dp_fire_metrics(c);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
     if (!rc) rc = fork_streams(c);
-    if (!rc) rc = tower_backward<float>(c, c->vision, batch);
-    if (!rc) rc = tower_backward<float>(c, c->audio, batch);
+    if (!rc) rc = towers_backward<float>(c, batch);
     if (!rc) rc = join_streams(c);
   }
+  if (!rc && c->dp) rc = dp_fire_tail(c);
   c->last_batch = batch;
+  c->last_global_batch = global_batch;
   return rc;
 }
 
 int l3_adam_step(l3_ctx* c, float lr) {
   L3_REQUIRE(c != nullptr, "null ctx");
   L3_REQUIRE(c->flags & L3_WS_TRAINING, "context was created without L3_WS_TRAINING");
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  if (c->dp && dp_join(c->dp, c->stream)) return -1;   // the summed gradients must have landed
   // keras 2.0.9 Adam.get_updates: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t); p -= lr_t * m / (sqrt(v) + eps)
   c->adam_t += 1;
   const double b1 = 0.9, b2 = 0.999;
@@ -1100,7 +1187,12 @@ int64_t l3_adam_get_t(l3_ctx* c) {
 // l2 penalty kernel + asynchronous read-back of {ce sum, #correct, l2} into the pinned metrics buffer
 static int enqueue_metrics(l3_ctx* c) {
   if (launch_l2_penalty(c->params, c->layout.n_l2, c->l2_out, c->stream)) return -1;
-  L3_CHECK_CUDA(cudaMemcpyAsync(c->metrics_host, c->head.metrics, 8, cudaMemcpyDeviceToHost, c->stream));
+  const float* src = c->head.metrics;
+  if (c->dp && c->last_global_batch > 0) {
+    if (dp_join(c->dp, c->stream)) return -1;
+    src = c->head.metrics + 8;     // sums over the global batch (dp_fire_metrics)
+  }
+  L3_CHECK_CUDA(cudaMemcpyAsync(c->metrics_host, src, 8, cudaMemcpyDeviceToHost, c->stream));
   L3_CHECK_CUDA(cudaMemcpyAsync(c->metrics_host + 2, c->l2_out, 8, cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
@@ -1110,7 +1202,7 @@ static void read_metrics(l3_ctx* c, float out[4]) {
   out[0] = c->metrics_host[0];
   out[1] = c->metrics_host[1];
   out[2] = (float)(1e-5 * l2);
-  out[3] = (float)c->last_batch;
+  out[3] = (float)((c->dp && c->last_global_batch > 0) ? c->last_global_batch : c->last_batch);
 }
 
 int l3_get_metrics(l3_ctx* c, float out[4]) {
@@ -1131,6 +1223,54 @@ int l3_train_step_staged(l3_ctx* c, int batch, float lr, float out_metrics[4]) {
   if (!rc) L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   if (!rc && out_metrics) read_metrics(c, out_metrics);
   return rc;
+}
+
+int l3_dp_train_step_staged(l3_ctx* c, int batch, int global_batch, float lr, float out_metrics[4]) {
+  L3_REQUIRE(c != nullptr && c->dp != nullptr, "data parallelism is not initialised (l3_dp_init)");
+  int rc = l3_forward_backward(c, nullptr, 0, nullptr, 0, nullptr, batch, global_batch);
+  if (!rc && out_metrics) rc = enqueue_metrics(c);
+  if (!rc) rc = l3_adam_step(c, lr);
+  if (!rc) L3_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  if (!rc && out_metrics) read_metrics(c, out_metrics);
+  return rc;
+}
+
+// ---- data parallelism -------------------------------------------------------------------------------------------
+int l3_dp_unique_id(char out[128]) {
+  L3_REQUIRE(out != nullptr, "null argument");
+  return dp_unique_id(out);
+}
+int l3_dp_nccl_version(void) { return dp_nccl_version(); }
+
+int l3_dp_init(l3_ctx* c, const char id[128], int rank, int nranks) {
+  L3_REQUIRE(c != nullptr && id != nullptr, "null argument");
+  L3_REQUIRE(c->flags & L3_WS_TRAINING, "data parallelism needs a training context");
+  L3_REQUIRE(c->dp == nullptr, "data parallelism is already initialised for this context");
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  c->dp = dp_create(id, rank, nranks);
+  return c->dp ? 0 : -1;
+}
+
+int l3_dp_info(l3_ctx* c, int* rank, int* nranks) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  if (rank) *rank = dp_rank(c->dp);
+  if (nranks) *nranks = dp_nranks(c->dp);
+  return c->dp ? 1 : 0;
+}
+
+__global__ void k_scale(float* __restrict__ p, long long n, float f) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] *= f;
+}
+int l3_dp_average_bn_state(l3_ctx* c) {
+  L3_REQUIRE(c != nullptr && c->dp != nullptr, "data parallelism is not initialised (l3_dp_init)");
+  L3_CHECK_CUDA(cudaSetDevice(c->device));
+  void* p = c->bn_state;
+  long long n = c->layout.n_state;
+  if (dp_allreduce_ranges(c->dp, c->stream, &p, &n, 1, 0)) return -1;
+  if (dp_join(c->dp, c->stream)) return -1;
+  k_scale<<<ceil_div(n, 256), 256, 0, c->stream>>>(c->bn_state, n, 1.0f / (float)dp_nranks(c->dp));
+  L3_CHECK_LAUNCH();
+  return 0;
 }
 
 int l3_train_step_host(l3_ctx* c, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
@@ -1154,6 +1294,7 @@ int l3_predict(l3_ctx* c, const void* video, int video_fmt, const void* audio, i
   if (probs_out) L3_CHECK_CUDA(cudaMemcpyAsync(probs_out, c->head.probs, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));
   if (logits_out) L3_CHECK_CUDA(cudaMemcpyAsync(logits_out, c->head.logits, (size_t)batch * 8, cudaMemcpyDeviceToDevice, c->stream));
   c->last_batch = batch;
+  c->last_global_batch = 0;      // evaluation metrics are local: the host sums them over the ranks it sharded over
   return 0;
 }
 

@@ -170,4 +170,21 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
 int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf16* out, int B, int H, int W, int C0,
                          int Cout, double* stats, cudaStream_t s);
 
+// ---- data-parallel gradient exchange (dp.cu): NCCL bound at run time ---------------------------------------------
+static const int kDpMaxBuckets = 24;
+struct DpState;
+int dp_unique_id(char out[128]);
+int dp_nccl_version();
+DpState* dp_create(const char id_bytes[128], int rank, int nranks);   // ncclCommInitRank on the current device
+void dp_destroy(DpState* d);
+int dp_rank(const DpState* d);
+int dp_nranks(const DpState* d);
+void dp_begin_step(DpState* d);
+// in-place sum over the ranks of disjoint ranges (one grouped NCCL launch on the communication stream), ordered after
+// everything enqueued so far on `producer`
+int dp_allreduce_ranges(DpState* d, cudaStream_t producer, void* const* ptrs, const long long* counts, int n_ranges,
+                        int is_f64);
+// `consumer` waits for every collective issued so far
+int dp_join(DpState* d, cudaStream_t consumer);
+
 }  // namespace l3

@@ -1,10 +1,12 @@
-"""Data-parallel glue replacing l3embedding/training_utils.py:21-170 (multi_gpu_model).
+"""Data-parallel bootstrap replacing l3embedding/training_utils.py:21-170 (multi_gpu_model).
 
 The reference builds one graph spanning N GPUs inside one process; here every GPU has its own process (torchrun)
-holding a full replica.  Per step each rank takes the contiguous slice `get_slice` (training_utils.py:121-133)
-would give its replica, runs forward/backward with its own BN batch statistics (reference semantics: no sync-BN),
-and the flat gradient arena is summed over ranks with ONE all-reduce (NCCL over NVLink on GPUs; gloo in the CPU
-tests).  Gradients are already scaled by 1/global_batch on the device, so the sum is the global-batch gradient.
+holding a full replica.  Per step each rank takes the contiguous slice `get_slice` (training_utils.py:121-133) would
+give its replica and runs forward/backward with its own BN batch statistics (reference semantics: no sync-BN).  The
+gradient exchange itself lives in the CUDA library (csrc/dp.cu, l3_dp_*): NCCL all-reduces on a communication stream,
+in buckets that leave while the backward pass is still running.  What is left here is the bootstrap -- rank, world
+size and handing rank 0's NCCL unique id to the other ranks through the torch.distributed process group torchrun users
+already have (gloo or nccl; any other 128-byte broadcast would do) -- and the sum of the validation scalars.
 """
 from __future__ import annotations
 
@@ -26,9 +28,6 @@ class SingleReplica:
     def attach(self, engine):
         return None
 
-    def allreduce_grads(self, engine):
-        return None
-
     def average_bn_state(self, engine):
         return None
 
@@ -36,8 +35,8 @@ class SingleReplica:
         return xs
 
 
-class TorchDistReplicas:
-    """One replica per torch.distributed rank."""
+class LibraryReplicas:
+    """One replica per torch.distributed rank; gradients are exchanged inside libl3b200 (attach -> l3_dp_init)."""
 
     def __init__(self):
         import torch.distributed as dist
@@ -48,26 +47,21 @@ class TorchDistReplicas:
     def slice(self, batch):
         return replica_slice(batch, self.rank, self.world_size)
 
-    def allreduce_tensor(self, t):
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return t
-
     def attach(self, engine):
-        return None
-
-    def allreduce_grads(self, engine):
-        # one flat fp32 arena (38 MB for cnn_L3_melspec2): a single NCCL ring/NVLS all-reduce
-        return self.allreduce_tensor(engine.grads)
+        """Joins `engine` to the job once (collective: every rank calls it for its engine at the same point)."""
+        if engine.dp_world is None:
+            box = [engine.dp_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(box, src=0)
+            engine.dp_init(box[0], self.rank, self.world_size)
 
     def average_bn_state(self, engine):
-        self.allreduce_tensor(engine.bn_state)
-        engine.bn_state.div_(self.world_size)
+        engine.dp_average_bn_state()
 
     def sum_scalars(self, *xs):
         import torch
         dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
         t = torch.tensor(xs, dtype=torch.float64, device=dev)
-        self.allreduce_tensor(t)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return tuple(t.tolist())
 
 
@@ -78,7 +72,7 @@ def current(num_gpus: int):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("num_gpus=%d needs one process per GPU: launch with torchrun and call "
-                           "torch.distributed.init_process_group('nccl') first" % num_gpus)
+                           "torch.distributed.init_process_group first" % num_gpus)
     if dist.get_world_size() != num_gpus:
         raise RuntimeError("model built for %d GPUs but the process group has %d ranks" % (num_gpus, dist.get_world_size()))
-    return TorchDistReplicas()
+    return LibraryReplicas()

@@ -261,6 +261,42 @@ class Engine:
             _lib.check(self.lib.l3_forward_backward(self.ctx, None, 0, None, 0, None, int(batch),
                                                     int(global_batch or batch)), "l3_forward_backward")
 
+    # ---- data parallelism (l3_dp_*: NCCL inside the library, gradient buckets overlapped with backward) -------
+    @staticmethod
+    def dp_unique_id() -> bytes:
+        """128-byte NCCL unique id (rank 0 creates it and hands it to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().l3_dp_unique_id(buf), "l3_dp_unique_id")
+        return buf.raw
+
+    def dp_init(self, unique_id: bytes, rank: int, world_size: int):
+        """Collective over all ranks: joins this engine's context to the data-parallel job."""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id has 128 bytes")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_dp_init(self.ctx, unique_id, int(rank), int(world_size)), "l3_dp_init")
+
+    @property
+    def dp_world(self):
+        """(rank, world size) once dp_init has run, else None."""
+        r, n = C.c_int(), C.c_int()
+        on = _lib.check(self.lib.l3_dp_info(self.ctx, C.byref(r), C.byref(n)), "l3_dp_info")
+        return (r.value, n.value) if on else None
+
+    def dp_train_step_staged(self, batch: int, global_batch: int, lr: float) -> Dict[str, float]:
+        """train_on_batch of the GLOBAL batch on this rank's staged slice; metrics are sums over the global batch."""
+        out = (C.c_float * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_dp_train_step_staged(self.ctx, int(batch), int(global_batch), float(lr), out),
+                       "l3_dp_train_step_staged")
+        n = max(out[3], 1.0)
+        return dict(ce=out[0] / n, acc=out[1] / n, l2=out[2], loss=out[0] / n + out[2], batch=out[3],
+                    ce_sum=out[0], correct=out[1])
+
+    def dp_average_bn_state(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.l3_dp_average_bn_state(self.ctx), "l3_dp_average_bn_state")
+
     def train_stream(self, batches, lr: float):
         """Pipelined training over an iterable of host batches (video, audio, labels): the upload of batch k+1 is in
         flight on the copy stream while step k computes.  Yields the metrics of every step."""

@@ -340,12 +340,9 @@ class L3Model:
         if par.world_size == 1:
             m = eng.train_step_staged(n, self.optimizer.lr)
             return [m["loss"], m["acc"]]
-        eng.forward_backward_staged(n, global_batch=B)
-        par.allreduce_grads(eng)
-        m = eng.metrics()            # loss of the weights the batch was run with, as keras reports
-        eng.adam_step(self.optimizer.lr)
-        ce_sum, correct = par.sum_scalars(m["ce_sum"], m["correct"])
-        return [ce_sum / B + m["l2"], correct / B]
+        # data parallel: the library sums gradients and the two loss scalars over the ranks while backward runs
+        m = eng.dp_train_step_staged(n, B, self.optimizer.lr)
+        return [m["ce_sum"] / B + m["l2"], m["correct"] / B]
 
     def train_on_batch(self, x, y):
         """x = [video (B,224,224,3), audio (B,1,48000)]; float inputs in [-1,1] as the reference generator yields

@@ -252,21 +252,37 @@ def test_replica_slice_follows_get_slice():
 def _dp_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
+    from l3embedding_b200 import train as T
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
         par = dp.current(world)
 
         class FakeEngine:
-            grads = torch.full((1000,), float(rank + 1))
+            """stands in for the CUDA engine: records what the bootstrap hands to l3_dp_init"""
+            dp_world = None
+            joined = None
+
+            @staticmethod
+            def dp_unique_id():
+                return bytes([65 + rank]) * 128          # only rank 0's id may reach l3_dp_init
+
+            def dp_init(self, uid, r, n):
+                self.joined, self.dp_world = (uid, r, n), (r, n)
         eng = FakeEngine()
-        par.allreduce_grads(eng)
+        par.attach(eng)
+        par.attach(eng)                                   # idempotent: joins once
         s = par.sum_scalars(float(rank), 1.0)
-        q.put((rank, par.slice(10), float(eng.grads[0]), float(eng.grads[-1]), s))
+        # train()'s rank awareness: rank 0 is the chief and names the directory for everybody
+        r, w, bcast = T._replicas(world)
+        model_dir = bcast("dir-from-rank-%d" % rank if r == 0 else None)
+        q.put((rank, par.slice(10), eng.joined, s, (r, w, model_dir)))
     finally:
         dist.destroy_process_group()
 
 
-def test_data_parallel_glue_over_gloo():
+def test_data_parallel_bootstrap_over_gloo():
+    """world_size 2 on CPU (gloo): slices, the NCCL-id hand-over of the bootstrap, the validation-scalar sum and the
+    rank-0-names-the-directory rule of train().  The gradient exchange itself is CUDA/NCCL (tests/test_gpu_g_dp.py)."""
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -282,8 +298,9 @@ def test_data_parallel_glue_over_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert res[0][1] == slice(0, 5) and res[1][1] == slice(5, 10)
-    assert all(r[2] == 3.0 and r[3] == 3.0 for r in res)          # 1 + 2 summed over ranks
-    assert all(r[4] == (1.0, 2.0) for r in res)
+    assert res[0][2] == (b"A" * 128, 0, 2) and res[1][2] == (b"A" * 128, 1, 2)
+    assert all(r[3] == (1.0, 2.0) for r in res)
+    assert res[0][4] == (0, 2, "dir-from-rank-0") and res[1][4] == (1, 2, "dir-from-rank-0")
 
 
 def test_batch_plan_reproduces_the_reference_sequence(tmp_path):
