@@ -535,6 +535,85 @@ def _construct(model_type, name):
     return m, list(m.inputs), m.outputs[0]
 
 
+# ---- tower sub-builders (audio_model.py:8,118,225,335,490; vision_model.py:7,102,221) and the merge (model.py:7-35) --
+
+class TowerHandle(TowerModel):
+    """What the reference's tower builders return as `m`: a stand-alone description of one tower (layer names, weight
+    inventory) that only L3_merge_audio_vision_models can turn into something that computes -- the library implements
+    the four tower pairings the reference's MODELS registry builds, as whole models."""
+
+    def __init__(self, tower, variant, model_type):
+        super().__init__(None, tower, model_type)
+        self.variant = variant
+
+
+# (vision variant, audio variant) -> model type, exactly the pairings of model.py:198-284
+_PAIRINGS = {("orig", "orig"): "cnn_L3_orig", ("inputbn", "kapredbinputbn"): "cnn_L3_kapredbinputbn",
+             ("inputbn", "melspec1"): "cnn_L3_melspec1", ("inputbn", "melspec2"): "cnn_L3_melspec2"}
+_X_I = TensorSpec("input_1", (None, 224, 224, 3))
+_X_A = TensorSpec("input_2", (None, 1, 48000))
+
+
+def _tower(tower, variant, model_type):
+    m = TowerHandle(tower, variant, model_type)
+    return m, (_X_A if tower == "audio" else _X_I), TensorSpec(tower + "_model/flatten", (None, 512))
+
+
+def construct_cnn_L3_orig_audio_model():
+    """audio_model.py:8-115: Spectrogram(n_dft 512, 'valid'), log(max(x, 1e-12))/5, no input BN."""
+    return _tower("audio", "orig", "cnn_L3_orig")
+
+
+def construct_cnn_L3_kapredbinputbn_audio_model():
+    """audio_model.py:118-223: Spectrogram dB + input batch normalisation."""
+    return _tower("audio", "kapredbinputbn", "cnn_L3_kapredbinputbn")
+
+
+def construct_cnn_L3_melspec1_audio_model():
+    """audio_model.py:225-332: Melspectrogram(n_dft 2048, 128 mels, 'same') dB + input BN."""
+    return _tower("audio", "melspec1", "cnn_L3_melspec1")
+
+
+def construct_cnn_L3_melspec2_audio_model():
+    """audio_model.py:335-442: Melspectrogram(n_dft 2048, 256 mels, 'same') dB + input BN."""
+    return _tower("audio", "melspec2", "cnn_L3_melspec2")
+
+
+def construct_cnn_L3_orig_vision_model():
+    """vision_model.py:7-99."""
+    return _tower("vision", "orig", "cnn_L3_orig")
+
+
+def construct_cnn_L3_orig_inputbn_vision_model():
+    """vision_model.py:102-195 (input batch normalisation)."""
+    return _tower("vision", "inputbn", "cnn_L3_melspec2")
+
+
+def construct_tiny_L3_audio_model():
+    raise NotImplementedError("tiny_L3 passes n_win to kapre.Spectrogram, which stock kapre 0.1.3.1/0.1.4 rejects "
+                              "(audio_model.py:516); it is not part of the B200 path")
+
+
+def construct_tiny_L3_vision_model():
+    raise NotImplementedError("tiny_L3 is not part of the B200 path (see construct_tiny_L3_audio_model)")
+
+
+def L3_merge_audio_vision_models(vision_model, x_i, audio_model, x_a, model_name, layer_size=128):
+    """model.py:7-35: concatenate([vision, audio]) -> Dense(layer_size, relu) -> Dense(2, softmax), l2(1e-5) on the
+    kernels.  Returns (model, [x_i, x_a], y).  The device library implements the reference's own pairings and head
+    width; anything else raises."""
+    if not isinstance(vision_model, TowerHandle) or not isinstance(audio_model, TowerHandle) \
+            or vision_model.tower != "vision" or audio_model.tower != "audio":
+        raise TypeError("L3_merge_audio_vision_models expects the towers of construct_*_vision_model / _audio_model")
+    key = (vision_model.variant, audio_model.variant)
+    if key not in _PAIRINGS:
+        raise ValueError("unsupported tower pairing %s: the reference builds %s" % (key, sorted(_PAIRINGS)))
+    if layer_size != 128:
+        raise ValueError("layer_size=%d: the reference's models (and libl3b200) use 128" % layer_size)
+    m = L3Model(_PAIRINGS[key], model_name)
+    return m, [x_i, x_a], m.outputs[0]
+
+
 @gpu_wrapper
 def construct_cnn_L3_orig():
     """Original L3 model (model.py:198-218)."""

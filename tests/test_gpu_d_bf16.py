@@ -131,7 +131,7 @@ def test_bf16_training_step_gradients_with_frozen_routing(model_type):
       * every bias / BN beta / BN gamma gradient (per-channel SUMS of bf16-stored terms): <= 2e-2 relative L2, or --
         for the sums that cancel -- every channel within 8 * 2^-9 * sqrt(sum of squared terms), i.e. a few half-ulps
         of the terms added in quadrature.  The cancelling ones are known analytically: the bias of a convolution
-        feeding a training-mode BN (exactly 0; the device does not even compute it), and beta / gamma of a BN whose
+        feeding a training-mode BN (exactly 0: compared with 0, see the loop), and beta / gamma of a BN whose
         output enters the next convolution without a ReLU mask in between (the input BN; vision bn1b, the
         Conv->ReLU->BN layer) -- their terms are data gradients of a batch-normalised signal and sum to border effects.
         Calibration (CPU, the same emulation evaluated in fp32 and in fp64 arithmetic with identical routing): kernels
@@ -157,6 +157,12 @@ def test_bf16_training_step_gradients_with_frozen_routing(model_type):
         g_ref = g_ref.numpy()
         if name.endswith("/kernel"):
             g_ref = g_ref - 2e-5 * w_np[name]
+        if name.endswith("/bias") and "/conv" in name and name != "vision/conv1b/bias":
+            # bias of a convolution feeding a training-mode BN: the gradient is analytically ZERO (BN backward removes
+            # the per-channel mean of dz).  The oracle's autograd value is the sum of its own bf16 rounding errors --
+            # coherent, not random: the many masked positions of a channel share one value and one rounding error -- so
+            # the device (which skips the reduction and leaves 0) is compared with the analytic value, not with that
+            g_ref = np.zeros_like(g_ref)
         err = rel_l2(got[name], g_ref)
         ok = err <= 2e-2
         ratio = None

@@ -91,3 +91,53 @@ def test_train_function_writes_reference_files_and_resumes(tmp_path):
                        continue_model_dir=model_dir, **kw)
     assert len(hist2.history["loss"]) == 1                      # only epoch index 2 ran
     assert T.get_restart_info(os.path.join(model_dir, "history_csvlog.csv"))[0] == 2
+
+
+def test_reference_embedding_extraction_call_sequence(tmp_path):
+    """05_generate_embedding_samples.py:142-157 + data/usc/us8k.py:146-162 + data/usc/features.py:256-306, statement for
+    statement, against the shim package: parse the model type out of the model path, `from l3embedding.model import
+    load_embedding`, `load_embedding(model_path, model_type, 'audio', pooling_type, tgt_num_gpus=num_gpus)`,
+    `get_l3_frames_uniform(audio, model, hop_size)`, `np.savez_compressed(path, X=..., y=...)` -- and the saved X against
+    the fp64 oracle on the same frames.  The checkpoint is a multi-GPU-layout file (src: a 4-GPU training run) written
+    by train()'s own ModelCheckpoint path."""
+    from l3embedding.model import load_embedding, load_model          # the reference's import line
+    from l3embedding_b200 import model as M
+    from l3embedding_b200.features import get_l3_frames_uniform, frame_signal
+    model_type, pooling_type, num_gpus = "cnn_L3_melspec2", "short", 0
+    model_dir = tmp_path / "embedding" / "music" / model_type / "20180920112233"
+    model_dir.mkdir(parents=True)
+    m, _, _ = M.MODELS[model_type]()
+    w_np = O.init_weights(model_type, seed=21, randomize_bn=True)
+    m.set_named_weights(w_np)
+    model_path = str(model_dir / "model_best_valid_accuracy.h5")
+    m.save_weights(model_path)
+    # 05_generate_embedding_samples.py:144-153
+    model_desc_start_idx = model_path.rindex("embedding") + 10
+    model_desc_end_idx = os.path.dirname(model_path).rindex("/")
+    embedding_desc_str = model_path[model_desc_start_idx:model_desc_end_idx]
+    assert embedding_desc_str.split("/")[-1] == model_type
+    l3embedding_model = load_embedding(model_path, embedding_desc_str.split("/")[-1], "audio", pooling_type,
+                                       tgt_num_gpus=num_gpus)
+    l3embedding_model.parent.configure(dtype="f32")
+    rng = np.random.default_rng(3)
+    audio = (0.1 * rng.standard_normal(48000 + 3 * 4800 + 17)).astype(np.float32)
+    X = get_l3_frames_uniform(audio, l3embedding_model, hop_size=0.1)
+    out = str(tmp_path / "clip.npz")
+    np.savez_compressed(out, X=X, y=3)                                   # us8k.py:162
+    with np.load(out) as z:
+        assert z["X"].shape == (4, 512) and z["X"].dtype == np.float32 and int(z["y"]) == 3
+    a, hop, n = frame_signal(audio)
+    idx = np.arange(48000)[None, :] + hop * np.arange(n)[:, None]
+    ref = O.audio_embedding(torch.from_numpy(a[idx].reshape(n, 1, 48000)).double(), O.to_torch(w_np, dtype=torch.float64),
+                            model_type, pooling_type, F64).numpy()
+    assert np.abs(X - ref).max() <= 1e-3
+    # a checkpoint in the multi-GPU layout (what a 4-GPU reference run saves) loads through the same calls
+    multi = str(model_dir / "model_latest.h5")
+    M.multi_gpu_model(m, gpus=4).save_weights(multi)
+    m.num_gpus = 0
+    e4 = load_embedding(multi, model_type, "audio", "original", src_num_gpus=4, tgt_num_gpus=1)
+    e4.parent.configure(dtype="f32")
+    X4 = e4.predict(a[idx].reshape(n, 1, 48000))
+    ref4 = O.audio_embedding(torch.from_numpy(a[idx].reshape(n, 1, 48000)).double(), O.to_torch(w_np, dtype=torch.float64),
+                             model_type, "original", F64).numpy()
+    assert X4.shape == (n, 6144) and np.abs(X4 - ref4).max() <= 1e-3

@@ -4,6 +4,7 @@ boundary (names, argument meaning, error behaviour), and the N>1 data
 import os
 import re
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -436,3 +437,101 @@ def test_multi_gpu_checkpoint_layout_round_trip(tmp_path):
             assert all(np.array_equal(got[k], w[k]) for k in w), (path, src)
     with pytest.raises(ValueError):
         M.load_model(multi, "cnn_L3_orig", src_num_gpus=4)
+
+
+REFERENCE = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree exists in the build container only")
+
+
+def test_shim_package_resolves_the_reference_imports():
+    """05_generate_embedding_samples.py:5, 03_train_embedding.py:4, classifier/train.py:28, l3embedding/train.py:17-18,
+    l3embedding/model.py:2-4: the reference's import statements, against the shim package at the repo root."""
+    ns = {}
+    exec("from l3embedding.model import load_embedding\n"
+         "from l3embedding.train import *\n"
+         "from l3embedding.train import LossHistory\n"
+         "from l3embedding.model import MODELS, load_model\n"
+         "from l3embedding.audio import pcm2float\n"
+         "from l3embedding.training_utils import multi_gpu_model\n"
+         "from l3embedding.vision_model import *\n"
+         "from l3embedding.audio_model import *\n", ns)
+    from l3embedding_b200 import model as M, train as T
+    assert ns["load_embedding"] is M.load_embedding and ns["train"] is T.train and ns["LossHistory"] is T.LossHistory
+    assert set(ns["MODELS"]) == {"cnn_L3_orig", "tiny_L3", "cnn_L3_kapredbinputbn", "cnn_L3_melspec1", "cnn_L3_melspec2"}
+    # tower sub-builders + merge reproduce the registry's pairings (model.py:198-284)
+    for vis, aud, mt in (("construct_cnn_L3_orig_vision_model", "construct_cnn_L3_orig_audio_model", "cnn_L3_orig"),
+                         ("construct_cnn_L3_orig_inputbn_vision_model", "construct_cnn_L3_kapredbinputbn_audio_model", "cnn_L3_kapredbinputbn"),
+                         ("construct_cnn_L3_orig_inputbn_vision_model", "construct_cnn_L3_melspec1_audio_model", "cnn_L3_melspec1"),
+                         ("construct_cnn_L3_orig_inputbn_vision_model", "construct_cnn_L3_melspec2_audio_model", "cnn_L3_melspec2")):
+        vm, x_i, y_i = ns[vis]()
+        am, x_a, y_a = ns[aud]()
+        m, inputs, y = M.L3_merge_audio_vision_models(vm, x_i, am, x_a, mt)
+        ref, _, _ = M.MODELS[mt]()
+        assert m.name == mt and m.weight_names() == ref.weight_names() and inputs == [x_i, x_a]
+        assert am.get_layer("audio_embedding_layer") and vm.get_layer("vision_embedding_layer")
+    vm, x_i, _ = ns["construct_cnn_L3_orig_vision_model"]()
+    am, x_a, _ = ns["construct_cnn_L3_melspec2_audio_model"]()
+    with pytest.raises(ValueError, match="unsupported tower pairing"):
+        M.L3_merge_audio_vision_models(vm, x_i, am, x_a, "x")
+
+
+@needs_reference
+def test_reference_train_cli_runs_against_the_shim_and_flag_surfaces_match():
+    """The reference's OWN 03_train_embedding.py, unmodified, imports `l3embedding.train` from the shim and parses its
+    flags; l3embedding_b200.cli yields the same argument dictionary (03_train_embedding.py:7-153)."""
+    import runpy
+    import subprocess
+    # run as a script, but with the repo root (the shim) on the path instead of the script's own directory
+    script = os.path.join(REFERENCE, "03_train_embedding.py")
+    code = ("import sys, runpy; sys.path.insert(0, %r); sys.argv = ['03_train_embedding.py', '-h']; "
+            "runpy.run_path(%r, run_name='__main__')" % (ROOT, script))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "--continue-model-dir" in r.stdout, r.stderr
+    from l3embedding_b200 import cli
+    argv = ["-e", "3", "-tes", "5", "--gpus", "4", "-mt", "cnn_L3_melspec2", "-cmd", "/x", "-v", "tr", "va", "out"]
+    old = sys.argv
+    try:
+        sys.argv = ["03_train_embedding.py"] + argv
+        ref_ns = runpy.run_path(os.path.join(REFERENCE, "03_train_embedding.py"), run_name="not_main")
+        ref_args = ref_ns["parse_arguments"]()
+    finally:
+        sys.argv = old
+    ours = cli.parse_arguments(argv)
+    assert {k: ours[k] for k in ref_args} == ref_args
+    assert set(ours) - set(ref_args) == {"dtype", "scale_on_host"}
+    import inspect
+    from l3embedding_b200 import train as T
+    assert set(ref_args) <= set(inspect.signature(T.train).parameters)
+
+
+@needs_reference
+def test_framing_equals_the_reference_function_executed():
+    """get_l3_frames_uniform: the reference's OWN function body (data/usc/features.py:256-306, read from the reference
+    tree at test time and executed with a numpy stand-in for librosa.util.utils.frame) hands its model exactly the
+    frames ours does -- including the operator-precedence quirk that leaves long clips unpadded."""
+    import re
+    import types
+    from l3embedding_b200 import features as F
+    src = open(os.path.join(REFERENCE, "data/usc/features.py")).read()
+    body = re.search(r"^def get_l3_frames_uniform\(.*?(?=^def )", src, re.S | re.M).group(0)
+
+    def frame(y, frame_length, hop_length):
+        n = 1 + (len(y) - frame_length) // hop_length
+        return np.stack([y[i * hop_length:i * hop_length + frame_length] for i in range(n)], axis=1)
+    librosa = types.SimpleNamespace(util=types.SimpleNamespace(utils=types.SimpleNamespace(frame=frame)))
+    ns = {"np": np, "librosa": librosa}
+    exec(body, ns)
+
+    class Recorder:
+        def predict(self, x):
+            self.x = np.array(x)
+            return np.zeros((len(x), 512), np.float32)
+    rng = np.random.default_rng(0)
+    for n in (1000, 48000, 48001, 52799, 52800, 52801, 48000 * 3 + 123, 48000 + 4800 * 7):
+        audio = rng.standard_normal(n).astype(np.float32)
+        a, b = Recorder(), Recorder()
+        ns["get_l3_frames_uniform"](audio.copy(), a, hop_size=0.1)
+        F.get_l3_frames_uniform(audio.copy(), b, hop_size=0.1)
+        assert a.x.shape == b.x.shape and np.array_equal(a.x, b.x), n
+        padded, hop, n_frames = F.frame_signal(audio)
+        assert n_frames == a.x.shape[0] and hop == 4800
