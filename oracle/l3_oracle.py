@@ -80,6 +80,13 @@ class OracleConfig:
     """Switches for the third-party semantics that could not be pinned."""
     db_ref: str = "per_sample"            # kapre amplitude_to_decibel max axis: per_sample | per_batch
     db_multiplier: float = 10.0           # 10*log10(amplitude) (kapre) ; 20 = notebooks/pimodel.ipynb variant
+    # The authors' own numpy restatement of the front-end (notebooks/pimodel.ipynb cells 4 and 12) differs from the
+    # kapre graph in three places; with all three switched (and db_multiplier=20) this oracle reproduces the notebook's
+    # arithmetic (tests/test_oracle.py::test_frontend_reproduces_the_authors_numpy_restatement) -- the one piece of
+    # reference-held front-end arithmetic there is, and the pin for n_fft / hop / window / mel / amin / range / max axis:
+    stft_center: bool = False             # librosa-style centring: pad n_fft//2 zeros on both sides, 1 + L//hop frames
+    mel_on_magnitude: bool = False        # mel(|STFT|)  instead of kapre's sqrt(mel(|STFT|^2))
+    db_amin_on_square: bool = False       # amin floors the squared value (10*log10(max(amin, x^2))), not x
     bn_eps: float = 1e-3                  # keras BatchNormalization default
     bn_momentum: float = 0.99
     bn_moving_var_unbiased: bool = True   # TF fused BN feeds Bessel-corrected var to the moving average
@@ -254,6 +261,8 @@ def frontend(audio: torch.Tensor, model_type: str, cfg: OracleConfig = OracleCon
     B, L = x.shape
     n_dft, n_hop = a["n_dft"], a["n_hop"]
     n_frames, left = frame_geometry(L, n_dft, n_hop, a["padding"])
+    if cfg.stft_center:
+        n_frames, left = 1 + L // n_hop, n_dft // 2
     total = (n_frames - 1) * n_hop + n_dft
     xp = torch.zeros(B, max(total, left + L), dtype=dt)
     xp[:, left:left + L] = x
@@ -263,12 +272,18 @@ def frontend(audio: torch.Tensor, model_type: str, cfg: OracleConfig = OracleCon
     power = spec.real ** 2 + spec.imag ** 2
     if a["kind"] == "mel":
         fb = torch.from_numpy(mel_filterbank(SR, n_dft, a["n_mels"]).astype(np.float32)).to(dt)  # kapre stores float32
-        out = torch.sqrt(power @ fb.t())                                   # power_melgram=1.0
+        if cfg.mel_on_magnitude:
+            out = torch.sqrt(power) @ fb.t()
+        else:
+            out = torch.sqrt(power @ fb.t())                               # power_melgram=1.0
     else:
         out = torch.sqrt(power)                                            # power_spectrogram=1.0
     out = out.transpose(1, 2)                                              # (B, F, T)
     if a["decibel"]:
-        log_spec = cfg.db_multiplier * torch.log(torch.clamp(out, min=1e-10)) / math.log(10.0)
+        if cfg.db_amin_on_square:
+            log_spec = 0.5 * cfg.db_multiplier * torch.log(torch.clamp(out * out, min=1e-10)) / math.log(10.0)
+        else:
+            log_spec = cfg.db_multiplier * torch.log(torch.clamp(out, min=1e-10)) / math.log(10.0)
         if cfg.db_ref == "per_sample":
             mx = log_spec.amax(dim=(1, 2), keepdim=True)
         else:

@@ -181,3 +181,54 @@ def test_emulate_bf16_first_layer_weight_switch():
     w64 = {"t/kernel": torch.randn(3, 3, 64, 64) * 0.05, "t/bias": torch.zeros(64)}
     assert torch.equal(O._conv(x64, w64, "t", O.OracleConfig(emulate_bf16=True)),
                        O._conv(x64, w64, "t", O.OracleConfig(emulate_bf16=True, first_layer_bf16_weights=False)))
+
+
+def _pimodel_frontend(frame, model_type):
+    """The authors' numpy front-end, restated from notebooks/pimodel.ipynb (cell 12, lines 303-319: librosa-style
+    `stft(frame, n_fft, hop_length=242, window='hann', center=True, pad_mode='constant')`, magnitude, for the mel models
+    `melspectrogram(sr=48000, S=S, n_mels, power=1.0, htk=True)` = mel_basis . S; cell 4, lines 139-148:
+    `amplitude_to_db` which squares the magnitude IN PLACE and then takes 10*log10(max(amin, .)) of that same array,
+    subtracts the per-frame-set maximum and floors at -80).  Plain numpy, float64, one 1 s frame."""
+    n_fft = 2048 if model_type in ("cnn_L3_melspec1", "cnn_L3_melspec2") else 512
+    hop = 242
+    y = np.pad(np.asarray(frame, np.float64), n_fft // 2, mode="constant")           # center=True, pad_mode='constant'
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n_fft) / n_fft)                 # get_window('hann', fftbins=True)
+    n_frames = 1 + (len(y) - n_fft) // hop
+    S = np.empty((n_fft // 2 + 1, n_frames))
+    for t in range(n_frames):
+        S[:, t] = np.abs(np.fft.rfft(y[t * hop:t * hop + n_fft] * win))
+    if n_fft == 2048:
+        n_mels = 256 if model_type == "cnn_L3_melspec2" else 128
+        S = O.mel_filterbank(48000, n_fft, n_mels) @ S
+    magnitude = np.abs(S)
+    np.square(magnitude, out=magnitude)                                                # the in-place square
+    log_spec = 10.0 * np.log10(np.maximum(1e-10, magnitude))
+    log_spec -= log_spec.max()
+    return np.maximum(log_spec, -80.0)
+
+
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_melspec1", "cnn_L3_kapredbinputbn"])
+def test_frontend_reproduces_the_authors_numpy_restatement(model_type):
+    """notebooks/pimodel.ipynb is the only front-end ARITHMETIC held by the reference tree.  It is not the
+    kapre graph: it centres the STFT (1024 zeros each side instead of TF-SAME's 982 / 'valid'), applies the mel basis to
+    the magnitude (kapre: sqrt of the mel of the power) and -- through an in-place square -- scales by 20*log10 with amin
+    on the squared value (kapre: 10*log10 of the amplitude).  With exactly those three switches (+ db_multiplier 20) the
+    oracle's front-end reproduces it (to float64 round-off; 1e-5 dB where the float32 mel basis enters), which pins everything else the two share: n_fft 2048 / 512,
+    hop 242, periodic hann, the htk / Slaney-normalised mel basis incl. its two empty rows, amin 1e-10, the 80 dB range
+    and the per-window maximum.  The defaults of OracleConfig remain the kapre semantics of SURVEY App. B."""
+    _, audio, _ = O.synthetic_batch(2, seed=5)
+    x = O.pcm2float(audio, "float64")
+    cfg = O.OracleConfig(dtype=torch.float64, stft_center=True, mel_on_magnitude=True, db_amin_on_square=True,
+                         db_multiplier=20.0)
+    got = O.frontend(torch.from_numpy(x), model_type, cfg)[..., 0].numpy()
+    for b in range(2):
+        want = _pimodel_frontend(x[b, 0], model_type)
+        assert got[b].shape == want.shape == ((256 if model_type == "cnn_L3_melspec2" else 128 if model_type == "cnn_L3_melspec1" else 257), 199)
+        # 1e-5 dB: the oracle keeps the mel basis in float32, as the kapre layer stores it (measured 6.5e-7 dB; the
+        # spectrogram model, which has no basis, agrees to 1e-9)
+        assert np.abs(got[b] - want).max() <= (1e-5 if "melspec" in model_type else 1e-9)
+    # the default (kapre) semantics are a different map: the switches matter (a 2x dB scale changes what the trained
+    # input BN sees), which is why each stays an explicit OracleConfig field
+    kapre = O.frontend(torch.from_numpy(x), model_type, O.OracleConfig(dtype=torch.float64))[..., 0].numpy()
+    if "melspec" in model_type:
+        assert kapre.shape == got.shape and np.abs(kapre - got).max() > 1.0
