@@ -62,6 +62,9 @@ void l3_ctx_destroy(l3_ctx* ctx);
 /* force the SIMT convolution path even in bf16 mode (debug / A-B checks) */
 int l3_ctx_set_use_tensor_cores(l3_ctx* ctx, int enable);
 int l3_ctx_uses_tensor_cores(l3_ctx* ctx);
+/* inference on the tensor-core path folds BatchNorm (moving statistics) + ReLU into the convolution epilogue and
+ * writes the next layer's input directly (default on); 0 keeps the layer-by-layer path (A/B checks, tests) */
+int l3_ctx_set_fused_inference(l3_ctx* ctx, int enable);
 
 /* ---- hot path -------------------------------------------------------------------------------------------- */
 /* async H2D of one batch from (pinned) host memory into one of the ctx's TWO staging slots, on the ctx's own copy

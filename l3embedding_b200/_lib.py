@@ -38,6 +38,7 @@ SIGNATURES = {
     "l3_ctx_destroy": (None, [_vp]),
     "l3_ctx_set_use_tensor_cores": (_i, [_vp, _i]),
     "l3_ctx_uses_tensor_cores": (_i, [_vp]),
+    "l3_ctx_set_fused_inference": (_i, [_vp, _i]),
     "l3_upload_batch_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i]),
     "l3_forward_backward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i]),
     "l3_adam_step": (_i, [_vp, _f]),

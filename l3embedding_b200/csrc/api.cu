@@ -201,6 +201,8 @@ struct l3_ctx {
   Tower vision, audio;
   HeadRef head;
   double* l2_out;
+  float* unit_scale;   // 512 x 1.0f / 512 x 0.0f: identity BN coefficients for the pool-only pass of the fused inference path
+  float* zero_shift;
   // the two towers are independent until the head: the audio tower runs on a second stream so its HBM-bound
   // kernels overlap the vision tower's tensor-core kernels (and vice versa)
   cudaStream_t stream2;
@@ -231,6 +233,7 @@ struct l3_ctx {
   int last_global_batch;
   long long adam_t;
   int use_tc;
+  int fuse_inference;    // fused BN + ReLU conv epilogue on the inference path (l3_ctx_set_fused_inference; default on)
   int last_batch;
   // optional per-kernel-class device timing (CUDA events on the ctx stream)
   int prof_on;
@@ -377,6 +380,8 @@ static long long carve(l3_ctx* c) {
   h.dconcat = (float*)bp.take(4 * B * 1024);
   h.metrics = (float*)bp.take(256);
   c->l2_out = (double*)bp.take(256);
+  c->unit_scale = (float*)bp.take(4 * 512);
+  c->zero_shift = (float*)bp.take(4 * 512);
   return bp.off;
 }
 
@@ -488,6 +493,35 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
   for (int l = 0; l < 8; ++l) {
     ConvLayer& L = tw.L[l];
     bool stats_done = false;
+    if (!training && l < 7 && L.tc && c->use_tc && c->fuse_inference && !(L.pool && L.relu_first)) {
+      // inference on the tensor-core path: BN uses the moving statistics, so scale / shift are known BEFORE the
+      // convolution and BN + ReLU ride in its epilogue on the fp32 accumulator.  Un-pooled layers store straight into
+      // the next layer's padded input (no z tensor, no activation pass); pooled layers store the activation un-padded
+      // and a pool-only pass (identity coefficients; values are >= 0) writes the next input.  The Conv -> ReLU -> BN
+      // -> pool layer (vision conv1b: BN output may be negative) keeps the un-fused path.
+      long long rows = (long long)B * L.H * L.W;
+      if (launch_bn_finalize(L.bn, rows, 0, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
+      {
+        ProfScope ps(c, PROF_CONV_FWD, s);
+        if (launch_conv3x3_tc_act((const bf16*)L.in, L.w_pk, L.b, (bf16*)(L.pool ? L.z : L.a), B, L.H, L.W, L.Cin, L.Cout,
+                                  L.bn.scale, L.bn.shift, L.relu_first, L.pool ? 0 : 1, s))
+          return -1;
+      }
+      if (L.pool && launch_act_fwd<T>((const T*)L.z, (T*)L.a, B, L.H, L.W, L.Cout, c->unit_scale, c->zero_shift, 1, 0, s))
+        return -1;
+      continue;
+    }
+    if (!training && l == 0 && L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16 && c->fuse_inference &&
+        first_conv_tc_enabled()) {
+      // the same for the first layer's own kernel (Cin 1 / 3; Conv -> BN -> ReLU, not pooled)
+      long long rows = (long long)B * L.H * L.W;
+      if (launch_bn_finalize(L.bn, rows, 0, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
+      ProfScope ps(c, PROF_CONV_FWD, s);
+      if (launch_first_conv_tc((const bf16*)L.in, L.w, L.b, (bf16*)L.a, B, L.H, L.W, L.Cin, L.Cout, nullptr, s, L.bn.scale,
+                               L.bn.shift, 1))
+        return -1;
+      continue;
+    }
     if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done, s)) return -1;
     if (l == 7 && embed_only) return 0;  // raw conv4b output incl. bias, before BN/ReLU (audio_model.py:482)
     long long rows = (long long)B * L.H * L.W;
@@ -577,12 +611,14 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
                                L.Cout, sw))
           return -1;
       } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64 && first_wgrad_tc_enabled()) {
-        if (launch_first_wgrad_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.db, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
+        // (the first layer is Conv -> BN in every model type: its bias gradient is identically zero as well -- summing
+        // the stored dz would only add up its rounding errors)
+        if (launch_first_wgrad_tc((const bf16*)L.in, (const bf16*)dz, L.dw, nullptr, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
                                   L.Cin, L.Cout, sw))
           return -1;
       } else if (l == 0) {
         // parity mode derives the input-BN gradient directly (below), not from d1
-        if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, L.db, (tw.has_bn0 && sizeof(T) != 4) ? tw.d1 : nullptr, B,
+        if (launch_first_wgrad<T>((const T*)L.in, (const T*)dz, L.dw, nullptr, (tw.has_bn0 && sizeof(T) != 4) ? tw.d1 : nullptr, B,
                                   L.H, L.W, L.Cin, L.Cout, sw, tw.wg64_0))
           return -1;
       } else {
@@ -919,6 +955,7 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->stream = (cudaStream_t)stream;
   c->adam_t = 0;
   c->use_tc = (dtype == L3_DTYPE_BF16) && conv_tc_supported();
+  c->fuse_inference = 1;
   c->device = 0;
   cudaGetDevice(&c->device);
   c->st_head = c->st_tail = c->st_count = 0;
@@ -968,6 +1005,15 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
     set_error("workspace memset failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
     return nullptr;
+  }
+  {
+    std::vector<float> ones(512, 1.0f);
+    if (cudaMemcpyAsync(c->unit_scale, ones.data(), 4 * 512, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("workspace init failed: %s", cudaGetErrorString(cudaGetLastError()));
+      delete c;
+      return nullptr;
+    }
   }
   int n_out, n_frames, left;
   audio_geometry(c->spec, &n_out, &n_frames, &left);
@@ -1053,6 +1099,11 @@ int l3_ctx_set_use_tensor_cores(l3_ctx* c, int enable) {
   return 0;
 }
 int l3_ctx_uses_tensor_cores(l3_ctx* c) { return c ? c->use_tc : 0; }
+int l3_ctx_set_fused_inference(l3_ctx* c, int enable) {
+  L3_REQUIRE(c != nullptr, "null ctx");
+  c->fuse_inference = enable ? 1 : 0;
+  return 0;
+}
 
 int l3_upload_batch_host(l3_ctx* c, const void* video_host, int video_fmt, const void* audio_host, int audio_fmt,
                          const float* labels_host, int batch) {

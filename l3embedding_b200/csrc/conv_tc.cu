@@ -731,8 +731,11 @@ enum { EPI_NONE = 0,        // no statistics (dgrad, inference): leanest registe
                             // (a warp must own a single chunk: BN = 64; costs ~50 registers per thread)
        EPI_FWD2 = 4,        // statistics taken in the STORE-phase mapping (lane = 16-byte piece of 4 rows): 8 column
                             // partials per lane and chunk, carried over the tiles; works for every BN
-       EPI_BWD = 5 };       // dgrad: the same mapping reads the matching 16 bytes of the layer-below's z (coalesced) and
+       EPI_BWD = 5,         // dgrad: the same mapping reads the matching 16 bytes of the layer-below's z (coalesced) and
                             // carries sum(dy), sum(dy*z) -- pass 1 of the BN/ReLU backward without re-reading da
+       EPI_ACT = 6 };       // inference: BatchNorm (moving statistics folded to scale / shift) + ReLU applied to the fp32
+                            // accumulator before the bf16 rounding; optionally stored straight into the NEXT layer's
+                            // zero-haloed padded input -- no z tensor, no activation pass
 template <int BN_, int MT_, int EPI_>
 struct Conv3Cfg {
   static const int BN = BN_, MT = MT_;
@@ -813,7 +816,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3Threads, 1)
 k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
               int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats, FastDiv dHWp, FastDiv dWp,
-              const bf16* __restrict__ zprev, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift) {
+              const bf16* __restrict__ zprev, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+              int out_padded) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -822,13 +826,14 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[kMaxCoutTc];   // whole bias vector, read by the epilogue as float4
-  __shared__ __align__(16) float s_aux[EPI == EPI_BWD ? 2 * kMaxCoutTc : 4];   // EPI_BWD: BN scale | shift of the layer below
+  // EPI_BWD: BN scale | shift of the layer below; EPI_ACT: of this layer
+  __shared__ __align__(16) float s_aux[(EPI == EPI_BWD || EPI == EPI_ACT) ? 2 * kMaxCoutTc : 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   if (bias != nullptr)
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_bias[i] = __ldg(bias + i);
-  if (EPI == EPI_BWD)
+  if (EPI == EPI_BWD || EPI == EPI_ACT)
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
       s_aux[i] = __ldg(bn_scale + i);
       s_aux[kMaxCoutTc + i] = __ldg(bn_shift + i);
@@ -1013,10 +1018,13 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // output pixel of this lane's row, -1 for halo / out-of-range rows (32-bit index math: Mp < 2^31)
         const int opix = out_pixel(mbase + t * kBM, Mp, H, W, dHWp, dWp);
         const bool valid = opix >= 0;
+        // destination row: the un-padded pixel index, or (EPI_ACT, out_padded) the padded index itself -- the output then IS
+        // the next layer's zero-haloed input; halo rows are never written and stay zero
+        const int dpix = (EPI == EPI_ACT && out_padded && valid) ? (int)(mbase + t * kBM) : opix;
         // store phase: lane l writes 16-byte piece (l & 3) of rows (l >> 2) + 8 i
         int spix[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
+        for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, dpix, (lane >> 2) + 8 * i);
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
 #pragma unroll
         for (int chh = 0; chh < NST; ++chh) {
@@ -1030,14 +1038,36 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (spix[i] >= 0)
                 zr[i] = *reinterpret_cast<const uint4*>(zprev + (long long)spix[i] * Cout + n0 + c0 + (lane & 3) * 8);
           }
-          if (EPI == EPI_CARRY || EPI == EPI_NONE || kStorePhaseStats) {
+          if (EPI == EPI_CARRY || EPI == EPI_NONE || EPI == EPI_ACT || kStorePhaseStats) {
             // 16 columns at a time: half the live registers of the 32-column path
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t v[16];
               tmem_ld16(t_row + c0 + hh * 16, v);
               tmem_ld_wait();
-              if (bias != nullptr) {
+              if (EPI == EPI_ACT) {
+                // y = relu(scale * (acc + bias) + shift), or scale * relu(acc + bias) + shift for the Conv -> ReLU -> BN
+                // layer (relu_stats doubles as that flag): the arithmetic of k_act_fwd on the un-rounded accumulator
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int col = n0 + c0 + hh * 16 + 4 * j;
+                  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (bias != nullptr) bb = *reinterpret_cast<const float4*>(&s_bias[col]);
+                  const float4 sc = *reinterpret_cast<const float4*>(&s_aux[col]);
+                  const float4 sf = *reinterpret_cast<const float4*>(&s_aux[kMaxCoutTc + col]);
+                  float y0 = __uint_as_float(v[4 * j]) + bb.x, y1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+                  float y2 = __uint_as_float(v[4 * j + 2]) + bb.z, y3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+                  if (relu_stats) {
+                    y0 = fmaf(fmaxf(y0, 0.f), sc.x, sf.x); y1 = fmaf(fmaxf(y1, 0.f), sc.y, sf.y);
+                    y2 = fmaf(fmaxf(y2, 0.f), sc.z, sf.z); y3 = fmaf(fmaxf(y3, 0.f), sc.w, sf.w);
+                  } else {
+                    y0 = fmaxf(fmaf(y0, sc.x, sf.x), 0.f); y1 = fmaxf(fmaf(y1, sc.y, sf.y), 0.f);
+                    y2 = fmaxf(fmaf(y2, sc.z, sf.z), 0.f); y3 = fmaxf(fmaf(y3, sc.w, sf.w), 0.f);
+                  }
+                  pk[hh * 8 + 2 * j] = pack_bf16x2(y0, y1);
+                  pk[hh * 8 + 2 * j + 1] = pack_bf16x2(y2, y3);
+                }
+              } else if (bias != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float4 bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + hh * 16 + 4 * j]);
@@ -1120,7 +1150,7 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             __syncwarp();   // the scratch is rewritten by the next chunk
           }
-          if (EPI == EPI_NONE || kStorePhaseStats || stats == nullptr) continue;
+          if (EPI == EPI_NONE || EPI == EPI_ACT || kStorePhaseStats || stats == nullptr) continue;
           // statistics of the values as stored (bf16-rounded); halo / out-of-range rows contribute nothing
           if (EPI == EPI_CARRY) {
             if (valid) {
@@ -1197,6 +1227,7 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 struct BwdFuse {
   const bf16* z;
   const float *scale, *shift;
+  int out_padded = 0;   // EPI_ACT: store into the zero-haloed padded layout
 };
 template <int BN, int MT, int EPI>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
@@ -1218,7 +1249,8 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   k_conv3x3_tc3<BN, MT, EPI><<<2 * pairs, kConv3Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_mp, num_n,
                                                                  stats, relu_stats,
                                                                  make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)),
-                                                                 make_fastdiv((uint32_t)(W + 2)), bf.z, bf.scale, bf.shift);
+                                                                 make_fastdiv((uint32_t)(W + 2)), bf.z, bf.scale, bf.shift,
+                                                                 bf.out_padded);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -1243,6 +1275,12 @@ static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const 
                             BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
 #define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s, bf)
   const int mode = conv_epi_mode();
+  if (bf.z == nullptr && bf.scale != nullptr) {   // inference: fused BatchNorm + ReLU epilogue
+    L3_REQUIRE(stats == nullptr, "fused activation epilogue: no statistics");
+    if (BN == 256) L3_GO(256, 1, EPI_ACT);
+    if (BN == 128) L3_GO(128, 2, EPI_ACT);
+    L3_GO(64, 4, EPI_ACT);
+  }
   if (bf.z != nullptr) {   // dgrad with fused BN-backward statistics
     L3_REQUIRE(stats != nullptr && bias == nullptr && !relu_stats, "fused dgrad statistics: stats, no bias, no relu_first");
     if (BN == 256) L3_GO(256, 1, EPI_BWD);
@@ -1315,6 +1353,21 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   if (BN == 256) return launch_conv_bn<256>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
   if (BN == 128) return launch_conv_bn<128>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
   return launch_conv_bn<64>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+}
+
+// Inference forward with BatchNorm (scale / shift from the moving statistics) and ReLU in the epilogue (relu_first: the
+// Conv -> ReLU -> BN order).  out_padded = 1: `out` is the next layer's zero-haloed padded input (B,H+2,W+2,Cout) whose
+// halo must already be zero; 0: un-padded (B,H,W,Cout), e.g. ahead of a max-pool pass.
+int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
+                          int Cout, const float* scale, const float* shift, int relu_first, int out_padded, cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  L3_REQUIRE(scale != nullptr && shift != nullptr, "conv_tc_act: scale / shift");
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
+  const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  BwdFuse bf{nullptr, scale, shift};
+  bf.out_padded = out_padded;
+  return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, nullptr, relu_first, s, bf);
 }
 
 int conv_tc_fuses_bwd_stats() {
@@ -2015,7 +2068,8 @@ template <int C0>
 __global__ void __launch_bounds__(kFcThreads, 1)
 k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const float* __restrict__ bias,
                 bf16* __restrict__ out, int H, int W, long long Mp, int num_tiles, double* __restrict__ stats,
-                FastDiv dHWp, FastDiv dWp) {
+                FastDiv dHWp, FastDiv dWp, const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                int out_padded) {
   using Cfg = FcCfg<C0>;
   constexpr int K = Cfg::K, KPAD = Cfg::KPAD, NQ = Cfg::NQ, ST = Cfg::kStages, ACCS = Cfg::kAccs, RS = Cfg::kRawStages;
   extern __shared__ uint8_t smem_raw[];
@@ -2026,6 +2080,7 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
   __shared__ __align__(8) uint64_t a_full[ST], a_empty[ST], t_full[ACCS], t_empty[ACCS], r_full[RS], r_empty[RS];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[64];
+  __shared__ __align__(16) float s_act[128];   // inference: BN scale | shift applied (with ReLU) in the epilogue
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // weight tile: element (co, k) at co*128 + ((k/8) ^ (co & 7))*16 + (k % 8)*2 ; zero beyond K
@@ -2037,6 +2092,10 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
   for (int i = threadIdx.x; i < RS * Cfg::kRawStage / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem_in)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 64) s_bias[threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
+  if (act_scale != nullptr && threadIdx.x < 64) {
+    s_act[threadIdx.x] = __ldg(act_scale + threadIdx.x);
+    s_act[64 + threadIdx.x] = __ldg(act_shift + threadIdx.x);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < ACCS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
@@ -2152,9 +2211,11 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       const int acc = it & (ACCS - 1);
       const uint32_t aph = (uint32_t)(it / ACCS) & 1u;
       const int opix = out_pixel((uint32_t)tile * kBM + q * 32 + lane, Mp, H, W, dHWp, dWp);
+      // inference with out_padded: the row lands at its own padded index = the next layer's zero-haloed input
+      const int dpix = (out_padded && opix >= 0) ? (int)((uint32_t)tile * kBM + q * 32 + lane) : opix;
       int spix[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
+      for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, dpix, (lane >> 2) + 8 * i);
       mbar_wait(&t_full[acc], aph);
       tc_fence_after();
       uint32_t v[32];
@@ -2165,11 +2226,25 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);   // accumulator is in registers: hand it back before the math
       uint32_t pk[16];
+      if (act_scale != nullptr) {
+        // inference: relu(scale * (acc + bias) + shift) on the un-rounded accumulator (the first layer is Conv -> BN -> ReLU)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
-        pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-        pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+          const float4 sc = *reinterpret_cast<const float4*>(&s_act[c0 + 4 * j]);
+          const float4 sf = *reinterpret_cast<const float4*>(&s_act[64 + c0 + 4 * j]);
+          pk[2 * j] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[4 * j]) + bb.x, sc.x, sf.x), 0.f),
+                                  fmaxf(fmaf(__uint_as_float(v[4 * j + 1]) + bb.y, sc.y, sf.y), 0.f));
+          pk[2 * j + 1] = pack_bf16x2(fmaxf(fmaf(__uint_as_float(v[4 * j + 2]) + bb.z, sc.z, sf.z), 0.f),
+                                      fmaxf(fmaf(__uint_as_float(v[4 * j + 3]) + bb.w, sc.w, sf.w), 0.f));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * j]);
+          pk[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+          pk[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+        }
       }
       if (opix < 0) {   // halo / out-of-range rows: not stored, and zero in the statistics
 #pragma unroll
@@ -2213,7 +2288,10 @@ k_first_conv_tc(const bf16* __restrict__ xin, const float* __restrict__ w, const
 }
 
 int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf16* out, int B, int H, int W, int C0,
-                         int Cout, double* stats, cudaStream_t s) {
+                         int Cout, double* stats, cudaStream_t s, const float* act_scale, const float* act_shift,
+                         int out_padded) {
+  L3_REQUIRE(act_scale == nullptr || (act_shift != nullptr && stats == nullptr), "first_conv_tc: fused activation excludes statistics");
+  L3_REQUIRE(!out_padded || act_scale != nullptr, "first_conv_tc: the padded store belongs to the fused-activation mode");
   L3_REQUIRE(Cout == 64 && (C0 == 1 || C0 == 3), "first_conv_tc: C0=%d Cout=%d", C0, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_conv_tc: pixel count out of range");
@@ -2228,8 +2306,12 @@ int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf1
   const int num_tiles = (int)((Mp + kBM - 1) / kBM);
   const int grid = num_tiles < 148 ? num_tiles : 148;
   const FastDiv dHWp = make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)), dWp = make_fastdiv((uint32_t)(W + 2));
-  if (C0 == 1) k_first_conv_tc<1><<<grid, kFcThreads, FcCfg<1>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp);
-  else k_first_conv_tc<3><<<grid, kFcThreads, FcCfg<3>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp);
+  if (C0 == 1)
+    k_first_conv_tc<1><<<grid, kFcThreads, FcCfg<1>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp, act_scale,
+                                                              act_shift, out_padded);
+  else
+    k_first_conv_tc<3><<<grid, kFcThreads, FcCfg<3>::kSmem, s>>>(xin, w, bias, out, H, W, Mp, num_tiles, stats, dHWp, dWp, act_scale,
+                                                              act_shift, out_padded);
   L3_CHECK_LAUNCH();
   return 0;
 }

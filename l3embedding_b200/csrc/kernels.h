@@ -149,6 +149,10 @@ int launch_pack_weights_batch(const PackBatch& pb, cudaStream_t s);
 // the epilogue so the tensor is not read again.
 int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
                       int Cout, double* stats, int relu_stats, cudaStream_t s);
+// Inference forward with BatchNorm (moving statistics folded into scale / shift) + ReLU fused into the epilogue, stored
+// un-padded (out_padded = 0) or straight into the next layer's zero-haloed padded input (out_padded = 1)
+int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
+                          int Cout, const float* scale, const float* shift, int relu_first, int out_padded, cudaStream_t s);
 // Data gradient of a conv (Cin -> Cout) on tensor cores with pass 1 of the BN/ReLU backward of the layer BELOW fused
 // into the epilogue: da (B,H,W,Cin) = conv(dz, packed_wt); sums[0..Cin) = sum(dy), sums[Cin..2Cin) = sum(dy * z_below)
 // with dy = da where scale*z_below + shift > 0 (the layer below is Conv -> BN -> ReLU, not pooled); sums are zeroed here.
@@ -167,8 +171,11 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
 
 // First-layer (Cin = 1|3, Cout = 64) forward on tensor cores: xin padded bf16 (B,H+2,W+2,C0), w fp32 HWIO, out unpadded
 // bf16 (B,H,W,64); stats as in launch_conv3x3_tc (zeroed here).
+// act_scale / act_shift (inference, optional): BN + ReLU fused into the epilogue; with out_padded the result is stored
+// into the next layer's zero-haloed padded input.
 int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf16* out, int B, int H, int W, int C0,
-                         int Cout, double* stats, cudaStream_t s);
+                         int Cout, double* stats, cudaStream_t s, const float* act_scale = nullptr,
+                         const float* act_shift = nullptr, int out_padded = 0);
 
 // ---- data-parallel gradient exchange (dp.cu): NCCL bound at run time ---------------------------------------------
 static const int kDpMaxBuckets = 24;

@@ -402,5 +402,9 @@ class Engine:
     def uses_tensor_cores(self) -> bool:
         return bool(self.lib.l3_ctx_uses_tensor_cores(self.ctx))
 
+    def set_fused_inference(self, enable: bool):
+        """Inference on the tensor-core path: BN + ReLU in the convolution epilogue (default) or layer by layer."""
+        _lib.check(self.lib.l3_ctx_set_fused_inference(self.ctx, int(bool(enable))), "l3_ctx_set_fused_inference")
+
     def set_use_tensor_cores(self, enable: bool):
         _lib.check(self.lib.l3_ctx_set_use_tensor_cores(self.ctx, int(bool(enable))), "l3_ctx_set_use_tensor_cores")

@@ -200,3 +200,41 @@ def test_bf16_throughput_mode_reports_error(model_type):
     assert np.isfinite(eng.metrics()["loss"])
     g = eng.get_grads()
     assert all(np.isfinite(v).all() for v in g.values())
+
+
+@pytest.mark.parametrize("model_type", MODEL_TYPES)
+@pytest.mark.parametrize("batch", [1, 5])
+def test_bf16_fused_inference_epilogue_matches_layerwise_path(model_type, batch):
+    """Inference on the tensor-core path folds BatchNorm (moving statistics) + ReLU into the convolution epilogue and
+    stores straight into the next layer's padded input (EPI_ACT of k_conv3x3_tc3, the fused mode of k_first_conv_tc).
+    Against the layer-by-layer path of the same library (z stored, k_act_fwd) on identical inputs and weights the only
+    difference is WHERE the bf16 rounding happens (the fused path activates the un-rounded fp32 accumulator), so the
+    two agree to bf16 rounding noise -- and the fused path is at least as close to the fp64 oracle."""
+    w_np = O.init_weights(model_type, seed=20180123, randomize_bn=True)
+    video, audio, _ = O.synthetic_batch(batch, seed=77)
+    vf, af = _oracle_inputs(video, audio)
+    w = O.to_torch(w_np, dtype=torch.float64)
+    ref = {"emb_o": O.audio_embedding(af, w, model_type, "original", F64).numpy(),
+           "emb_s": O.audio_embedding(af, w, model_type, "short", F64).numpy(),
+           "emb_v": O.vision_embedding(vf, w, model_type, F64).numpy(),
+           "logits": O.avc_forward(vf, af, w, model_type, False, F64).numpy()}
+    eng = _engine(model_type, batch, "bf16", training=False, weights=w_np)
+    assert eng.uses_tensor_cores
+    got = {}
+    for fused in (True, False):
+        eng.set_fused_inference(fused)
+        got[fused] = {"emb_o": eng.embed_audio(audio, "original").cpu().numpy(),
+                      "emb_s": eng.embed_audio(audio, "short").cpu().numpy(),
+                      "emb_v": eng.embed_vision(video).cpu().numpy(),
+                      "logits": eng.predict(video, audio)[1]}
+    rows = []
+    for k, r in ref.items():
+        scale = max(1.0, float(np.abs(r).max()))
+        e_f = float(np.abs(got[True][k] - r).max()) / scale
+        e_u = float(np.abs(got[False][k] - r).max()) / scale
+        d = float(np.abs(got[True][k] - got[False][k]).max()) / scale
+        rows.append((k, round(e_f, 5), round(e_u, 5), round(d, 5)))
+        assert np.isfinite(got[True][k]).all()
+        assert e_f <= 0.03 and d <= 0.03, rows                 # bf16: ~1 % of the largest value (SURVEY 0.5)
+        assert e_f <= 1.5 * e_u + 2e-3, rows                   # not worse than the layer-by-layer path
+    print(model_type, batch, "fused inference (quantity, fused err, layerwise err, fused-vs-layerwise; relative to max):", rows)
