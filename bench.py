@@ -365,19 +365,29 @@ def embedding_inference_record(dev):
                 torch.cuda.synchronize()
                 r = {"clips_per_s_resident": n_iter * BATCH / (e0.elapsed_time(e1) / 1e3), "clips": n_iter * BATCH,
                      "conv_tflops": n_iter * BATCH / (e0.elapsed_time(e1) / 1e3) * 20.405 / 1e3}
-                if dtype == "bf16":
-                    hres = torch.empty(BATCH, dim).pin_memory()
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    for _ in range(n_iter):
-                        dd = host.to(dev, non_blocking=True)
-                        eng.embed_audio(dd, pooling, out=res)
-                        hres.copy_(res, non_blocking=True)
-                    torch.cuda.synchronize()
-                    r["clips_per_s_host_to_host"] = n_iter * BATCH / (time.perf_counter() - t0)
                 rec["%s_%s" % (dtype, pooling)] = r
         finally:
             eng.close()
+    # the call a user of the reference makes (05_generate_embedding_samples.py:154-157 -> features.py:304): the keras-
+    # style embedding model's predict() on a pageable host array of all 10 000 clips, pageable float32 result
+    try:
+        import numpy as np
+        from l3embedding_b200 import model as M
+        m, _, _ = M.MODELS[MODEL_TYPE]()
+        m.configure(dtype="bf16")
+        x = np.tile(audio, (N // BATCH, 1, 1))
+        for pooling in ("original", "short"):
+            e, _, _ = M.convert_audio_model_to_embedding(m.get_layer("audio_model"), m.inputs[1], MODEL_TYPE, pooling)
+            e.predict(x[:1024])                               # engine creation + warm-up
+            t0 = time.perf_counter()
+            y = e.predict(x)
+            dt = time.perf_counter() - t0
+            rec["bf16_" + pooling]["clips_per_s_host_to_host"] = N / dt
+            rec["bf16_" + pooling]["host_to_host_api"] = ("EmbeddingModel.predict: pageable int16 (10000,1,48000) -> pageable "
+                                                          "float32 (10000,%d), 3-stage pinned pipeline" % y.shape[1])
+            e._engine.close()
+    except Exception as ex:
+        rec["host_to_host_error"] = "%s: %s" % (type(ex).__name__, ex)
     return rec
 
 

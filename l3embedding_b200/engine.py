@@ -362,10 +362,11 @@ class Engine:
             self._keep = (sig,)
             return out
 
-    def embed_vision(self, video) -> torch.Tensor:
+    def embed_vision(self, video, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         with torch.cuda.device(self.device):
             v, vf, _, _, _, n = self._inputs(video, None)
-            out = torch.empty(n, 4 * 4 * 512, dtype=torch.float32, device=self.device)
+            if out is None:
+                out = torch.empty(n, 4 * 4 * 512, dtype=torch.float32, device=self.device)
             _lib.check(self.lib.l3_embed_vision(self.ctx, self._p(v), vf, n, self._p(out)), "l3_embed_vision")
             self._keep = (v,)
             return out

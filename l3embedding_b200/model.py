@@ -493,15 +493,79 @@ class EmbeddingModel:
         eng = self._get_engine(min(batch_size, max(n_frames, 1)))
         return eng.embed_audio_frames(sig, hop_length, self.pooling_type).cpu().numpy()
 
+    # device batch of predict(): keras' default batch_size of 32 (data/usc/features.py:304 passes none) would leave the
+    # GPU idle between tiny launch sequences; inference results do not depend on how samples are batched (BN uses the
+    # moving statistics), so larger chunks are used internally
+    DEVICE_BATCH = 512
+
     def predict(self, x, batch_size=32, verbose=0):
-        x = np.asarray(x) if not hasattr(x, "shape") else x
+        """keras `Model.predict`: (n,1,48000) audio [float32 in [-1,1) or int16 PCM] -> (n, 6144|512) float32, or
+        (n,224,224,3) frames [float32 in [-1,1] or uint8] -> (n, 8192).  Host arrays are streamed through a three-stage
+        pipeline: a worker thread copies chunk k+1 into page-locked memory while chunk k is on the device (H2D, towers,
+        D2H all asynchronous on the engine's stream) and chunk k-1 is copied out of its pinned result buffer."""
+        import threading
+
+        import torch
+        x = np.asarray(x)
         n = len(x)
-        eng = self._get_engine(min(batch_size, max(n, 1)))
+        audio = self.embedding_type == "audio"
+        want = (np.int16, np.float32) if audio else (np.uint8, np.float32)
+        if x.dtype not in want:
+            x = x.astype(np.float32)
         out = np.empty((n, self.output_dim), np.float32)
-        for s in range(0, n, batch_size):
-            xb = x[s:s + batch_size]
-            e = eng.embed_audio(xb, self.pooling_type) if self.embedding_type == "audio" else eng.embed_vision(xb)
-            out[s:s + batch_size] = e.cpu().numpy()
+        if n == 0:
+            return out
+        step = min(max(int(batch_size), self.DEVICE_BATCH if audio else 64), n)
+        eng = self._get_engine(step)
+        step = min(step, eng.max_batch)
+        dev = eng.device
+        tdt = {np.dtype(np.int16): torch.int16, np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8}[x.dtype]
+        sample = tuple(x.shape[1:])
+        pin_in = [torch.empty((step,) + sample, dtype=tdt).pin_memory() for _ in range(2)]
+        pin_out = [torch.empty((step, self.output_dim), dtype=torch.float32).pin_memory() for _ in range(2)]
+        dev_in = [torch.empty((step,) + sample, dtype=tdt, device=dev) for _ in range(2)]
+        dev_out = [torch.empty((step, self.output_dim), dtype=torch.float32, device=dev) for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        chunks = [(s, min(s + step, n)) for s in range(0, n, step)]
+        staged = [threading.Event() for _ in chunks]
+        free = [threading.Semaphore(1), threading.Semaphore(1)]      # pinned input slot may be overwritten
+        err = []
+
+        def stage():
+            try:
+                for k, (a, b) in enumerate(chunks):
+                    free[k % 2].acquire()
+                    np.copyto(pin_in[k % 2].numpy()[:b - a], x[a:b])
+                    staged[k].set()
+            except BaseException as e:       # surfaced in the caller
+                err.append(e)
+                for ev in staged:
+                    ev.set()
+        worker = threading.Thread(target=stage, name="l3-predict-stage", daemon=True)
+        worker.start()
+
+        def drain(k):
+            a, b = chunks[k]
+            done[k % 2].synchronize()
+            out[a:b] = pin_out[k % 2].numpy()[:b - a]
+            free[k % 2].release()            # its H2D copy completed long before the D2H did
+        with torch.cuda.device(dev):
+            for k, (a, b) in enumerate(chunks):
+                staged[k].wait()
+                if err:
+                    raise err[0]
+                m = b - a
+                dev_in[k % 2][:m].copy_(pin_in[k % 2][:m], non_blocking=True)
+                if audio:
+                    eng.embed_audio(dev_in[k % 2][:m], self.pooling_type, out=dev_out[k % 2])
+                else:
+                    eng.embed_vision(dev_in[k % 2][:m], out=dev_out[k % 2])
+                pin_out[k % 2][:m].copy_(dev_out[k % 2][:m], non_blocking=True)
+                done[k % 2].record()
+                if k >= 1:
+                    drain(k - 1)
+            drain(len(chunks) - 1)
+        worker.join()
         return out
 
 
