@@ -293,16 +293,6 @@ static void carve_bn(Bump& bp, BnRef& bn, int C) {
   bn.c2 = (float*)bp.take(4 * C);
 }
 
-// L3_POOL_RECORD=0: the pooled backward kernels re-derive the max-pool routing from z instead of reading the forward
-// pass's record (A/B checks)
-static bool pool_record_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_POOL_RECORD");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
 
 // Walks every workspace allocation; with ctx->ws == nullptr it only measures.
 static long long carve(l3_ctx* c) {
@@ -347,7 +337,7 @@ static long long carve(l3_ctx* c) {
       carve_bn(bp, L.bn, L.Cout);
       int OH = L.pool ? H / 2 : H, OW = L.pool ? W / 2 : W;  // valid pooling floors; vision sizes are even
       L.a = l < 7 ? bp.take(es * B * (OH + 2) * (OW + 2) * L.Cout) : nullptr;
-      const bool rec = training && L.pool && pool_record_enabled();
+      const bool rec = training && L.pool;
       L.zsel = rec ? bp.take(es * B * OH * OW * L.Cout) : nullptr;
       L.sel = rec ? (uint8_t*)bp.take(B * OH * OW * L.Cout) : nullptr;
       L.w_t = training ? (float*)bp.take(4LL * 9 * L.Cin * L.Cout) : nullptr;
@@ -426,15 +416,6 @@ static void bind_params(l3_ctx* c) {
 static const float kBnMomentum = 0.99f, kBnEps = 1e-3f;  // keras BatchNormalization defaults
 static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm feeds the Bessel-corrected variance
 
-// L3_FIRST_CONV_TC=0 keeps the SIMT first-layer forward in bf16 mode (A/B checks)
-static bool first_conv_tc_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_FIRST_CONV_TC");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
 
 // want_stats: training-mode BN statistics of the output; *stats_done tells the caller they were fused
 template <typename T>
@@ -447,7 +428,7 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* s
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
                              fuse ? L.bn.sum : nullptr, L.relu_first, s);
   }
-  if (L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16 && first_conv_tc_enabled()) {
+  if (L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16) {
     *stats_done = want_stats;
     return launch_first_conv_tc((const bf16*)L.in, L.w, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
                                 want_stats ? L.bn.sum : nullptr, s);
@@ -511,8 +492,7 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
         return -1;
       continue;
     }
-    if (!training && l == 0 && L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16 && c->fuse_inference &&
-        first_conv_tc_enabled()) {
+    if (!training && l == 0 && L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16 && c->fuse_inference) {
       // the same for the first layer's own kernel (Cin 1 / 3; Conv -> BN -> ReLU, not pooled)
       long long rows = (long long)B * L.H * L.W;
       if (launch_bn_finalize(L.bn, rows, 0, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
@@ -541,14 +521,6 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
   return 0;
 }
 
-static bool first_wgrad_tc_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_FIRST_WGRAD_TC");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
 
 // Backward of one tower, cut into begin / per-layer / end so that the host can interleave the two towers layer by
 // layer (their kernels run concurrently on the towers' streams) and fire the data-parallel gradient buckets as soon as a
@@ -610,7 +582,7 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
         if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
                                L.Cout, sw))
           return -1;
-      } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64 && first_wgrad_tc_enabled()) {
+      } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64) {
         // (the first layer is Conv -> BN in every model type: its bias gradient is identically zero as well -- summing
         // the stored dz would only add up its rounding errors)
         if (launch_first_wgrad_tc((const bf16*)L.in, (const bf16*)dz, L.dw, nullptr, tw.has_bn0 ? tw.d1 : nullptr, B, L.H, L.W,
@@ -655,16 +627,9 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
   }
   // data gradient: da = conv(dz, flip/transpose(w))
   ConvLayer& Lp = tw.L[l - 1];
-  // un-pooled Conv -> BN -> ReLU layer below: pass 1 of its BN/ReLU backward (sum dy, sum dy*z) can ride in the dgrad
-  // epilogue (L3_DGRAD_FUSE_STATS=1; measured neutral, off by default)
-  const bool fuse_stats = L.tc && c->use_tc && !Lp.pool && !Lp.relu_first && conv_tc_fuses_bwd_stats();
   {
     ProfScope ps(c, PROF_CONV_DGRAD, s);
-    if (fuse_stats) {
-      if (launch_dgrad3x3_tc_bwdstats((const bf16*)dz, L.wt_pk, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, (const bf16*)Lp.z,
-                                      Lp.bn.scale, Lp.bn.shift, Lp.bn.sum, s))
-        return -1;
-    } else if (L.tc && c->use_tc) {
+    if (L.tc && c->use_tc) {
       if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
     } else {
       if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
@@ -673,8 +638,8 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
   }
   // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
   long long rows_p = (long long)B * Lp.H * Lp.W;
-  if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s,
-                                         (const T*)Lp.zsel, Lp.sel))
+  if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s, (const T*)Lp.zsel,
+                          Lp.sel))
     return -1;
   if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
   // dz(l-1) goes into the buffer the weight gradient of layer l+1 read
@@ -989,10 +954,8 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->stream_v = nullptr;
   c->vision.wstream = c->audio.wstream = nullptr;
   {
-    const char* e = getenv("L3_TWO_STREAMS");
-    c->two_streams = e ? atoi(e) : 1;
-    const char* e2 = getenv("L3_WGRAD_STREAMS");
-    c->wgrad_streams = e2 ? atoi(e2) : 1;
+    c->two_streams = 1;     // l3_ctx_set_two_streams(ctx, 0) serialises the towers (per-kernel timing)
+    c->wgrad_streams = 1;
     if (c->two_streams && create_streams(c)) {
       delete c;
       return nullptr;

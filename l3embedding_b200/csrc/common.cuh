@@ -114,6 +114,23 @@ __host__ __device__ __forceinline__ long long pad_off(long long b, int y, int x,
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute (opt-in to > 48 KB of dynamic shared memory) is per DEVICE: one flag per launcher and device,
+// so that a second context on another GPU of the same process gets its own opt-in.  Setting the attribute twice is
+// harmless, so the flag is only marked after the calls succeeded (two racing threads both set it).
+struct PerDeviceOnce {
+  unsigned long long done = 0;   // bit d: configured on device d
+  bool needed() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return !((done >> (d & 63)) & 1ull);
+  }
+  void mark() {
+    int d = 0;
+    cudaGetDevice(&d);
+    __atomic_fetch_or(&done, 1ull << (d & 63), __ATOMIC_RELAXED);
+  }
+};
+
 // ---- per-BN-layer device record ---------------------------------------------------------
 // All pointers are device pointers into caller-owned buffers.
 struct BnRef {

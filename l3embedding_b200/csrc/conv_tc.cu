@@ -1,15 +1,14 @@
 // tcgen05 (5th-gen tensor core) bf16 implicit-GEMM 3x3 convolutions for sm_100a.  Replaces what cuDNN ran for the keras
 // Conv2D layers of l3embedding/audio_model.py:376-432 and l3embedding/vision_model.py:130-186 (forward and backward).
 //
-// Kernels in this file (the training step uses the ones marked *):
-//   k_conv3x3_tc      forward / dgrad, version 1: one 128 x BN tile per tap and 64-channel chunk          (A/B reference)
-//   k_conv3x3_tc2     version 2: shared-halo A regions, MT m-tiles per CTA, fused BN statistics            (A/B reference)
-// * k_conv3x3_tc3     version 3: version 2 on CTA pairs (cta_group::2), coalescing epilogue, epilogue flavours EPI_*
-//   k_wgrad3x3_tc     weight gradient, version 1 (per-tap boxes)                                           (A/B reference)
-// * k_wgrad3x3_tc2    weight gradient, version 2 (shared-halo regions, tap pairing for Cin = 64)
-// * k_first_conv_tc   Cin = 1 / 3 forward: im2col operand built in shared memory from bulk-copy-staged input runs
-// * k_first_wgrad_tc  Cin = 1 / 3 weight gradient (+ the input-BN / bias gradient columns), same staging
-// * k_pack_weights_batch  fp32 HWIO -> bf16 K-major operand rows, all layers in one launch
+// Kernels in this file:
+//   k_conv3x3_tc3         forward / dgrad: shared-halo A regions on CTA pairs (cta_group::2), coalescing epilogue with
+//                         per-configuration flavours EPI_* (BN statistics, fused BN + ReLU for inference, fp32 output)
+//   k_wgrad3x3_tc2        weight gradient: shared-halo regions, tap pairing for Cin = 64
+//   k_first_conv_tc       Cin = 1 / 3 forward: im2col operand built in shared memory from bulk-copy-staged input runs
+//   k_first_wgrad_tc      Cin = 1 / 3 weight gradient (+ the input-BN gradient columns), same staging
+//   k_pack_weights_batch  fp32 HWIO -> bf16 K-major operand rows, all layers in one launch
+// (Round 1's per-tap / single-CTA versions of the forward and weight-gradient kernels were retired in round 2.)
 //
 // Layout trick: every convolution input lives in a zero-haloed buffer (B,H+2,W+2,C).  Flattening (b,y,x) to one
 // row index m makes tap (ky,kx) of a 'same' 3x3 convolution a CONSTANT row shift (ky-1)*(W+2)+(kx-1), so the
@@ -276,440 +275,7 @@ int launch_pack_weights_tc(const float* w, bf16* packed, int Cin, int Cout, int 
 // ---------------------------------------------------------------------------------------------------------
 // forward / dgrad
 // ---------------------------------------------------------------------------------------------------------
-static const int kConvThreads = 192;
-static const int kBM = 128;
-static const int kAStageBytes = kBM * 128;  // 128 rows x 64 bf16
-
-template <int BN>
-struct ConvCfg {
-  static const int kBStageBytes = BN * 128;
-  static const int kStageBytes = kAStageBytes + kBStageBytes;
-  static const int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static const int kSmem = kStages * kStageBytes + 1024;
-  static const int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512: powers of two
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kConvThreads, 1)
-k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-             int num_m_tiles, int num_n_tiles) {
-  using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
-                 "n"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  const int KC = Cin >> 6;
-  const int k_iters = 9 * KC;
-  const int Wp = W + 2;
-  const int num_tiles = num_m_tiles * num_n_tiles;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * kBM;
-        const int n0 = (tile % num_n_tiles) * BN;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = (tap / 3 - 1) * Wp + (tap % 3 - 1);
-          for (int kc = 0; kc < KC; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(&tmA, &full_bar[stage], sa, kc * 64, m0 + shift);
-            tma_load_2d(&tmB, &full_bar[stage], sa + kAStageBytes, 0, (tap * KC + kc) * Cout + n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_addr(smem + stage * Cfg::kStageBytes);
-          const uint64_t a_desc = make_desc(sa, 16, 1024);
-          const uint64_t b_desc = make_desc(sa + kAStageBytes, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzled row
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ===== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global (interior pixels only) =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const long long HWp = (long long)(H + 2) * Wp;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m = (long long)(tile / num_n_tiles) * kBM + q * 32 + lane;
-      const int n0 = (tile % num_n_tiles) * BN;
-      bool valid = m < Mp;
-      bf16* optr = nullptr;
-      if (valid) {
-        const long long b = m / HWp;
-        const int r = (int)(m - b * HWp);
-        const int yp = r / Wp, xp = r - yp * Wp;
-        valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
-        optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]) + (bias ? __ldg(bias + n0 + c0 + j + i) : 0.f);
-            store8(optr + c0 + j, f);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
-  }
-}
-
-template <int BN>
-static int launch_conv_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, bf16* out, int H, int W,
-                          int Cin, int Cout, long long Mp, cudaStream_t s) {
-  using Cfg = ConvCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
-  }
-  int num_m = (int)((Mp + kBM - 1) / kBM), num_n = Cout / BN;
-  long long tiles = (long long)num_m * num_n;
-  int sms = 148;
-  int grid = (int)(tiles < sms ? tiles : sms);
-  k_conv3x3_tc<BN><<<grid, kConvThreads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n);
-  L3_CHECK_LAUNCH();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// forward / dgrad, version 2: shared-halo A regions
-// ---------------------------------------------------------------------------------------------------------
-// The three kx taps of one filter row read the SAME pixels shifted by one row of the flattened index, so one
-// shared-memory region of (MT*128 + 2) rows serves all three: the UMMA descriptor of tap kx simply starts kx rows
-// (kx*128 B) into the region (the 128-byte swizzle is a function of the absolute shared-memory address, so a
-// row-granular start is legal).  One CTA tile covers MT consecutive 128-row M tiles that share every weight tile.
-// Per (ky, 64-channel chunk) the CTA ingests (MT*128+8)*128 B of activations + 3*BN*128 B of weights for
-// 12*MT MMAs, instead of 3*(MT*16 KB + BN*128 B) -- 2-3x less L2->SMEM traffic per FLOP and 3*MT x fewer barrier
-// round trips per MMA than version 1, which is what the small-N layers (Cout 64/128) were bound by.
-template <int BN, int MT>
-struct Conv2Cfg {
-  static const int kARows = MT * kBM + 8;                 // region rows (multiple of 8 -> 1024-byte multiple)
-  static const int kABoxes = (MT == 4) ? 5 : (MT == 2 ? 3 : 1);
-  static const int kABoxRows = kARows / kABoxes;          // 104 / 88 / 136: multiples of 8
-  static const int kAStage = kARows * 128;
-  static const int kAStages = (MT == 4) ? 2 : (MT == 2 ? 3 : 4);
-  static const int kBStage = BN * 128;
-  static const int kBStages = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
-  static const int kSmem = kAStages * kAStage + kBStages * kBStage + 1024;
-  static const int kTmemCols = 2 * MT * BN;               // 512 for (64,4), (128,2), (256,1)
-};
-
-static const int kConv2Threads = 64 + 256;   // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
-
-template <int BN, int MT>
-__global__ void __launch_bounds__(kConv2Threads, 1)
-k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
-              int num_m_tiles, int num_n_tiles, double* __restrict__ stats, int relu_stats) {
-  using Cfg = Conv2Cfg<BN, MT>;
-  constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + AST * Cfg::kAStage;
-  __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tfull_bar[2], tempty_bar[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < AST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < BST; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
-                 "n"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  const int KC = Cin >> 6;
-  const int Wp = W + 2;
-  const int num_tiles = num_m_tiles * num_n_tiles;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * (MT * kBM);
-        const int n0 = (tile % num_n_tiles) * BN;
-        for (int kc = 0; kc < KC; ++kc)
-          for (int ky = 0; ky < 3; ++ky) {
-            mbar_wait(&a_empty[as], aph ^ 1);
-            uint8_t* sa = smem + as * Cfg::kAStage;
-            mbar_expect_tx(&a_full[as], Cfg::kAStage);
-            const int row0 = m0 + (ky - 1) * Wp - 1;
-#pragma unroll
-            for (int bx = 0; bx < Cfg::kABoxes; ++bx)
-              tma_load_2d(&tmA, &a_full[as], sa + bx * Cfg::kABoxRows * 128, kc * 64, row0 + bx * Cfg::kABoxRows);
-            if (++as == AST) { as = 0; aph ^= 1; }
-            for (int kx = 0; kx < 3; ++kx) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_expect_tx(&b_full[bs], Cfg::kBStage);
-              tma_load_2d(&tmB, &b_full[bs], smem_b + bs * Cfg::kBStage, 0, ((ky * 3 + kx) * KC + kc) * Cout + n0);
-              if (++bs == BST) { bs = 0; bph ^= 1; }
-            }
-          }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow so descriptors live in uniform
-    // registers; one elected lane issues tcgen05.mma / tcgen05.commit =====
-    constexpr uint32_t idesc = make_idesc(kBM, BN, 0, 0);
-    constexpr uint32_t hi = desc_hi(1024);
-    const bool leader = elect_one();
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t sa_base = smem_addr(smem), sb_base = smem_addr(smem_b);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-      uint32_t first = 1;
-      for (int it = 0; it < 3 * KC; ++it) {
-        mbar_wait(&a_full[as], aph);
-        const uint32_t a_lo0 = desc_lo(sa_base + as * Cfg::kAStage, 16);
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          mbar_wait(&b_full[bs], bph);
-          tc_fence_after();
-          const uint32_t b_lo0 = desc_lo(sb_base + bs * Cfg::kBStage, 16);
-          if (leader) {
-#pragma unroll
-            for (int t = 0; t < MT; ++t) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                // A rows start (t*128 + kx) rows = (t*128+kx)*8 sixteen-byte units into the region; k-step = 32 B = 2 units
-                const uint32_t a_lo = a_lo0 + (uint32_t)((t * kBM + kx) * 8 + k * 2);
-                umma_bf16_lh(d_tmem + t * BN, a_lo, hi, b_lo0 + (uint32_t)(k * 2), hi, idesc,
-                             (first && kx == 0 && k == 0) ? 0u : 1u);   // first MMA of each accumulator overwrites
-              }
-            }
-            umma_commit(&b_empty[bs]);
-          }
-          __syncwarp();
-          if (++bs == BST) { bs = 0; bph ^= 1; }
-        }
-        first = 0;
-        if (leader) umma_commit(&a_empty[as]);
-        __syncwarp();
-        if (++as == AST) { as = 0; aph ^= 1; }
-      }
-      if (leader) umma_commit(&tfull_bar[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  } else {
-    // ===== epilogue: TMEM -> regs -> (+bias) -> bf16 -> HBM, plus per-channel sum / sum-of-squares of the stored
-    // values (BatchNorm batch statistics) reduced across the 32 rows of a warp by a transposing butterfly =====
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the (m-tile, 32-column chunk) items
-    constexpr int NCH = BN / 32, NITEMS = MT * NCH, NST = NCH / 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const long long HWp = (long long)(H + 2) * Wp;
-    float st_sum[NST], st_sq[NST];   // lane i owns column c0 + i of this warp's chunks (ch = half, half+2, ...)
-#pragma unroll
-    for (int i = 0; i < NST; ++i) st_sum[i] = st_sq[i] = 0.f;
-    int st_n0 = -1;
-    auto flush_stats = [&]() {
-      if (stats != nullptr && st_n0 >= 0) {
-#pragma unroll
-        for (int i = 0; i < NST; ++i) {
-          const int col = st_n0 + (2 * i + half) * 32 + lane;
-          atomicAdd(&stats[col], (double)st_sum[i]);
-          atomicAdd(&stats[Cout + col], (double)st_sq[i]);
-          st_sum[i] = st_sq[i] = 0.f;
-        }
-      }
-    };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long mbase = (long long)(tile / num_n_tiles) * (MT * kBM) + q * 32 + lane;
-      const int n0 = (tile % num_n_tiles) * BN;
-      if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int it = 0; it < NITEMS / 2; ++it) {
-        // item = 2*it + half  ->  m-tile t = it / NST, chunk ch = 2*(it % NST) + half (NCH is even)
-        const int t = it / NST, chh = it % NST;
-        const int ch = 2 * chh + half;
-        const long long m = mbase + t * kBM;
-        bool valid = m < Mp;
-        bf16* optr = nullptr;
-        if (valid) {
-          const long long b = m / HWp;
-          const int r = (int)(m - b * HWp);
-          const int yp = r / Wp, xp = r - yp * Wp;
-          valid = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
-          optr = out + (((b * H + (yp - 1)) * W + (xp - 1)) * (long long)Cout + n0);
-        }
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN);
-        {
-          const int c0 = ch * 32;
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float f0 = __uint_as_float(v[2 * j]) + (bias ? __ldg(bias + n0 + c0 + 2 * j) : 0.f);
-            const float f1 = __uint_as_float(v[2 * j + 1]) + (bias ? __ldg(bias + n0 + c0 + 2 * j + 1) : 0.f);
-            pk[j] = pack_bf16x2(f0, f1);
-          }
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(optr + c0 + j * 8) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-          if (stats != nullptr) {
-            // statistics of the values as stored (bf16-rounded), zero for halo / out-of-range rows
-            float a[32], b2[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x0 = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-              float x1 = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
-              if (relu_stats) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              a[2 * j] = x0; a[2 * j + 1] = x1;
-              b2[2 * j] = x0 * x0; b2[2 * j + 1] = x1 * x1;
-            }
-            // transposing butterfly: after the 5 steps lane i holds the sum over the warp's 32 rows of column i
-#pragma unroll
-            for (int step = 0; step < 5; ++step) {
-              const int hv = 16 >> step;              // values kept per lane after this step
-              const bool upper = (lane >> (4 - step)) & 1;
-#pragma unroll
-              for (int j = 0; j < hv; ++j) {
-                const float send_a = upper ? a[j] : a[j + hv];
-                const float keep_a = upper ? a[j + hv] : a[j];
-                const float send_b = upper ? b2[j] : b2[j + hv];
-                const float keep_b = upper ? b2[j + hv] : b2[j];
-                a[j] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, 16 >> step);
-                b2[j] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, 16 >> step);
-              }
-            }
-            st_sum[chh] += a[0];
-            st_sq[chh] += b2[0];
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    flush_stats();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
-  }
-}
-
-template <int BN, int MT>
-static int launch_conv2(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
-                        int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s) {
-  using Cfg = Conv2Cfg<BN, MT>;
-  static bool configured = false;
-  if (!configured) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc2<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
-  }
-  CUtensorMap tmA, tmB;
-  if (make_tmap(&tmA, in, Cin, Mp, Cfg::kABoxRows)) return -1;
-  if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;
-  int num_m = (int)((Mp + MT * kBM - 1) / (MT * kBM)), num_n = Cout / BN;
-  long long tiles = (long long)num_m * num_n;
-  int grid = (int)(tiles < 148 ? tiles : 148);
-  if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
-  k_conv3x3_tc2<BN, MT><<<grid, kConv2Threads, Cfg::kSmem, s>>>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, num_m, num_n,
-                                                              stats, relu_stats);
-  L3_CHECK_LAUNCH();
-  return 0;
-}
+static const int kBM = 128;   // pixel rows of one UMMA M tile
 
 // ---------------------------------------------------------------------------------------------------------
 // forward / dgrad, version 3: CTA pairs (tcgen05 cta_group::2), N = 256
@@ -1234,10 +800,10 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
                         long long Mp, double* stats, int relu_stats, cudaStream_t s, BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   L3_REQUIRE(Cout <= kMaxCoutTc, "conv_tc: Cout=%d exceeds the bias staging buffer", Cout);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_conv3x3_tc3<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
+    once.mark();
   }
   CUtensorMap tmA, tmB;
   if (make_tmap(&tmA, in, Cin, Mp, Cfg::kABoxRows)) return -1;
@@ -1255,81 +821,38 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
   return 0;
 }
 
-// L3_CONV_EPI (statistics epilogue of the CTA-pair kernel): unset = per-configuration best (see launch_conv3_any);
-// carry (EPI_CARRY for Cout 64, EPI_SMEM for Cout 128), smem, butterfly, store (EPI_FWD2 everywhere) force one flavour
-// for A/B runs.  Cout % 256 == 0 layers have no shared memory to spare for EPI_SMEM.
-static int conv_epi_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_CONV_EPI");
-    v = 4;   // auto: the fastest flavour measured per tile configuration (profiles/r1_launches_step_detail.txt)
-    if (e && !strcmp(e, "smem")) v = 1;
-    else if (e && !strcmp(e, "butterfly")) v = 2;
-    else if (e && !strcmp(e, "carry")) v = 0;
-    else if (e && !strcmp(e, "store")) v = 3;
-  }
-  return v;
-}
 static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin,
                             int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s,
                             BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
 #define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s, bf)
-  const int mode = conv_epi_mode();
   if (bf.z == nullptr && bf.scale != nullptr) {   // inference: fused BatchNorm + ReLU epilogue
     L3_REQUIRE(stats == nullptr, "fused activation epilogue: no statistics");
     if (BN == 256) L3_GO(256, 1, EPI_ACT);
     if (BN == 128) L3_GO(128, 2, EPI_ACT);
     L3_GO(64, 4, EPI_ACT);
   }
-  if (bf.z != nullptr) {   // dgrad with fused BN-backward statistics
+  if (bf.z != nullptr) {   // dgrad with fused BN-backward statistics (stand-alone op; the step does not use it)
     L3_REQUIRE(stats != nullptr && bias == nullptr && !relu_stats, "fused dgrad statistics: stats, no bias, no relu_first");
     if (BN == 256) L3_GO(256, 1, EPI_BWD);
     if (BN == 128) L3_GO(128, 2, EPI_BWD);
     L3_GO(64, 4, EPI_BWD);
   }
-  if (mode == 3 && stats != nullptr) {
-    if (BN == 256) L3_GO(256, 1, EPI_FWD2);
-    if (BN == 128) L3_GO(128, 2, EPI_FWD2);
-    L3_GO(64, 4, EPI_FWD2);
+  if (stats == nullptr) {
+    if (BN == 256) L3_GO(256, 1, EPI_NONE);
+    if (BN == 128) L3_GO(128, 2, EPI_NONE);
+    L3_GO(64, 4, EPI_NONE);
   }
-  if (mode == 4 && stats != nullptr) {
-    // measured per launch (B = 64): BN 256: butterfly 127 us vs store-phase 136; BN 128: store-phase 138 vs smem 143;
-    // BN 64: carry 216 vs store-phase 225 vs smem 302
-    if (BN == 256) L3_GO(256, 1, EPI_BUTTERFLY);
-    if (BN == 128) L3_GO(128, 2, EPI_FWD2);
-    L3_GO(64, 4, EPI_CARRY);
-  }
-  if (BN == 256) {
-    if (stats == nullptr) L3_GO(256, 1, EPI_NONE);
-    L3_GO(256, 1, EPI_BUTTERFLY);
-  }
-  if (BN == 128) {
-    if (stats == nullptr) L3_GO(128, 2, EPI_NONE);
-    if (mode == 2) L3_GO(128, 2, EPI_BUTTERFLY);
-    L3_GO(128, 2, EPI_SMEM);
-  }
-  if (stats == nullptr) L3_GO(64, 4, EPI_NONE);
-  if (mode == 2) L3_GO(64, 4, EPI_BUTTERFLY);
-  if (mode == 1) L3_GO(64, 4, EPI_SMEM);
+  // statistics flavour per tile configuration, chosen by measurement (B = 64, us per launch): BN 256: butterfly 127 vs
+  // store-phase 136; BN 128: store-phase 138 vs shared-memory transposition 143; BN 64: carried 216 vs store-phase 225
+  if (BN == 256) L3_GO(256, 1, EPI_BUTTERFLY);
+  if (BN == 128) L3_GO(128, 2, EPI_FWD2);
   L3_GO(64, 4, EPI_CARRY);
 #undef L3_GO
 }
 
-// L3_CONV_TC_VARIANT: 1 = per-tap tiles (version 1), 2 = shared-halo regions, 3 = shared-halo regions on CTA
-// pairs (cta_group::2; default).  (Measured on B200: the
-// descriptor "base offset" field must stay 0 for row-shifted starts -- the swizzle is applied to absolute
-// shared-memory address bits; setting the field to (addr >> 7) & 7 produces wrong results.)
-static int conv_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_CONV_TC_VARIANT");
-    v = e ? atoi(e) : 3;
-    if (v < 1 || v > 3) v = 3;
-  }
-  return v;
-}
-
-int conv_tc_fuses_stats() { return conv_variant() >= 2; }
+// (Measured on B200: the UMMA descriptor "base offset" field must stay 0 for row-shifted operand starts -- the swizzle is
+// applied to absolute shared-memory address bits; setting the field to (addr >> 7) & 7 produces wrong results.)
+int conv_tc_fuses_stats() { return 1; }
 
 int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int B, int H, int W, int Cin,
                       int Cout, double* stats, int relu_stats, cudaStream_t s) {
@@ -1337,22 +860,7 @@ int launch_conv3x3_tc(const bf16* in, const bf16* packed_w, const float* bias, b
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
-  const int variant = conv_variant();
-  if (variant >= 2) {
-    if (variant == 3) {
-      return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-    }
-    if (BN == 256) return launch_conv2<256, 1>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-    if (BN == 128) return launch_conv2<128, 2>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-    return launch_conv2<64, 4>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
-  }
-  L3_REQUIRE(stats == nullptr, "conv_tc variant 1 has no fused statistics");
-  CUtensorMap tmA, tmB;
-  if (make_tmap(&tmA, in, Cin, Mp, kBM)) return -1;
-  if (make_tmap(&tmB, packed_w, 64, 9LL * (Cin / 64) * Cout, BN)) return -1;
-  if (BN == 256) return launch_conv_bn<256>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
-  if (BN == 128) return launch_conv_bn<128>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
-  return launch_conv_bn<64>(tmA, tmB, bias, out, H, W, Cin, Cout, Mp, s);
+  return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s);
 }
 
 // Inference forward with BatchNorm (scale / shift from the moving statistics) and ReLU in the epilogue (relu_first: the
@@ -1370,24 +878,16 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
   return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, nullptr, relu_first, s, bf);
 }
 
-int conv_tc_fuses_bwd_stats() {
-  static int v = -1;
-  if (v < 0) {
-    // default OFF: measured neutral at B = 64 (the fused launches cost what the separate k_bwd_stats launches saved:
-    // 356 vs 210 + 135 us at 64 channels, 206 vs 153 + 77 at 128, 178 vs ~170 + 45 at 256/512) -- the extra z loads sit
-    // on the epilogue's critical path; kept as a tested option
-    const char* e = getenv("L3_DGRAD_FUSE_STATS");
-    v = (e ? atoi(e) : 0) != 0 && conv_variant() == 3;
-  }
-  return v;
-}
+// Pass 1 of the BN/ReLU backward in the dgrad epilogue (EPI_BWD) measured neutral at B = 64 (356 us fused vs 210 + 135 us
+// separate at 64 channels: the extra z loads sit on the epilogue's critical path), so the step keeps the separate pass;
+// the fused launch stays available as a stand-alone, tested op (l3_conv3x3_dgrad_stats).
+int conv_tc_fuses_bwd_stats() { return 0; }
 
 int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
                                 const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
                                 cudaStream_t s) {
   // a conv with Cin' = Cout (of the layer), Cout' = Cin (= channels of the layer below)
   L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "dgrad_tc: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
-  L3_REQUIRE(conv_variant() == 3, "fused dgrad statistics need the CTA-pair kernel");
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
   const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
@@ -1404,147 +904,6 @@ int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da,
 // Per 32-pixel chunk the producer loads, for every block, two [32 px][64 ch] boxes of A (at the taps' row shifts) and
 // BN/64 boxes of dZ; both are MN-major UMMA operands.
 static const int kWgThreads = 192;
-static const int kWgChunk = 32;             // pixels (GEMM-K) per pipeline stage
-static const int kWgBox = kWgChunk * 128;   // bytes of one [32 px][64 ch] box
-
-template <bool PAIR>
-struct WgCfg {
-  static const int G = PAIR ? 5 : 3;
-  static const int BN = PAIR ? 64 : 128;
-  static const int kABytes = G * 2 * kWgBox;
-  static const int kBBytes = (BN / 64) * kWgBox;
-  static const int kStageBytes = kABytes + kBBytes;
-  static const int kStages = PAIR ? 4 : 6;
-  static const int kSmem = kStages * kStageBytes + 1024;
-  static const int kTmemCols = 512;
-};
-
-template <bool PAIR>
-__global__ void __launch_bounds__(kWgThreads, 1)
-k_wgrad3x3_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmZ, float* __restrict__ dw,
-              int W, int Cin, int Cout, int total_chunks, int chunks_per_slice) {
-  using Cfg = WgCfg<PAIR>;
-  constexpr int STAGES = Cfg::kStages, G = Cfg::G, BN = Cfg::BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar;
-  __shared__ uint32_t tmem_base_s;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tfull_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)),
-                 "n"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  // ---- unit decode ----
-  const int unit = blockIdx.x;
-  int cob, ci_base, ky;
-  if (PAIR) { cob = unit; ci_base = 0; ky = 0; }
-  else {
-    const int n_cob = Cout / BN;
-    ky = unit % 3;
-    cob = (unit / 3) % n_cob;
-    ci_base = (unit / 3 / n_cob) * 128;
-  }
-  const int co0 = cob * BN;
-  const int Wp = W + 2;
-  const int c_begin = blockIdx.y * chunks_per_slice;
-  const int c_end = min(total_chunks, c_begin + chunks_per_slice);
-  // sub-block (j, h) -> tap and first input channel
-  auto sub_tap = [&](int j, int h) -> int { return PAIR ? min(2 * j + h, 8) : ky * 3 + j; };
-  auto sub_ci = [&](int h) -> int { return PAIR ? 0 : ci_base + h * 64; };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        const int m = c * kWgChunk;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int tap = sub_tap(j, h);
-            const int shift = (tap / 3 - 1) * Wp + (tap % 3 - 1);
-            tma_load_2d(&tmA, &full_bar[stage], sa + (j * 2 + h) * kWgBox, sub_ci(h), m + shift);
-          }
-#pragma unroll
-        for (int nb = 0; nb < BN / 64; ++nb)
-          tma_load_2d(&tmZ, &full_bar[stage], sa + Cfg::kABytes + nb * kWgBox, co0 + nb * 64, m);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_addr(smem + stage * Cfg::kStageBytes);
-#pragma unroll
-        for (int j = 0; j < G; ++j)
-#pragma unroll
-          for (int ks = 0; ks < kWgChunk / 16; ++ks) {   // 16 pixels per UMMA = two 8-row swizzle atoms (2048 B)
-            const uint64_t a_desc = make_desc(sa + (j * 2) * kWgBox + ks * 2048, kWgBox, 1024);
-            const uint64_t b_desc = make_desc(sa + Cfg::kABytes + ks * 2048, kWgBox, 1024);
-            umma_bf16(tmem_base + j * BN, a_desc, b_desc, idesc, (c > c_begin || ks > 0) ? 1u : 0u);
-          }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(&tfull_bar);
-    }
-  } else if (c_end > c_begin) {
-    // ===== epilogue: fp32 accumulators -> atomicAdd into dw[tap][ci][co] =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;   // accumulator row = h*64 + channel
-    const int h = row >> 6;
-    mbar_wait(&tfull_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int j = 0; j < G; ++j) {
-      const int tap = sub_tap(j, h);
-      const bool dup = PAIR && (2 * j + h > 8);
-      const int ci = sub_ci(h) + (row & 63);
-      float* dst = dw + ((long long)tap * Cin + ci) * Cout + co0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + c0), v);
-        tmem_ld_wait();
-        if (!dup) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                       __uint_as_float(v[i + 3]));
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
-  }
-}
-
 // ---- weight gradient, version 2: shared-halo regions -------------------------------------------------------
 // Per 64-pixel chunk a CTA loads, per filter row ky, ONE region of 72 pixel rows x 64 channels; the three kx taps
 // are UMMA descriptors starting kx rows into it (MN-major: one pixel = one 128-byte row, so a pixel shift is a
@@ -1706,10 +1065,10 @@ template <bool PAIR>
 static int launch_wgrad2_cfg(const bf16* a, const bf16* dz, float* dw, int W, int Cin, int Cout, long long Mp,
                              cudaStream_t s) {
   using Cfg = Wg2Cfg<PAIR>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad3x3_tc2<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
+    once.mark();
   }
   CUtensorMap tmA, tmZ;
   if (make_tmap(&tmA, a, Cin, Mp, kWg2RegionRows)) return -1;
@@ -1726,16 +1085,6 @@ static int launch_wgrad2_cfg(const bf16* a, const bf16* dz, float* dw, int W, in
   k_wgrad3x3_tc2<PAIR><<<grid, kWgThreads, Cfg::kSmem, s>>>(tmA, tmZ, dw, W, Cin, Cout, total_chunks, cps);
   L3_CHECK_LAUNCH();
   return 0;
-}
-
-static int wgrad_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("L3_WGRAD_TC_VARIANT");
-    v = e ? atoi(e) : 2;
-    if (v < 1 || v > 2) v = 2;
-  }
-  return v;
 }
 
 // ---- raw input staging for the first-layer kernels ----------------------------------------------------------
@@ -2018,11 +1367,11 @@ int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db,
   if (d1) L3_CHECK_CUDA(cudaMemsetAsync(d1, 0, sizeof(float) * 9 * 64, s));
   L3_REQUIRE(((uintptr_t)xin & 15) == 0, "first_wgrad_tc: input must be 16-byte aligned (bulk copies)");
   const int smem = kFwStages * 2 * kFwTile + kFwRawStages * RawCfg<3, 64>::kStage + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_wgrad_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_wgrad_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    once.mark();
   }
   CUtensorMap tmZ;
   if (make_tmap(&tmZ, dz, 64, Mp, 64)) return -1;
@@ -2296,11 +1645,11 @@ int launch_first_conv_tc(const bf16* xin, const float* w, const float* bias, bf1
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 1024 < 0x7fffffffLL && Mp >= 3, "first_conv_tc: pixel count out of range");
   L3_REQUIRE(((uintptr_t)xin & 15) == 0, "first_conv_tc: input must be 16-byte aligned (bulk copies)");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<1>::kSmem));
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_first_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<3>::kSmem));
-    configured = true;
+    once.mark();
   }
   if (stats) L3_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s));
   const int num_tiles = (int)((Mp + kBM - 1) / kBM);
@@ -2338,47 +1687,14 @@ __global__ void k_bias_grad(const bf16* __restrict__ dz, long long rows, int C, 
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sh[i]);
 }
 
-template <bool PAIR>
-static int launch_wgrad_cfg(const CUtensorMap& tmA, const CUtensorMap& tmZ, float* dw, int W, int Cin, int Cout,
-                            long long Mp, cudaStream_t s) {
-  using Cfg = WgCfg<PAIR>;
-  static bool configured = false;
-  if (!configured) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_wgrad3x3_tc<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
-  }
-  const int units = PAIR ? Cout / Cfg::BN : (Cin / 128) * (Cout / Cfg::BN) * 3;
-  const int total_chunks = (int)((Mp + kWgChunk - 1) / kWgChunk);
-  // enough slices for ~2 waves of 148 CTAs, but at least 16 chunks of work per slice
-  int slices = (2 * 148 + units - 1) / units;
-  int max_slices = (total_chunks + 15) / 16;
-  if (slices > max_slices) slices = max_slices;
-  if (slices < 1) slices = 1;
-  int cps = (total_chunks + slices - 1) / slices;
-  slices = (total_chunks + cps - 1) / cps;
-  dim3 grid(units, slices);
-  k_wgrad3x3_tc<PAIR><<<grid, kWgThreads, Cfg::kSmem, s>>>(tmA, tmZ, dw, W, Cin, Cout, total_chunks, cps);
-  L3_CHECK_LAUNCH();
-  return 0;
-}
-
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                        cudaStream_t s) {
   L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && (Cin == 64 || Cin % 128 == 0) && (Cin == 64 || Cout % 128 == 0),
              "wgrad_tc: unsupported channels Cin=%d Cout=%d", Cin, Cout);
   const long long Mp = (long long)B * (H + 2) * (W + 2);
   L3_REQUIRE(Mp + 4LL * (W + 2) < 0x7fffffffLL, "wgrad_tc: too many pixels for 32-bit TMA coordinates");
-  int rc;
-  if (wgrad_variant() == 2) {
-    rc = (Cin == 64) ? launch_wgrad2_cfg<true>(a, dz, dw, W, Cin, Cout, Mp, s)
-                     : launch_wgrad2_cfg<false>(a, dz, dw, W, Cin, Cout, Mp, s);
-  } else {
-    CUtensorMap tmA, tmZ;
-    if (make_tmap(&tmA, a, Cin, Mp, kWgChunk)) return -1;
-    if (make_tmap(&tmZ, dz, Cout, Mp, kWgChunk)) return -1;
-    rc = (Cin == 64) ? launch_wgrad_cfg<true>(tmA, tmZ, dw, W, Cin, Cout, Mp, s)
-                     : launch_wgrad_cfg<false>(tmA, tmZ, dw, W, Cin, Cout, Mp, s);
-  }
+  const int rc = (Cin == 64) ? launch_wgrad2_cfg<true>(a, dz, dw, W, Cin, Cout, Mp, s)
+                             : launch_wgrad2_cfg<false>(a, dz, dw, W, Cin, Cout, Mp, s);
   if (rc) return rc;
   if (db) {
     L3_REQUIRE(256 % (Cout / 8) == 0, "bias_grad: Cout=%d", Cout);

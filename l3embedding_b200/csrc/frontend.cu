@@ -332,10 +332,10 @@ static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out
   size_t stage_elems = (size_t)(kFramesPerCta - 1) * p.n_hop + N + 16;
   size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + (size_t)N * 4 + kFramesPerCta * (size_t)(NF + 3) * 4 +
                 (size_t)p.n_out * kFramesPerCta * 4 + (size_t)p.mel_nnz * 4 + 16 + stage_elems * ES;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    once.mark();
   }
   L3_REQUIRE(smem <= 200 * 1024, "frontend smem %zu too large", smem);
   dim3 grid(ceil_div(p.n_frames, kFramesPerCta), B);

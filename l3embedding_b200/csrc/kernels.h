@@ -156,7 +156,7 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
 // Data gradient of a conv (Cin -> Cout) on tensor cores with pass 1 of the BN/ReLU backward of the layer BELOW fused
 // into the epilogue: da (B,H,W,Cin) = conv(dz, packed_wt); sums[0..Cin) = sum(dy), sums[Cin..2Cin) = sum(dy * z_below)
 // with dy = da where scale*z_below + shift > 0 (the layer below is Conv -> BN -> ReLU, not pooled); sums are zeroed here.
-int conv_tc_fuses_bwd_stats();   // L3_DGRAD_FUSE_STATS=1 (default 0: measured neutral) and the CTA-pair variant
+int conv_tc_fuses_bwd_stats();   // 0: measured neutral, the step keeps the separate statistics pass (stand-alone op only)
 int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
                                 const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
                                 cudaStream_t s);
