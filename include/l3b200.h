@@ -22,8 +22,14 @@ extern "C" {
 
 /* l3embedding/model.py:307-313 MODELS keys (tiny_L3 is non-functional upstream and not provided) */
 enum { L3_MODEL_ORIG = 0, L3_MODEL_KAPREDBINPUTBN = 1, L3_MODEL_MELSPEC1 = 2, L3_MODEL_MELSPEC2 = 3 };
-/* activation storage / conv operand precision: F32 = parity mode (SIMT fp32), BF16 = throughput mode (tcgen05) */
-enum { L3_DTYPE_F32 = 0, L3_DTYPE_BF16 = 1 };
+/* activation storage / conv operand precision:
+ *   F32   = parity mode, fp32 storage, SIMT fp32 convolutions (run-to-run deterministic);
+ *   BF16  = throughput mode, bf16 storage, tcgen05 convolutions with fp32 accumulation;
+ *   F32TC = parity mode ON TENSOR CORES: fp32 storage, the Cin%64==0 convolutions run on tcgen05 with every fp32 operand
+ *           split into two 16-bit parts concatenated along K (forward: fp16 parts, 22 significant bits, weights pre-scaled
+ *           by 2^10; backward: bf16 parts, fp32's range) and fp32 accumulation -- meets the 1e-3 embedding bar of the
+ *           reference comparison at several times the SIMT mode's speed (activations must stay below 65504) */
+enum { L3_DTYPE_F32 = 0, L3_DTYPE_BF16 = 1, L3_DTYPE_F32TC = 2 };
 /* input formats */
 enum { L3_VIDEO_U8 = 0, L3_VIDEO_F32 = 1 };   /* u8 raw frames (scaled on device, train.py:186) | f32 in [-1,1] */
 enum { L3_AUDIO_I16 = 0, L3_AUDIO_F32 = 1 };  /* int16 PCM (pcm2float on device, audio.py:21-31) | f32 in [-1,1) */

@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libl3b200.so")
 
 MODEL_IDS = {"cnn_L3_orig": 0, "cnn_L3_kapredbinputbn": 1, "cnn_L3_melspec1": 2, "cnn_L3_melspec2": 3}
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F32TC = 0, 1, 2
+DTYPES = {"f32": DTYPE_F32, "bf16": DTYPE_BF16, "f32tc": DTYPE_F32TC}
 VIDEO_U8, VIDEO_F32 = 0, 1
 AUDIO_I16, AUDIO_F32 = 0, 1
 WS_TRAINING, WS_VISION, WS_AUDIO, WS_HOST_STAGING = 1, 2, 4, 8

@@ -158,7 +158,9 @@ struct ConvLayer {
   float* w_t;               // flipped/transposed fp32 kernel for dgrad-as-conv (SIMT path)
   bf16* w_pk;               // tcgen05 operand packs (forward, dgrad)
   bf16* wt_pk;
-  int tc;                   // this layer runs on the tcgen05 path
+  int tc;                   // this layer runs on the tcgen05 path (bf16 throughput mode)
+  int tcs;                  // this layer runs on the tcgen05 path with SPLIT 16-bit operands and fp32 storage (parity mode
+                            // L3_DTYPE_F32TC): w_pk = fp16 parts [hi ; hi ; lo] of 2^10 * w, wt_pk = bf16 parts (dgrad)
 };
 struct Tower {
   int present;
@@ -171,6 +173,9 @@ struct Tower {
   int* argmax;  // (B,512)
   unsigned long long* pool_scratch;  // (B,512) packed (value, ~index) keys of the global max-pool
   float* d1;    // 9*64 floats + 1 int flag: first-layer "ones" weight gradient for the input-BN backward
+  void* sp_a;     // L3_DTYPE_F32TC: split operand buffers, (B,H+2,W+2,3*C) 16-bit parts of a convolution input / of dz
+  void* sp_z;
+  float* dw4;     //   and the 2Cin x 2Cout weight-gradient scratch of launch_wgrad3x3_tc_split
   double* wg64;   // parity mode (f32), training: fp64 merge scratch of the weight-gradient kernels (one launch at a time
   double* wg64_0; //   per stream: the side stream's layers share wg64, the first layer on the main stream has wg64_0)
   int concat_off;
@@ -311,7 +316,7 @@ static long long carve(l3_ctx* c) {
     c->st_labels[sl] = on ? (float*)bp.take(B * 2 * 4) : nullptr;
   }
   for (int t = 0; t < 2; ++t) {
-    long long g0_max = 0, g1_max = 0;
+    long long g0_max = 0, g1_max = 0, spa_max = 0, spz_max = 0, dw4_max = 0;
     Tower& tw = t == 0 ? c->vision : c->audio;
     tw.present = (c->flags & (t == 0 ? L3_WS_VISION : L3_WS_AUDIO)) ? 1 : 0;
     tw.C0 = t == 0 ? 3 : 1;
@@ -342,18 +347,29 @@ static long long carve(l3_ctx* c) {
       L.sel = rec ? (uint8_t*)bp.take(B * OH * OW * L.Cout) : nullptr;
       L.w_t = training ? (float*)bp.take(4LL * 9 * L.Cin * L.Cout) : nullptr;
       L.tc = (c->dtype == L3_DTYPE_BF16 && L.Cin % 64 == 0 && L.Cout % 64 == 0) ? 1 : 0;
-      L.w_pk = L.tc ? (bf16*)bp.take(2LL * 9 * L.Cin * L.Cout) : nullptr;
-      L.wt_pk = (L.tc && training) ? (bf16*)bp.take(2LL * 9 * L.Cin * L.Cout) : nullptr;
+      L.tcs = (c->dtype == L3_DTYPE_F32TC && L.Cin % 64 == 0 && L.Cout % 64 == 0) ? 1 : 0;
+      const long long pk = 2LL * 9 * L.Cin * L.Cout * (L.tcs ? 3 : 1);
+      L.w_pk = (L.tc || L.tcs) ? (bf16*)bp.take(pk) : nullptr;
+      L.wt_pk = ((L.tc || L.tcs) && training) ? (bf16*)bp.take(pk) : nullptr;
       long long dz = B * (H + 2) * (W + 2) * L.Cout, da = B * H * W * L.Cin;
       if (dz > g0_max) g0_max = dz;
       if (da > g1_max) g1_max = da;
+      if (L.tcs) {
+        const long long a3 = B * (H + 2) * (W + 2) * 3 * L.Cin, w4 = 9LL * 4 * L.Cin * L.Cout;
+        if (a3 > spa_max) spa_max = a3;
+        if (3 * dz > spz_max) spz_max = 3 * dz;
+        if (w4 > dw4_max) dw4_max = w4;
+      }
       prev = L.a;
       H = OH; W = OW;
     }
     tw.argmax = (int*)bp.take(4 * B * 512);
     tw.pool_scratch = (unsigned long long*)bp.take(8 * B * 512);
     tw.d1 = (float*)bp.take(4 * (9 * 64 + 4));
-    const bool f64_merge = training && c->dtype == L3_DTYPE_F32;
+    tw.sp_a = spa_max ? bp.take(2 * spa_max) : nullptr;
+    tw.sp_z = (spz_max && training) ? bp.take(2 * spz_max) : nullptr;
+    tw.dw4 = (dw4_max && training) ? (float*)bp.take(4 * dw4_max) : nullptr;
+    const bool f64_merge = training && c->dtype != L3_DTYPE_BF16;
     tw.wg64 = f64_merge ? (double*)bp.take(8LL * (9 * 512 * 512 + 512)) : nullptr;
     tw.wg64_0 = f64_merge ? (double*)bp.take(8LL * (9 * 3 * 64 + 10 * 64)) : nullptr;
     tw.g0 = training ? bp.take(es * g0_max) : nullptr;
@@ -418,8 +434,10 @@ static const int kBnUnbiasedMoving = 1;                  // TF fused batch norm 
 
 
 // want_stats: training-mode BN statistics of the output; *stats_done tells the caller they were fused
+static const float kSplitWeightScale = 1024.f, kSplitWeightScaleInv = 1.f / 1024.f;   // exact powers of two
+
 template <typename T>
-static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done, cudaStream_t s) {
+static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* stats_done, cudaStream_t s, void* tw_sp_a) {
   ProfScope ps(c, PROF_CONV_FWD, s);
   *stats_done = false;
   if (L.tc && c->use_tc) {
@@ -427,6 +445,13 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* s
     *stats_done = fuse;
     return launch_conv3x3_tc((const bf16*)L.in, L.w_pk, L.b, (bf16*)L.z, B, L.H, L.W, L.Cin, L.Cout,
                              fuse ? L.bn.sum : nullptr, L.relu_first, s);
+  }
+  if (L.tcs && c->use_tc) {
+    // parity mode on tensor cores: fp16 parts of the fp32 input, weights pre-scaled by 2^10 (kept inside fp16's normal
+    // range), fp32 accumulate and output; the BN statistics are taken by the caller from the fp32 tensor
+    const long long rows_p = (long long)B * (L.H + 2) * (L.W + 2);
+    if (launch_split16((const float*)L.in, tw_sp_a, rows_p, L.Cin, 1, s)) return -1;
+    return launch_conv3x3_tc_split(tw_sp_a, L.w_pk, L.b, (float*)L.z, B, L.H, L.W, L.Cin, L.Cout, 1, kSplitWeightScaleInv, s);
   }
   if (L.Cin <= 3 && L.Cout == 64 && c->use_tc && c->dtype == L3_DTYPE_BF16) {
     *stats_done = want_stats;
@@ -502,7 +527,7 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
         return -1;
       continue;
     }
-    if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done, s)) return -1;
+    if (conv_forward<T>(c, L, B, training && !(l == 7 && embed_only), &stats_done, s, tw.sp_a)) return -1;
     if (l == 7 && embed_only) return 0;  // raw conv4b output incl. bias, before BN/ReLU (audio_model.py:482)
     long long rows = (long long)B * L.H * L.W;
     if (training && !stats_done && launch_channel_stats<T>((const T*)L.z, rows, L.Cout, L.relu_first, L.bn.sum, s)) return -1;
@@ -529,7 +554,8 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
 // two events per buffer: ev_dz (dz(l) complete -> wgrad(l) may read it) and ev_wg (wgrad(l) done -> the BN/ReLU
 // backward of layer l-2 may overwrite the buffer)
 static bool tower_defers_wgrad(l3_ctx* c, Tower& tw) {
-  return tw.wstream != nullptr && c->wgrad_streams && c->two_streams && tw.stream != c->stream;
+  // (the split-operand parity mode shares one pair of operand buffers per tower: its weight gradients stay in stream order)
+  return tw.wstream != nullptr && c->wgrad_streams && c->two_streams && tw.stream != c->stream && c->dtype != L3_DTYPE_F32TC;
 }
 
 template <typename T>
@@ -576,7 +602,17 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
     }
     {
       ProfScope ps(c, PROF_CONV_WGRAD, sw);
-      if (L.tc && c->use_tc) {
+      if (L.tcs && c->use_tc) {
+        // parity mode on tensor cores: bf16 parts of both operands (gradients need fp32's range), all four part products
+        const long long rows_p = (long long)B * (L.H + 2) * (L.W + 2);
+        if (launch_split16((const float*)dz, tw.sp_z, rows_p, L.Cout, 0, sw)) return -1;   // also the dgrad operand below
+        if (launch_split16((const float*)L.in, tw.sp_a, rows_p, L.Cin, 0, sw)) return -1;
+        if (launch_wgrad3x3_tc_split(tw.sp_a, tw.sp_z, L.dw, tw.dw4, B, L.H, L.W, L.Cin, L.Cout, sw)) return -1;
+        if (L.relu_first) {   // the one Conv -> ReLU -> BN layer: its bias gradient is not identically zero
+          if (launch_channel_stats<float>((const float*)dz, rows_p, L.Cout, 0, tw.wg64, sw)) return -1;
+          if (launch_f64_to_f32(tw.wg64, L.db, L.Cout, sw)) return -1;
+        }
+      } else if (L.tc && c->use_tc) {
         // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
         // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
         if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
@@ -629,7 +665,10 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
   ConvLayer& Lp = tw.L[l - 1];
   {
     ProfScope ps(c, PROF_CONV_DGRAD, s);
-    if (L.tc && c->use_tc) {
+    if (L.tcs && c->use_tc) {
+      // sp_z holds the bf16 parts of dz (split for the weight gradient above, same stream)
+      if (launch_conv3x3_tc_split(tw.sp_z, L.wt_pk, nullptr, (float*)da, B, L.H, L.W, L.Cout, L.Cin, 0, 1.f, s)) return -1;
+    } else if (L.tc && c->use_tc) {
       if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
     } else {
       if (launch_flip_transpose(L.w, L.w_t, L.Cin, L.Cout, s)) return -1;
@@ -715,6 +754,17 @@ static int pack_all_weights(l3_ctx* c, bool vision, bool audio, bool with_dgrad,
     if (!tw.present || !(t == 0 ? vision : audio)) continue;
     for (int l = 0; l < 8; ++l) {
       ConvLayer& L = tw.L[l];
+      if (L.tcs) {
+        PackJob f{L.w, L.w_pk, L.Cin, L.Cout, 0};
+        f.split = 1; f.fp16 = 1; f.scale = kSplitWeightScale;
+        pb.job[pb.n++] = f;
+        if (with_dgrad && L.wt_pk) {
+          PackJob d{L.w, L.wt_pk, L.Cin, L.Cout, 1};
+          d.split = 1;
+          pb.job[pb.n++] = d;
+        }
+        continue;
+      }
       if (!L.tc) continue;
       pb.job[pb.n++] = PackJob{L.w, L.w_pk, L.Cin, L.Cout, 0};
       if (with_dgrad && L.wt_pk) pb.job[pb.n++] = PackJob{L.w, L.wt_pk, L.Cin, L.Cout, 1};
@@ -845,7 +895,7 @@ int l3_embedding_map_shape(int m, int* h, int* w) {
 
 int64_t l3_workspace_bytes(int model_type, int max_batch, int dtype, int flags) {
   if (!valid_model(model_type)) return -2;
-  if (max_batch < 1 || (dtype != L3_DTYPE_F32 && dtype != L3_DTYPE_BF16)) {
+  if (max_batch < 1 || (dtype != L3_DTYPE_F32 && dtype != L3_DTYPE_BF16 && dtype != L3_DTYPE_F32TC)) {
     set_error("bad max_batch %d / dtype %d", max_batch, dtype);
     return -2;
   }
@@ -919,7 +969,12 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
   c->ws_bytes = workspace_bytes;
   c->stream = (cudaStream_t)stream;
   c->adam_t = 0;
-  c->use_tc = (dtype == L3_DTYPE_BF16) && conv_tc_supported();
+  c->use_tc = (dtype != L3_DTYPE_F32) && conv_tc_supported();
+  if (dtype == L3_DTYPE_F32TC && !c->use_tc) {
+    set_error("L3_DTYPE_F32TC needs the tcgen05 path (sm_100)");
+    delete c;
+    return nullptr;
+  }
   c->fuse_inference = 1;
   c->device = 0;
   cudaGetDevice(&c->device);
@@ -1057,7 +1112,8 @@ int l3_ctx_profile_read(l3_ctx* c, float ms_out[4], int launches_out[4]) {
 
 int l3_ctx_set_use_tensor_cores(l3_ctx* c, int enable) {
   L3_REQUIRE(c != nullptr, "null ctx");
-  L3_REQUIRE(!enable || (c->dtype == L3_DTYPE_BF16 && conv_tc_supported()), "tensor-core path needs a bf16 context on sm_100");
+  L3_REQUIRE(!enable || (c->dtype != L3_DTYPE_F32 && conv_tc_supported()), "tensor-core path needs a bf16 / f32tc context on sm_100");
+  L3_REQUIRE(enable || c->dtype != L3_DTYPE_F32TC, "an f32tc context has no SIMT fallback for its split layers: use L3_DTYPE_F32");
   c->use_tc = enable ? 1 : 0;
   return 0;
 }
@@ -1379,9 +1435,48 @@ int l3_frontend_fwd(l3_ctx* c, const void* audio, int audio_fmt, int n, float* o
 }
 
 // ---- stand-alone ops (unit tests) -------------------------------------------------------------------------
+namespace {
+// stream-ordered temporary
+struct TempBuf {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    L3_CHECK_CUDA(cudaMallocAsync(&p, bytes, s));
+    return 0;
+  }
+  ~TempBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+// L3_DTYPE_F32TC forward (flip = 0: fp16 parts, weights x 2^10) / data gradient (flip = 1: bf16 parts) of one layer
+int conv_split_op(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
+                  int flip, cudaStream_t s) {
+  L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "split conv: C%%64");
+  const int Ci = flip ? Cout : Cin, Co = flip ? Cin : Cout;   // channels of the convolution that actually runs
+  const long long rows_p = (long long)B * (H + 2) * (W + 2);
+  TempBuf sp, pk;
+  if (sp.alloc((size_t)rows_p * 3 * Ci * 2, s) || pk.alloc((size_t)9 * 3 * Ci * Co * 2, s)) return -1;
+  PackBatch pb;
+  pb.n = 1;
+  pb.job[0] = PackJob{w, (bf16*)pk.p, Cin, Cout, flip};
+  pb.job[0].split = 1;
+  pb.job[0].fp16 = flip ? 0 : 1;
+  pb.job[0].scale = flip ? 1.f : kSplitWeightScale;
+  if (launch_pack_weights_batch(pb, s)) return -1;
+  if (launch_split16(in, sp.p, rows_p, Ci, flip ? 0 : 1, s)) return -1;
+  return launch_conv3x3_tc_split(sp.p, pk.p, bias, out, B, H, W, Ci, Co, flip ? 0 : 1, flip ? 1.f : kSplitWeightScaleInv, s);
+}
+}  // namespace
+
 int l3_conv3x3_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin, int Cout,
                    int dtype, int use_tc, void* scratch, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == L3_DTYPE_F32TC) {
+    L3_REQUIRE(use_tc, "L3_DTYPE_F32TC is a tensor-core mode");
+    return conv_split_op((const float*)in, w, bias, (float*)out, B, H, W, Cin, Cout, 0, s);
+  }
   if (use_tc && (Cin == 1 || Cin == 3)) {
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cout == 64, "tc first-layer conv: bf16, Cout 64");
     L3_REQUIRE(conv_tc_supported(), "tcgen05 path unavailable on this device");
@@ -1413,6 +1508,10 @@ int l3_conv3x3_fwd_stats(const void* in, const float* w, const float* bias, void
 int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
                      int use_tc, void* scratch, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == L3_DTYPE_F32TC) {
+    L3_REQUIRE(use_tc, "L3_DTYPE_F32TC is a tensor-core mode");
+    return conv_split_op((const float*)dz, w, nullptr, (float*)da, B, H, W, Cin, Cout, 1, s);
+  }
   L3_REQUIRE(scratch, "dgrad needs scratch of 9*Cin*Cout floats");
   if (use_tc) {
     L3_REQUIRE(dtype == L3_DTYPE_BF16 && Cin % 64 == 0 && Cout % 64 == 0, "tc dgrad: bf16, C%%64");
@@ -1438,6 +1537,23 @@ int l3_conv3x3_dgrad_stats(const void* dz, const float* w, void* da, int B, int 
 int l3_conv3x3_wgrad(const void* a, const void* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                      int dtype, int use_tc, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == L3_DTYPE_F32TC) {
+    L3_REQUIRE(use_tc && conv_tc_supported(), "L3_DTYPE_F32TC is a tensor-core mode (sm_100)");
+    L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "split wgrad: C%%64");
+    const long long rows_p = (long long)B * (H + 2) * (W + 2);
+    TempBuf spa, spz, w4, s64;
+    if (spa.alloc((size_t)rows_p * 3 * Cin * 2, s) || spz.alloc((size_t)rows_p * 3 * Cout * 2, s) ||
+        w4.alloc(sizeof(float) * 9 * 4 * (size_t)Cin * Cout, s) || s64.alloc(sizeof(double) * 2 * Cout, s))
+      return -1;
+    if (launch_split16((const float*)a, spa.p, rows_p, Cin, 0, s)) return -1;
+    if (launch_split16((const float*)dz, spz.p, rows_p, Cout, 0, s)) return -1;
+    if (launch_wgrad3x3_tc_split(spa.p, spz.p, dw, (float*)w4.p, B, H, W, Cin, Cout, s)) return -1;
+    if (db) {
+      if (launch_channel_stats<float>((const float*)dz, rows_p, Cout, 0, (double*)s64.p, s)) return -1;
+      if (launch_f64_to_f32((const double*)s64.p, db, Cout, s)) return -1;
+    }
+    return 0;
+  }
   L3_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * Cin * Cout, s));
   if (db) L3_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Cout, s));
   if (use_tc && (Cin == 1 || Cin == 3)) {

@@ -24,6 +24,7 @@
 //   both operands are "MN-major" (channels contiguous), which UMMA reads directly from the same TMA boxes;
 //   split-K over pixel slices with fp32 vector reductions into dW.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 #include "kernels.h"
@@ -234,13 +235,27 @@ __global__ void k_pack_weights(const float* __restrict__ w, bf16* __restrict__ o
     out[i] = __float2bfloat16_rn(v);
   }
 }
-// all layers of a step in one launch: blockIdx.y = job
+// 16-bit hi / lo parts of x: x ~ hi + lo with hi = round16(x), lo = round16(x - hi)
+__device__ __forceinline__ unsigned short part16(float x, int which, int fp16) {
+  if (fp16) {
+    const __half h = __float2half_rn(x);
+    const __half r = which ? __float2half_rn(x - __half2float(h)) : h;
+    return *reinterpret_cast<const unsigned short*>(&r);
+  }
+  const bf16 h = __float2bfloat16_rn(x);
+  const bf16 r = which ? __float2bfloat16_rn(x - __bfloat162float(h)) : h;
+  return *reinterpret_cast<const unsigned short*>(&r);
+}
+// all layers of a step in one launch: blockIdx.y = job.  split jobs (parity mode on tensor cores) write the operand of a
+// convolution with 3*Ci input channels: segments [hi ; hi ; lo] of scale * w, as fp16 or bf16 parts
 __global__ void k_pack_weights_batch(PackBatch pb) {
   const PackJob j = pb.job[blockIdx.y];
   const int Cin = j.Cin, Cout = j.Cout, flip = j.flip;
   const int Ci = flip ? Cout : Cin, Co = flip ? Cin : Cout;
-  const int KC = Ci / 64;
-  const long long n = 9LL * Ci * Co;
+  const int Cik = j.split ? 3 * Ci : Ci;      // channels of the kernel's K axis
+  const int KC = Cik / 64;
+  const long long n = 9LL * Cik * Co;
+  unsigned short* const out16 = reinterpret_cast<unsigned short*>(j.out);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int cil = (int)(i & 63);
     long long r = i >> 6;
@@ -248,9 +263,11 @@ __global__ void k_pack_weights_batch(PackBatch pb) {
     long long r2 = r / Co;
     int kc = (int)(r2 % KC);
     int tap = (int)(r2 / KC);
-    int ci = kc * 64 + cil;
+    int cik = kc * 64 + cil;
+    const int seg = cik / Ci, ci = cik - seg * Ci;
     float v = flip ? j.w[((long long)(8 - tap) * Cin + co) * Cout + ci] : j.w[((long long)tap * Cin + ci) * Cout + co];
-    j.out[i] = __float2bfloat16_rn(v);
+    if (j.split) out16[i] = part16(v * j.scale, seg == 2 ? 1 : 0, j.fp16);
+    else j.out[i] = __float2bfloat16_rn(v);
   }
 }
 int launch_pack_weights_batch(const PackBatch& pb, cudaStream_t s) {
@@ -299,6 +316,8 @@ enum { EPI_NONE = 0,        // no statistics (dgrad, inference): leanest registe
                             // partials per lane and chunk, carried over the tiles; works for every BN
        EPI_BWD = 5,         // dgrad: the same mapping reads the matching 16 bytes of the layer-below's z (coalesced) and
                             // carries sum(dy), sum(dy*z) -- pass 1 of the BN/ReLU backward without re-reading da
+       EPI_F32 = 7,         // parity mode on tensor cores: fp32 output = out_scale * accumulator + bias (split 16-bit
+                            // operands concatenated along K, see launch_conv3x3_tc_split); no statistics
        EPI_ACT = 6 };       // inference: BatchNorm (moving statistics folded to scale / shift) + ReLU applied to the fp32
                             // accumulator before the bf16 rounding; optionally stored straight into the NEXT layer's
                             // zero-haloed padded input -- no z tensor, no activation pass
@@ -383,7 +402,7 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const float* __restrict__ bias, bf16* __restrict__ out, int H, int W, int Cin, int Cout, long long Mp,
               int num_m_pairs, int num_n_tiles, double* __restrict__ stats, int relu_stats, FastDiv dHWp, FastDiv dWp,
               const bf16* __restrict__ zprev, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-              int out_padded) {
+              int out_padded, int ab_fp16, float out_scale) {
   using Cfg = Conv3Cfg<BN, MT, EPI>;
   constexpr int AST = Cfg::kAStages, BST = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -457,7 +476,9 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
-      constexpr uint32_t idesc = make_idesc(2 * kBM, BN, 0, 0);
+      // A / B element format: bf16 (format code 1 in bits 7..9 / 10..12) or, for the split-fp16 operands of the parity
+      // mode's forward pass, fp16 (code 0); same 16-bit layout, same MMA rate
+      const uint32_t idesc = ab_fp16 ? (make_idesc(2 * kBM, BN, 0, 0) & ~((1u << 7) | (1u << 10))) : make_idesc(2 * kBM, BN, 0, 0);
       constexpr uint32_t hi = desc_hi(1024);
       const bool leader = elect_one();
       int as = 0, bs = 0;
@@ -595,6 +616,40 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
         for (int chh = 0; chh < NST; ++chh) {
           const int c0 = (2 * chh + half) * 32;
+          if (EPI == EPI_F32) {
+            // fp32 output: 16 columns (64 bytes per row) at a time through the same swizzled scratch, so that one store
+            // instruction writes 8 rows x 64 contiguous bytes
+            float* const outf = reinterpret_cast<float*>(out);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16];
+              tmem_ld16(t_row + c0 + hh * 16, v);
+              tmem_ld_wait();
+              uint4* const srow = st_scr + lane * 4;
+              const int sw4 = (lane >> 1) & 3;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + hh * 16 + 4 * c]);
+                uint4 u;
+                u.x = __float_as_uint(fmaf(__uint_as_float(v[4 * c]), out_scale, bb.x));
+                u.y = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 1]), out_scale, bb.y));
+                u.z = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 2]), out_scale, bb.z));
+                u.w = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 3]), out_scale, bb.w));
+                srow[c ^ sw4] = u;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int R = (lane >> 2) + 8 * i;
+                const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
+                if (spix[i] >= 0)
+                  *reinterpret_cast<uint4*>(outf + (long long)spix[i] * Cout + n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+              }
+              __syncwarp();   // the scratch is rewritten by the next group
+            }
+            continue;
+          }
           uint32_t pk[16];
           uint4 zr[EPI == EPI_BWD ? 4 : 1];
           if (EPI == EPI_BWD) {
@@ -794,6 +849,9 @@ struct BwdFuse {
   const bf16* z;
   const float *scale, *shift;
   int out_padded = 0;   // EPI_ACT: store into the zero-haloed padded layout
+  int f32_out = 0;      // EPI_F32: fp32 output = out_scale * accumulator + bias
+  int ab_fp16 = 0;      //          operands are fp16 (else bf16)
+  float out_scale = 1.f;
 };
 template <int BN, int MT, int EPI>
 static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias, bf16* out, int H, int W, int Cin, int Cout,
@@ -816,7 +874,7 @@ static int launch_conv3(const bf16* in, const bf16* packed_w, const float* bias,
                                                                  stats, relu_stats,
                                                                  make_fastdiv((uint32_t)(H + 2) * (uint32_t)(W + 2)),
                                                                  make_fastdiv((uint32_t)(W + 2)), bf.z, bf.scale, bf.shift,
-                                                                 bf.out_padded);
+                                                                 bf.out_padded, bf.ab_fp16, bf.out_scale);
   L3_CHECK_LAUNCH();
   return 0;
 }
@@ -825,6 +883,12 @@ static int launch_conv3_any(int BN, const bf16* in, const bf16* packed_w, const 
                             int Cout, long long Mp, double* stats, int relu_stats, cudaStream_t s,
                             BwdFuse bf = BwdFuse{nullptr, nullptr, nullptr}) {
 #define L3_GO(bn, mt, epi) return launch_conv3<bn, mt, epi>(in, packed_w, bias, out, H, W, Cin, Cout, Mp, stats, relu_stats, s, bf)
+  if (bf.f32_out) {   // parity mode on tensor cores
+    L3_REQUIRE(stats == nullptr, "fp32-output epilogue: no statistics");
+    if (BN == 256) L3_GO(256, 1, EPI_F32);
+    if (BN == 128) L3_GO(128, 2, EPI_F32);
+    L3_GO(64, 4, EPI_F32);
+  }
   if (bf.z == nullptr && bf.scale != nullptr) {   // inference: fused BatchNorm + ReLU epilogue
     L3_REQUIRE(stats == nullptr, "fused activation epilogue: no statistics");
     if (BN == 256) L3_GO(256, 1, EPI_ACT);
@@ -882,6 +946,25 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
 // separate at 64 channels: the extra z loads sit on the epilogue's critical path), so the step keeps the separate pass;
 // the fused launch stays available as a stand-alone, tested op (l3_conv3x3_dgrad_stats).
 int conv_tc_fuses_bwd_stats() { return 0; }
+
+// Parity mode on tensor cores: `in` holds 16-bit SPLIT operands concatenated along the channel axis,
+//   [hi | lo | hi] (3*Cin channels, zero-haloed padded) x packed weights [hi ; hi ; lo]  ->  a_hi w_hi + a_lo w_hi + a_hi w_lo
+// accumulated in fp32 in TMEM -- a convolution with Cin' = 3*Cin as far as the kernel is concerned.  Output: fp32
+// un-padded (B,H,W,Cout) = out_scale * acc + bias.  fp16 = 1: the parts are fp16 (2 x 11 significant bits: forward pass,
+// weights pre-scaled by 1/out_scale to stay in fp16's normal range); 0: bf16 (2 x 8 bits, fp32's range: backward pass).
+int launch_conv3x3_tc_split(const void* in_split, const void* packed_w_split, const float* bias, float* out, int B, int H, int W,
+                            int Cin, int Cout, int fp16, float out_scale, cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv_tc_split: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) + 1024 < 0x7fffffffLL, "conv_tc: too many pixels for 32-bit TMA coordinates");
+  const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  BwdFuse bf{nullptr, nullptr, nullptr};
+  bf.f32_out = 1;
+  bf.ab_fp16 = fp16;
+  bf.out_scale = out_scale;
+  return launch_conv3_any(BN, (const bf16*)in_split, (const bf16*)packed_w_split, bias, (bf16*)out, H, W, 3 * Cin, Cout, Mp,
+                          nullptr, 0, s, bf);
+}
 
 int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
                                 const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
@@ -1061,9 +1144,11 @@ k_wgrad3x3_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// a_pitch / z_pitch: channels per pixel row in memory when the operand is a channel PREFIX of a wider buffer (the split
+// [hi | lo | hi] buffers of the parity mode, of which the weight gradient uses [hi | lo]); 0 = dense
 template <bool PAIR>
 static int launch_wgrad2_cfg(const bf16* a, const bf16* dz, float* dw, int W, int Cin, int Cout, long long Mp,
-                             cudaStream_t s) {
+                             cudaStream_t s, int a_pitch = 0, int z_pitch = 0) {
   using Cfg = Wg2Cfg<PAIR>;
   static PerDeviceOnce once;
   if (once.needed()) {
@@ -1071,8 +1156,8 @@ static int launch_wgrad2_cfg(const bf16* a, const bf16* dz, float* dw, int W, in
     once.mark();
   }
   CUtensorMap tmA, tmZ;
-  if (make_tmap(&tmA, a, Cin, Mp, kWg2RegionRows)) return -1;
-  if (make_tmap(&tmZ, dz, Cout, Mp, kWg2Chunk)) return -1;
+  if (make_tmap(&tmA, a, a_pitch ? a_pitch : Cin, Mp, kWg2RegionRows)) return -1;
+  if (make_tmap(&tmZ, dz, z_pitch ? z_pitch : Cout, Mp, kWg2Chunk)) return -1;
   const int units = PAIR ? Cout / Cfg::BN : (Cin / 128) * (Cout / Cfg::BN) * 3;
   const int total_chunks = (int)((Mp + kWg2Chunk - 1) / kWg2Chunk);
   int slices = (2 * 148) / units;   // units*slices <= 296: exactly two waves of one CTA per SM, never a third
@@ -1685,6 +1770,39 @@ __global__ void k_bias_grad(const bf16* __restrict__ dz, long long rows, int C, 
   for (int i = 0; i < 8; ++i) atomicAdd(&sh[g * 8 + i], s1[i]);
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sh[i]);
+}
+
+// dw[tap][ci][co] = sum over the four (operand part) x (operand part) blocks of the split weight gradient
+// dw4 (3,3,2*Cin,2*Cout): (a_hi + a_lo)(dz_hi + dz_lo) -- overwrites dw
+__global__ void k_fold_split_dw(const float* __restrict__ dw4, float* __restrict__ dw, int Cin, int Cout) {
+  const long long n = 9LL * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int ci = (int)(r % Cin);
+    const int tap = (int)(r / Cin);
+    const float* b = dw4 + ((long long)tap * 2 * Cin + ci) * (2 * Cout) + co;
+    const long long up = (long long)Cin * 2 * Cout;
+    dw[i] = (b[0] + b[Cout]) + (b[up] + b[up + Cout]);
+  }
+}
+
+// Weight gradient of the parity mode on tensor cores: a_split (B,H+2,W+2,3*Cin) and dz_split (B,H+2,W+2,3*Cout) hold bf16
+// parts [hi | lo | hi]; the kernel runs on the [hi | lo] prefixes as a layer with 2*Cin x 2*Cout channels into the fp32
+// scratch dw4 (9 * 2*Cin * 2*Cout floats, zeroed here), whose four blocks are then folded into dw (overwritten).
+int launch_wgrad3x3_tc_split(const void* a_split, const void* dz_split, float* dw, float* dw4, int B, int H, int W, int Cin,
+                             int Cout, cudaStream_t s) {
+  L3_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "wgrad_tc_split: channels Cin=%d Cout=%d", Cin, Cout);
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Mp + 4LL * (W + 2) < 0x7fffffffLL, "wgrad_tc: too many pixels for 32-bit TMA coordinates");
+  L3_CHECK_CUDA(cudaMemsetAsync(dw4, 0, sizeof(float) * 9 * 4 * (size_t)Cin * Cout, s));
+  if (launch_wgrad2_cfg<false>((const bf16*)a_split, (const bf16*)dz_split, dw4, W, 2 * Cin, 2 * Cout, Mp, s, 3 * Cin, 3 * Cout))
+    return -1;
+  const long long n = 9LL * Cin * Cout;
+  int blocks = (int)((n + 255) / 256 > 148 * 8 ? 148 * 8 : (n + 255) / 256);
+  k_fold_split_dw<<<blocks, 256, 0, s>>>(dw4, dw, Cin, Cout);
+  L3_CHECK_LAUNCH();
+  return 0;
 }
 
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,

@@ -4,6 +4,7 @@
 // l3embedding/audio_model.py:370-437 and l3embedding/vision_model.py:124-190; Adam at l3embedding/train.py:282.
 // All activations are NHWC; per-thread work is 8 channels (one 16-byte bf16 vector) with coalesced access.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "kernels.h"
 
 namespace l3 {
@@ -977,6 +978,69 @@ __global__ void k_l2_penalty(const float* __restrict__ p, long long n, double* _
 int launch_l2_penalty(const float* p, long long n_l2, double* out, cudaStream_t s) {
   L3_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
   k_l2_penalty<<<148 * 2, kThreads, 0, s>>>(p, n_l2, out);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// parity mode on tensor cores: split an fp32 tensor into 16-bit parts, x ~ hi + lo, laid out [hi | lo | hi] along the
+// channel axis -- against weights packed [hi ; hi ; lo] one K-concatenated MMA chain accumulates
+// a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32.  fp16 parts carry 2 x 11 significant bits (forward: activations are O(1),
+// well inside fp16's range), bf16 parts 2 x 8 bits with fp32's range (backward: gradients can be tiny).
+// --------------------------------------------------------------------------------------------
+template <bool FP16>
+__global__ void k_split16(const float* __restrict__ src, unsigned short* __restrict__ dst, long long rows, int C) {
+  const int groups = C >> 3;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int g = (int)(i - r * groups);
+    float v[8];
+    load8(src + r * C + g * 8, v);
+    unsigned short hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (FP16) {
+        const __half h = __float2half_rn(v[k]);
+        const __half l = __float2half_rn(v[k] - __half2float(h));
+        hi[k] = *reinterpret_cast<const unsigned short*>(&h);
+        lo[k] = *reinterpret_cast<const unsigned short*>(&l);
+      } else {
+        const bf16 h = __float2bfloat16_rn(v[k]);
+        const bf16 l = __float2bfloat16_rn(v[k] - __bfloat162float(h));
+        hi[k] = *reinterpret_cast<const unsigned short*>(&h);
+        lo[k] = *reinterpret_cast<const unsigned short*>(&l);
+      }
+    }
+    uint4 uh, ul;
+    uh.x = hi[0] | ((uint32_t)hi[1] << 16); uh.y = hi[2] | ((uint32_t)hi[3] << 16);
+    uh.z = hi[4] | ((uint32_t)hi[5] << 16); uh.w = hi[6] | ((uint32_t)hi[7] << 16);
+    ul.x = lo[0] | ((uint32_t)lo[1] << 16); ul.y = lo[2] | ((uint32_t)lo[3] << 16);
+    ul.z = lo[4] | ((uint32_t)lo[5] << 16); ul.w = lo[6] | ((uint32_t)lo[7] << 16);
+    unsigned short* d = dst + r * 3 * C + g * 8;
+    *reinterpret_cast<uint4*>(d) = uh;
+    *reinterpret_cast<uint4*>(d + C) = ul;
+    *reinterpret_cast<uint4*>(d + 2 * C) = uh;
+  }
+}
+int launch_split16(const float* src, void* dst, long long rows, int C, int fp16, cudaStream_t s) {
+  L3_REQUIRE(C % 8 == 0, "split16: C=%d", C);
+  const long long total = rows * (C / 8);
+  long long want = (total + kThreads - 1) / kThreads;
+  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  if (fp16) k_split16<true><<<blocks, kThreads, 0, s>>>(src, (unsigned short*)dst, rows, C);
+  else k_split16<false><<<blocks, kThreads, 0, s>>>(src, (unsigned short*)dst, rows, C);
+  L3_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void k_f64_to_f32_ew(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+int launch_f64_to_f32(const double* src, float* dst, long long n, cudaStream_t s) {
+  int blocks = (int)((n + 255) / 256 > kMaxBlocks ? kMaxBlocks : (n + 255) / 256);
+  k_f64_to_f32_ew<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(src, dst, n);
   L3_CHECK_LAUNCH();
   return 0;
 }

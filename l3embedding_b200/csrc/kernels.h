@@ -74,6 +74,11 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, long 
                 float b2, float eps, float l2, cudaStream_t s);
 int launch_l2_penalty(const float* p, long long n_l2, double* out, cudaStream_t s);
 int launch_zero(void* p, size_t bytes, cudaStream_t s);
+// Parity mode on tensor cores: fp32 (rows, C) -> 16-bit parts [hi | lo | hi] (rows, 3*C); fp16 = 1: fp16 parts of scale*x
+// (forward operands), 0: bf16 parts (backward operands).  rows counts PADDED pixel rows (halo rows split to zeros).
+int launch_split16(const float* src, void* dst, long long rows, int C, int fp16, cudaStream_t s);
+// dst[i] = (float)src[i]
+int launch_f64_to_f32(const double* src, float* dst, long long n, cudaStream_t s);
 
 // ---- SIMT fp32-accumulate convolutions (conv_simt.cu) --------------------------------------
 // out[b,y,x,co] = bias[co] + sum_{ky,kx,ci} in[b,y+ky-1,x+kx-1,ci] * w[(ky*3+kx)*Cin*Cout + ci*Cout + co]
@@ -137,6 +142,9 @@ struct PackJob {
   const float* w;
   bf16* out;
   int Cin, Cout, flip;
+  int split = 0;       // parity mode on tensor cores: [hi ; hi ; lo] parts of scale * w over 3x the input channels
+  int fp16 = 0;        //   parts are fp16 (forward) / bf16 (backward)
+  float scale = 1.f;
 };
 struct PackBatch {
   PackJob job[kMaxPackJobs];
@@ -156,6 +164,9 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
 // Data gradient of a conv (Cin -> Cout) on tensor cores with pass 1 of the BN/ReLU backward of the layer BELOW fused
 // into the epilogue: da (B,H,W,Cin) = conv(dz, packed_wt); sums[0..Cin) = sum(dy), sums[Cin..2Cin) = sum(dy * z_below)
 // with dy = da where scale*z_below + shift > 0 (the layer below is Conv -> BN -> ReLU, not pooled); sums are zeroed here.
+// Parity mode on tensor cores (split 16-bit operands, fp32 accumulate and output): see conv_tc.cu
+int launch_conv3x3_tc_split(const void* in_split, const void* packed_w_split, const float* bias, float* out, int B, int H, int W,
+                            int Cin, int Cout, int fp16, float out_scale, cudaStream_t s);
 int conv_tc_fuses_bwd_stats();   // 0: measured neutral, the step keeps the separate statistics pass (stand-alone op only)
 int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
                                 const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
@@ -164,6 +175,9 @@ int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da,
 // dw (3,3,Cin,Cout) fp32 and db (Cout) are accumulated into (pre-zeroed by the caller).
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                        cudaStream_t s);
+// Parity mode on tensor cores: bf16 split operands [hi | lo | hi]; dw4 = fp32 scratch of 9 * 2*Cin * 2*Cout floats
+int launch_wgrad3x3_tc_split(const void* a_split, const void* dz_split, float* dw, float* dw4, int B, int H, int W, int Cin,
+                             int Cout, cudaStream_t s);
 // First-layer (Cin = 1|3, Cout = 64) weight gradient on tensor cores: xin padded (B,H+2,W+2,C0), dz padded
 // (B,H+2,W+2,64); accumulates dw (9*C0*64), db (64) and d1 (9*64, optional; zeroed here) -- see launch_first_wgrad.
 int launch_first_wgrad_tc(const bf16* xin, const bf16* dz, float* dw, float* db, float* d1, int B, int H, int W, int C0,

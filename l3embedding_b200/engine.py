@@ -30,7 +30,8 @@ def _as_device(x, device, dtypes):
 
 class Engine:
     """One replica on one GPU.  dtype 'f32' = parity mode (fp32 storage, fp32 SIMT convolutions);
-    'bf16' = throughput mode (bf16 activations, tcgen05 convolutions with fp32 accumulation)."""
+    'bf16' = throughput mode (bf16 activations, tcgen05 convolutions with fp32 accumulation);
+    'f32tc' = parity mode on tensor cores (fp32 storage, split 16-bit operands on tcgen05; include/l3b200.h)."""
 
     def __init__(self, model_type: str, max_batch: int, dtype: str = "f32", training: bool = True,
                  towers=("vision", "audio"), device: Optional[torch.device] = None, host_staging: bool = True,
@@ -38,8 +39,8 @@ class Engine:
         self.lib = _lib.load()
         self.model_type = model_type
         self.mid = _lib.model_id(model_type)
-        if dtype not in ("f32", "bf16"):
-            raise ValueError("dtype must be 'f32' or 'bf16'")
+        if dtype not in _lib.DTYPES:
+            raise ValueError("dtype must be one of %s" % sorted(_lib.DTYPES))
         if not torch.cuda.is_available():
             raise L3Error("no CUDA device: the L3 B200 path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -56,7 +57,7 @@ class Engine:
             self.flags |= _lib.WS_VISION
         if "audio" in towers:
             self.flags |= _lib.WS_AUDIO
-        dt = _lib.DTYPE_BF16 if dtype == "bf16" else _lib.DTYPE_F32
+        dt = _lib.DTYPES[dtype]
         with torch.cuda.device(self.device):
             f32 = dict(dtype=torch.float32, device=self.device)
             self.params = torch.zeros(self.n_params, **f32)

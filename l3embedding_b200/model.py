@@ -151,10 +151,11 @@ class L3Model:
 
     # ---- configuration ---------------------------------------------------------------------------------
     def configure(self, dtype: Optional[str] = None):
-        """dtype 'f32' (parity mode) or 'bf16' (tcgen05 throughput mode).  Re-creates the device state."""
+        """dtype 'f32' (parity mode), 'f32tc' (parity mode on tensor cores) or 'bf16' (tcgen05 throughput mode).
+        Re-creates the device state."""
         if dtype is not None and dtype != self.dtype:
-            if dtype not in ("f32", "bf16"):
-                raise ValueError("dtype must be 'f32' or 'bf16'")
+            if dtype not in _lib.DTYPES:
+                raise ValueError("dtype must be one of %s" % sorted(_lib.DTYPES))
             self._pull()
             self._drop_engine()
             self.dtype = dtype

@@ -221,3 +221,40 @@ def test_stream_schedules_agree_on_a_training_step():
         if k.endswith("/bias") or "/bn0/" in k:
             continue
         assert r <= 1e-3, (k, r)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 13, 64, 64), (2, 20, 11, 64, 128), (1, 8, 24, 128, 256), (2, 6, 5, 256, 512),
+                                   (1, 7, 9, 512, 512), (3, 33, 31, 64, 64)])
+def test_split_operand_convs_reach_fp32_accuracy(lib, shape):
+    """L3_DTYPE_F32TC (parity mode on tensor cores): fp32 tensors, every operand split into two 16-bit parts that are
+    concatenated along K -- [hi | lo | hi] x [hi ; hi ; lo] -- and accumulated in fp32 in TMEM.  Forward: fp16 parts
+    (2 x 11 significant bits, weights pre-scaled by 2^10); data / weight gradient: bf16 parts (2 x 8 bits, fp32's range).
+    Against float64 PyTorch on the same fp32 inputs: forward within 2e-5 of the output's largest value (a single bf16
+    pass is ~4e-3), gradients within 2e-4."""
+    from l3embedding_b200 import _lib
+    B, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(29)
+    x = torch.randn(B, H, W, Ci, generator=g) * 3.0                       # un-rounded fp32 operands
+    w = torch.randn(3, 3, Ci, Co, generator=g) * (2.0 / (9 * Ci)) ** 0.5
+    b = torch.randn(Co, generator=g)
+    dz = torch.randn(B, H, W, Co, generator=g) * 1e-4                      # small, like real gradients
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), b.double(), padding=1).permute(0, 2, 3, 1)
+    y.backward(dz.double())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xp, dzp = _pad(x).contiguous().cuda(), _pad(dz).contiguous().cuda()
+    wd, bd = w.contiguous().cuda(), b.cuda()
+    out = torch.full((B, H, W, Co), float("nan"), device="cuda")
+    _lib.check(lib.l3_conv3x3_fwd(_p(xp), _p(wd), _p(bd), _p(out), B, H, W, Ci, Co, 2, 1, None, st), "fwd f32tc")
+    da = torch.full((B, H, W, Ci), float("nan"), device="cuda")
+    _lib.check(lib.l3_conv3x3_dgrad(_p(dzp), _p(wd), _p(da), B, H, W, Ci, Co, 2, 1, None, st), "dgrad f32tc")
+    dw = torch.full((3, 3, Ci, Co), float("nan"), device="cuda")
+    db = torch.full((Co,), float("nan"), device="cuda")
+    _lib.check(lib.l3_conv3x3_wgrad(_p(xp), _p(dzp), _p(dw), _p(db), B, H, W, Ci, Co, 2, 1, st), "wgrad f32tc")
+    torch.cuda.synchronize()
+    rel = lambda got, ref: float((got.double().cpu() - ref).abs().max() / ref.abs().max())
+    errs = dict(fwd=rel(out, y.detach()), dgrad=rel(da, xr.grad), wgrad=rel(dw, wr.grad),
+                db=rel(db, dz.double().sum(dim=(0, 1, 2))))
+    print(shape, {k: "%.2e" % v for k, v in errs.items()})
+    assert errs["fwd"] <= 2e-5 and errs["dgrad"] <= 2e-4 and errs["wgrad"] <= 2e-4 and errs["db"] <= 1e-5, errs

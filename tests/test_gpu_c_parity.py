@@ -77,17 +77,22 @@ def test_conv_simt_fwd_dgrad_wgrad_f32(shape):
     assert torch.allclose(db.cpu(), dz.sum(dim=(0, 1, 2)), atol=1e-3, rtol=1e-4)
 
 
+PARITY_MODES = ["f32", "f32tc"]      # SIMT fp32 / split 16-bit operands on tcgen05 (include/l3b200.h): the same 1e-3 bar
+
+
+@pytest.mark.parametrize("mode", PARITY_MODES)
 @pytest.mark.parametrize("model_type", MODEL_TYPES)
-def test_inference_logits_and_embeddings_f32(model_type):
+def test_inference_logits_and_embeddings_f32(model_type, mode):
     """keras predict path (BN moving statistics): AVC logits/probabilities and both audio embeddings + the vision
-    embedding within 1e-3 max-abs of the fp64 oracle."""
+    embedding within 1e-3 max-abs of the fp64 oracle -- in both parity modes."""
     B = 2
     w_np = O.init_weights(model_type, seed=20180123, randomize_bn=True)
     video, audio, _ = O.synthetic_batch(B, seed=202)
     vf, af = _oracle_inputs(video, audio)
     w = O.to_torch(w_np, dtype=torch.float64)
     ref_logits = O.avc_forward(vf, af, w, model_type, False, F64).numpy()
-    eng = _engine(model_type, B, "f32", training=False, weights=w_np)
+    eng = _engine(model_type, B, mode, training=False, weights=w_np)
+    assert eng.uses_tensor_cores == (mode == "f32tc")
     probs, logits = eng.predict(video, audio)
     assert np.abs(logits - ref_logits).max() <= 1e-3, np.abs(logits - ref_logits).max()
     ref_p = torch.softmax(torch.from_numpy(ref_logits), dim=1).numpy()
@@ -104,12 +109,13 @@ def test_inference_logits_and_embeddings_f32(model_type):
     assert np.abs(p2 - probs).max() <= 1e-6
 
 
-def test_embedding_matches_golden_fixture():
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_embedding_matches_golden_fixture(mode):
     with np.load(GOLDEN) as z:
         meta = json.loads(str(z["meta"]))
         _, audio, _ = O.synthetic_batch(meta["batch"], seed=meta["data_seed"])
         for mt in meta["embedding_types"]:
             w_np = O.init_weights(mt, seed=meta["weight_seed"], randomize_bn=True)
-            eng = _engine(mt, meta["batch"], "f32", training=False, towers=("audio",), weights=w_np)
+            eng = _engine(mt, meta["batch"], mode, training=False, towers=("audio",), weights=w_np)
             assert np.abs(eng.embed_audio(audio, "short").cpu().numpy() - z[mt + "/embedding_short"]).max() <= 1e-3
             assert np.abs(eng.embed_audio(audio, "original").cpu().numpy() - z[mt + "/embedding_original"]).max() <= 1e-3

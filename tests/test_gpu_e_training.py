@@ -17,8 +17,9 @@ from _gpu_common import MODEL_TYPES, GOLDEN, F64, engine as _engine, rel_l2, pad
 
 pytestmark = pytest.mark.gpu
 
+@pytest.mark.parametrize("mode", ["f32", "f32tc"])
 @pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_orig"])
-def test_training_step_gradients_f32(model_type):
+def test_training_step_gradients_f32(model_type, mode):
     """train_on_batch: loss, accuracy, every gradient tensor, BN moving statistics and the Adam update against
     fp64 autograd of the oracle."""
     B = 2
@@ -27,7 +28,7 @@ def test_training_step_gradients_f32(model_type):
     vf, af = _oracle_inputs(video, audio)
     w = O.to_torch(w_np, dtype=torch.float64, requires_grad=True)
     grads, out, stats = O.compute_grads(vf, af, torch.from_numpy(label), w, model_type, F64)
-    eng = _engine(model_type, B, "f32", training=True, weights=w_np)
+    eng = _engine(model_type, B, mode, training=True, weights=w_np)   # f32tc: split 16-bit operands on tcgen05
     eng.forward_backward(video, audio, label)
     m = eng.metrics()
     assert abs(m["loss"] - float(out["loss"])) <= 1e-4 * max(1.0, abs(float(out["loss"])))
