@@ -486,12 +486,21 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t sa_base = smem_addr(smem), sb_base = smem_addr(smem_b);
+      // EPI_F32 (parity mode): the accumulator is handed to the epilogue every kFlushIts (ky, channel-chunk) iterations
+      // and restarted from zero -- tcgen05 adds each MMA's products into the fp32 accumulator with truncation, a bias of
+      // ~2^-25 of the running sum per MMA that grows linearly with the chain length (measured 2.9e-5 relative at
+      // K = 3 * 4608); short chains summed by the epilogue in registers (round-to-nearest) keep it at ~1e-6
+      constexpr int kFlushIts = (EPI == EPI_F32) ? 3 : (1 << 30);
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        uint32_t d_tmem = 0;
         uint32_t first = 1;
         for (int it = 0; it < 3 * KC; ++it) {
+          if (it % kFlushIts == 0) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            d_tmem = tmem_base + acc * (MT * BN);
+            first = 1;
+          }
           mbar_wait(&a_full[as], aph);
           const uint32_t a_lo0 = desc_lo(sa_base + as * Cfg::kAStage, 16);
 #pragma unroll
@@ -515,11 +524,13 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (leader) umma_commit_pair(&a_empty[as]);
           __syncwarp();
           if (++as == AST) { as = 0; aph ^= 1; }
+          if (it % kFlushIts == kFlushIts - 1 || it == 3 * KC - 1) {
+            if (leader) umma_commit_pair(&tfull_bar[acc]);
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+          }
         }
-        if (leader) umma_commit_pair(&tfull_bar[acc]);
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -597,6 +608,77 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const unsigned mbase = (unsigned)(tile / num_n_tiles) * (2 * MT * kBM) + rank * (MT * kBM) + q * 32 + lane;
       const int n0 = (tile % num_n_tiles) * BN;
+      if (EPI == EPI_F32) {
+        // parity mode: sum the short accumulation chains (see the MMA issuer) in registers, round-to-nearest
+        constexpr int NR = (EPI == EPI_F32) ? MT * NST * 32 : 1;
+        float racc[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) racc[i] = 0.f;
+        const int n_groups = (3 * KC + 2) / 3;
+#pragma unroll 1
+        for (int grp = 0; grp < n_groups; ++grp) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < MT; ++t)
+#pragma unroll
+            for (int chh = 0; chh < NST; ++chh)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (MT * BN) + t * BN + (2 * chh + half) * 32 + hh * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) racc[(EPI == EPI_F32) ? ((t * NST + chh) * 32 + hh * 16 + j) : 0] += __uint_as_float(v[j]);
+              }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        float* const outf = reinterpret_cast<float*>(out);
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {   // unrolled: racc must be indexed statically to stay in registers
+          const int opix = out_pixel(mbase + t * kBM, Mp, H, W, dHWp, dWp);
+          int spix[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) spix[i] = __shfl_sync(0xffffffffu, opix, (lane >> 2) + 8 * i);
+#pragma unroll
+          for (int chh = 0; chh < NST; ++chh) {
+            const int c0 = (2 * chh + half) * 32;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              // 16 columns (64 bytes per row) at a time through the swizzled scratch: one store instruction writes
+              // 8 rows x 64 contiguous bytes
+              uint4* const srow = st_scr + lane * 4;
+              const int sw4 = (lane >> 1) & 3;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + hh * 16 + 4 * c]);
+                const int r0 = (EPI == EPI_F32) ? ((t * NST + chh) * 32 + hh * 16 + 4 * c) : 0;
+                uint4 u;
+                u.x = __float_as_uint(fmaf(racc[r0], out_scale, bb.x));
+                u.y = __float_as_uint(fmaf(racc[(EPI == EPI_F32) ? r0 + 1 : 0], out_scale, bb.y));
+                u.z = __float_as_uint(fmaf(racc[(EPI == EPI_F32) ? r0 + 2 : 0], out_scale, bb.z));
+                u.w = __float_as_uint(fmaf(racc[(EPI == EPI_F32) ? r0 + 3 : 0], out_scale, bb.w));
+                srow[c ^ sw4] = u;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int R = (lane >> 2) + 8 * i;
+                const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
+                if (spix[i] >= 0)
+                  *reinterpret_cast<uint4*>(outf + (long long)spix[i] * Cout + n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
+              }
+              __syncwarp();   // the scratch is rewritten by the next group
+            }
+          }
+        }
+        continue;
+      }
       if (n0 != st_n0) { flush_stats(); st_n0 = n0; }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -616,40 +698,6 @@ k_conv3x3_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
         for (int chh = 0; chh < NST; ++chh) {
           const int c0 = (2 * chh + half) * 32;
-          if (EPI == EPI_F32) {
-            // fp32 output: 16 columns (64 bytes per row) at a time through the same swizzled scratch, so that one store
-            // instruction writes 8 rows x 64 contiguous bytes
-            float* const outf = reinterpret_cast<float*>(out);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t v[16];
-              tmem_ld16(t_row + c0 + hh * 16, v);
-              tmem_ld_wait();
-              uint4* const srow = st_scr + lane * 4;
-              const int sw4 = (lane >> 1) & 3;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bias != nullptr) bb = *reinterpret_cast<const float4*>(&s_bias[n0 + c0 + hh * 16 + 4 * c]);
-                uint4 u;
-                u.x = __float_as_uint(fmaf(__uint_as_float(v[4 * c]), out_scale, bb.x));
-                u.y = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 1]), out_scale, bb.y));
-                u.z = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 2]), out_scale, bb.z));
-                u.w = __float_as_uint(fmaf(__uint_as_float(v[4 * c + 3]), out_scale, bb.w));
-                srow[c ^ sw4] = u;
-              }
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int R = (lane >> 2) + 8 * i;
-                const uint4 val = st_scr[R * 4 + ((lane & 3) ^ ((R >> 1) & 3))];
-                if (spix[i] >= 0)
-                  *reinterpret_cast<uint4*>(outf + (long long)spix[i] * Cout + n0 + c0 + hh * 16 + (lane & 3) * 4) = val;
-              }
-              __syncwarp();   // the scratch is rewritten by the next group
-            }
-            continue;
-          }
           uint32_t pk[16];
           uint4 zr[EPI == EPI_BWD ? 4 : 1];
           if (EPI == EPI_BWD) {
