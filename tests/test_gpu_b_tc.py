@@ -215,12 +215,13 @@ def test_stream_schedules_agree_on_a_training_step():
         worst.append((float(np.linalg.norm(x - y) / den), k))
     worst.sort(reverse=True)
     print("overlapped vs serial schedule, largest relative L2 differences:", worst[:5])
-    # fp32 split-K reductions arrive in a different order: 1e-6-level differences, amplified where the sum cancels
-    # (input-BN gradients, analytically-zero biases); anything above 1e-3 on a well-conditioned tensor is a race
+    # fp32 split-K reductions arrive in a different order: 1e-6-level differences per addend, amplified where the sum
+    # cancels (input-BN gradients, analytically-zero biases, and to ~1e-3 the first-layer kernels: 576 sums of 3 M
+    # terms each); a missing dependency between the streams shows up as an O(0.1 .. 1) difference
     for r, k in worst:
         if k.endswith("/bias") or "/bn0/" in k or k == "vision/bn1b/beta":   # the cancelling sums (see test_gpu_d_bf16)
             continue
-        assert r <= 1e-3, (k, r)
+        assert r <= 5e-3, (k, r)
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 13, 64, 64), (2, 20, 11, 64, 128), (1, 8, 24, 128, 256), (2, 6, 5, 256, 512),

@@ -45,6 +45,12 @@ def test_training_step_gradients_f32(model_type, mode):
         # relative L2 on these gradients at B=2 (BN backward cancels large terms), and by up to 6e-5 absolute on the
         # analytically-zero ones (bias of a conv feeding training-mode BN).  Hence 1e-2 relative / 1e-4 absolute.
         tol = 1e-2
+        if mode == "f32tc" and ("/bn0/" in name or name == "vision/bn1b/beta"):
+            # f32tc splits the BACKWARD operands into two bf16 parts (fp32's range; 2^-17 per operand instead of 2^-24).
+            # That is ~1e-5 on every well-conditioned gradient, but the input-BN gradients (and beta of the one BN that
+            # feeds a convolution without a ReLU in between) are sums of data gradients that cancel down to border
+            # effects -- the same tensors the bf16 test singles out (test_gpu_d_bf16.py) -- measured 1.1e-2 here
+            tol = 3e-2
         if not (err <= tol or max_abs <= 1e-4):
             bad.append((name, err, max_abs, float(np.abs(g_ref).max())))
     assert not bad, bad
