@@ -213,6 +213,7 @@ struct l3_ctx {
   cudaStream_t stream2;
   cudaEvent_t ev_fork, ev_join, ev_pack;
   int two_streams;
+  int pack_event_pending;   // this step's operand packs were enqueued on the context stream: towers wait for ev_pack
   // Inside a tower the backward chain is dgrad -> BN/ReLU backward (HBM-bound) -> dgrad ...; the weight gradients hang
   // off it as leaves.  With wgrad_streams they run on a low-priority side stream per tower and fill the tensor pipe
   // while the chain is in its HBM-bound kernels (needs the double dz buffer and the internal tower streams).
@@ -499,6 +500,7 @@ static int tower_forward(l3_ctx* c, Tower& tw, int B, bool training, bool embed_
   for (int l = 0; l < 8; ++l) {
     ConvLayer& L = tw.L[l];
     bool stats_done = false;
+    if (l == 1 && c->pack_event_pending && s != c->stream) L3_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_pack, 0));
     if (!training && l < 7 && L.tc && c->use_tc && c->fuse_inference && !(L.pool && L.relu_first)) {
       // inference on the tensor-core path: BN uses the moving statistics, so scale / shift are known BEFORE the
       // convolution and BN + ReLU ride in its epilogue on the fp32 accumulator.  Un-pooled layers store straight into
@@ -615,9 +617,10 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
       } else if (L.tc && c->use_tc) {
         // Conv -> BN layers: sum_pixels(dz) == 0 identically (BN backward removes the mean), so the bias gradient
         // stays at the zero the grads arena was cleared to; only the ReLU-before-BN layer needs the reduction.
-        if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, L.relu_first ? L.db : nullptr, B, L.H, L.W, L.Cin,
-                               L.Cout, sw))
-          return -1;
+        // (that reduction is HBM-bound: on the tower's own stream, not queued behind the side stream's weight gradients,
+        // where it used to finish last of the whole step)
+        if (launch_wgrad3x3_tc((const bf16*)L.in, (const bf16*)dz, L.dw, nullptr, B, L.H, L.W, L.Cin, L.Cout, sw)) return -1;
+        if (L.relu_first && launch_bias_grad_tc((const bf16*)dz, L.db, B, L.H, L.W, L.Cout, s)) return -1;
       } else if (l == 0 && c->use_tc && c->dtype == L3_DTYPE_BF16 && L.Cout == 64) {
         // (the first layer is Conv -> BN in every model type: its bias gradient is identically zero as well -- summing
         // the stored dz would only add up its rounding errors)
@@ -798,14 +801,20 @@ template <typename T>
 static int forward_all(l3_ctx* c, const void* video, int vfmt, const void* audio, int afmt, const float* labels, int B,
                        bool training, float grad_scale) {
   if (fork_streams(c)) return -1;
-  // the bf16 operand packs are first needed by the second conv layer: they are built on the vision tower's stream while
-  // the audio stream already runs the front-end (the first-layer kernels read the fp32 weights themselves)
-  if (pack_all_weights(c, true, true, training, c->vision.stream)) return -1;
-  if (c->audio.stream != c->vision.stream) L3_CHECK_CUDA(cudaEventRecord(c->ev_pack, c->vision.stream));
+  // The bf16 operand packs are first needed by the SECOND conv layer (the first-layer kernels read the fp32 weights
+  // themselves): they are built on the context stream, beside the towers' input stages, and each tower waits for them
+  // right before its first tensor-core layer (tower_forward).  On the vision stream they used to delay the whole tower.
+  c->pack_event_pending = 0;
+  if (c->vision.stream != c->stream) {
+    if (pack_all_weights(c, true, true, training, c->stream)) return -1;
+    L3_CHECK_CUDA(cudaEventRecord(c->ev_pack, c->stream));
+    c->pack_event_pending = 1;
+  } else if (pack_all_weights(c, true, true, training, c->stream)) {
+    return -1;
+  }
   // interleave the two towers' launches so neither stream starves while the host is still enqueuing the other
   if (tower_input<T>(c, c->vision, false, video, vfmt, B, training)) return -1;
   if (tower_input<T>(c, c->audio, true, audio, afmt, B, training)) return -1;
-  if (c->audio.stream != c->vision.stream) L3_CHECK_CUDA(cudaStreamWaitEvent(c->audio.stream, c->ev_pack, 0));
   if (tower_forward<T>(c, c->vision, B, training, false)) return -1;
   if (tower_forward<T>(c, c->audio, B, training, false)) return -1;
   if (join_streams(c)) return -1;
@@ -976,6 +985,7 @@ l3_ctx* l3_ctx_create(int model_type, int max_batch, int dtype, int flags, float
     return nullptr;
   }
   c->fuse_inference = 1;
+  c->pack_event_pending = 0;
   c->device = 0;
   cudaGetDevice(&c->device);
   c->st_head = c->st_tail = c->st_count = 0;

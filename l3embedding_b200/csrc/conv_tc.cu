@@ -1862,14 +1862,19 @@ int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int 
   const int rc = (Cin == 64) ? launch_wgrad2_cfg<true>(a, dz, dw, W, Cin, Cout, Mp, s)
                              : launch_wgrad2_cfg<false>(a, dz, dw, W, Cin, Cout, Mp, s);
   if (rc) return rc;
-  if (db) {
-    L3_REQUIRE(256 % (Cout / 8) == 0, "bias_grad: Cout=%d", Cout);
-    int lanes = 256 / (Cout / 8);
-    long long want = (Mp + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
-    int blocks = (int)(want > 148 * 4 ? 148 * 4 : (want < 1 ? 1 : want));
-    k_bias_grad<<<blocks, 256, Cout * sizeof(float), s>>>(dz, Mp, Cout, db);
-    L3_CHECK_LAUNCH();
-  }
+  if (db) return launch_bias_grad_tc(dz, db, B, H, W, Cout, s);
+  return 0;
+}
+
+// db[co] += sum of dz over all pixels (dz zero-haloed padded bf16); HBM-bound
+int launch_bias_grad_tc(const bf16* dz, float* db, int B, int H, int W, int Cout, cudaStream_t s) {
+  const long long Mp = (long long)B * (H + 2) * (W + 2);
+  L3_REQUIRE(Cout % 8 == 0 && 256 % (Cout / 8) == 0, "bias_grad: Cout=%d", Cout);
+  int lanes = 256 / (Cout / 8);
+  long long want = (Mp + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+  int blocks = (int)(want > 148 * 4 ? 148 * 4 : (want < 1 ? 1 : want));
+  k_bias_grad<<<blocks, 256, Cout * sizeof(float), s>>>(dz, Mp, Cout, db);
+  L3_CHECK_LAUNCH();
   return 0;
 }
 

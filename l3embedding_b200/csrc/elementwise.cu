@@ -11,6 +11,10 @@ namespace l3 {
 
 static const int kThreads = 256;
 static const int kMaxBlocks = 148 * 8;  // grid-stride kernels: a multiple of the SM count
+// Grid caps of the big grid-stride kernels below (148 x 8 / 148 x 16 blocks): measured in round 2 with everything from one
+// to six blocks per SM -- the training step does not move (10.7 .. 11.1 ms, inside the run-to-run spread): under the
+// board's power cap the step is bound by the work, not by how the element-wise blocks interleave with the convolutions.
+static inline int ew_cap(int dflt) { return dflt; }
 
 // Merge type of the per-channel reductions.  bf16 (throughput) mode: fp32 partials merged with fp32 shared-memory
 // atomics, one fp64 global atomic per block and channel.  fp32 (parity) mode: every partial is widened to fp64 BEFORE
@@ -356,7 +360,8 @@ int launch_act_fwd(const T* z, T* a, int B, int H, int W, int C, const float* sc
   L3_REQUIRE(npix < 0x7fffffffLL, "act_fwd: too many pixels");
   int lanes = kThreads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
-  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  const int cap = ew_cap(148 * 16);
+  int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   if (pool && zsel && sel)
     k_act_fwd<T, true, true><<<blocks, kThreads, 0, s>>>(z, a, H, W, C, OH, OW, npix, scale, shift, relu_first, zsel, sel);
   else if (pool)
@@ -671,7 +676,8 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
     const long long npix = (long long)B * (H / 2) * (W / 2);
     const int lanes = kThreads / (C / 8);
     long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
-    int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+    const int cap = ew_cap(148 * 8);
+    int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
     k_bwd_stats_sel<T><<<blocks, kThreads, 2 * C * sizeof(typename MergeT<T>::type), s>>>(da, zsel, sel, C, npix, bn, relu_first);
     L3_CHECK_LAUNCH();
     return 0;
@@ -685,7 +691,8 @@ int launch_bwd_stats(const T* da, const T* z, int B, int H, int W, int C, const 
   long long npix = (long long)B * OH * OW;
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 4 - 1) / ((long long)lanes * 4);
-  int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+  const int cap = ew_cap(148 * 8);
+  int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   const size_t shb = 2 * C * sizeof(typename MergeT<T>::type);
   if (pool) k_bwd_stats<T, true><<<blocks, threads, shb, s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
   else k_bwd_stats<T, false><<<blocks, kThreads, shb, s>>>(da, z, H, W, C, OH, OW, npix, bn, relu_first);
@@ -818,7 +825,8 @@ int launch_bwd_apply(const T* da, const T* z, T* dz, int B, int H, int W, int C,
   long long npix = (long long)B * OH * OW;
   int lanes = threads / (C / 8);
   long long want = (npix + (long long)lanes * 2 - 1) / ((long long)lanes * 2);
-  int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  const int cap = ew_cap(148 * 16);
+  int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   if (pool && sel) k_bwd_apply<T, true, true><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, sel);
   else if (pool) k_bwd_apply<T, true, false><<<blocks, threads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);
   else k_bwd_apply<T, false, false><<<blocks, kThreads, 0, s>>>(da, z, dz, H, W, C, OH, OW, npix, bn, relu_first, nullptr);

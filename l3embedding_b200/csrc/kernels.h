@@ -175,6 +175,7 @@ int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da,
 // dw (3,3,Cin,Cout) fp32 and db (Cout) are accumulated into (pre-zeroed by the caller).
 int launch_wgrad3x3_tc(const bf16* a, const bf16* dz, float* dw, float* db, int B, int H, int W, int Cin, int Cout,
                        cudaStream_t s);
+int launch_bias_grad_tc(const bf16* dz, float* db, int B, int H, int W, int Cout, cudaStream_t s);
 // Parity mode on tensor cores: bf16 split operands [hi | lo | hi]; dw4 = fp32 scratch of 9 * 2*Cin * 2*Cout floats
 int launch_wgrad3x3_tc_split(const void* a_split, const void* dz_split, float* dw, float* dw4, int B, int H, int W, int Cin,
                              int Cout, cudaStream_t s);
