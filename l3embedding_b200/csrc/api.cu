@@ -641,10 +641,12 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
       tw.wg_pending[l & 1] = 1;
     }
     // gradient buckets of the big layers leave as soon as their weight gradient is enqueued: conv4b, conv4a, conv3a+3b
-    // hold 74 % + 18 % of the bytes and are complete after ~27 % / ~45 % of the backward FLOPs; the small
-    // rest of the tower goes in the final grouped launch (l3_forward_backward).  Layers 7..1 share the stream `sw`.
+    // hold 74 % + 18 % of the bytes and are complete after ~27 % / ~45 % of the backward FLOPs, conv2a + 2b
+    // follow; only conv1a + 1b of each tower (0.15 MB) wait for the final grouped launch (dp_fire_tail), whose latency
+    // is the one part of the exchange the backward pass cannot hide.  Layers 7..1 share the stream `sw`.
     if (l == 7 || l == 6) { if (dp_fire_kernels(c, tw, l, l, sw)) return -1; }
     else if (l == 4) { if (dp_fire_kernels(c, tw, 4, 5, sw)) return -1; }
+    else if (l == 2) { if (dp_fire_kernels(c, tw, 2, 3, sw)) return -1; }
   }
   if (l == 0) {
     if (tw.has_bn0) {
@@ -727,21 +729,25 @@ static int dp_fire_metrics(l3_ctx* c) {
   return dp_allreduce_ranges(c->dp, c->stream, &p, &n, 1, 0);
 }
 
-// The rest of the gradient arena in ONE grouped launch once both towers have joined the context stream: the small
-// conv kernels of each tower (conv1a..conv2b), the dense kernels, and everything that is not a kernel (biases, BN
-// gamma / beta).  ~2.6 MB of 38 MB: this is the only part of the exchange that the backward pass cannot hide.
+// The dense kernels' gradients are complete as soon as the head's backward is (before the towers' backward starts)
+static int dp_fire_dense(l3_ctx* c) {
+  void* p = c->head.dw1;                                  // dense_1 and dense_2 kernels are adjacent (build_layout)
+  long long n = 1024LL * 128 + 128 * 2;
+  return dp_allreduce_ranges(c->dp, c->stream, &p, &n, 1, 0);
+}
+
+// The rest of the gradient arena in ONE grouped launch once both towers have joined the context stream: conv1a + conv1b
+// of each tower and everything that is not a kernel (biases, BN gamma / beta) -- 0.35 MB of 38 MB.
 static int dp_fire_tail(l3_ctx* c) {
-  void* ptrs[4];
-  long long counts[4];
+  void* ptrs[3];
+  long long counts[3];
   int n = 0;
   for (Tower* tw : {&c->vision, &c->audio}) {
     long long k = 0;
-    for (int l = 0; l <= 3; ++l) k += 9LL * tw->L[l].Cin * tw->L[l].Cout;
+    for (int l = 0; l <= 1; ++l) k += 9LL * tw->L[l].Cin * tw->L[l].Cout;
     ptrs[n] = tw->L[0].dw;
     counts[n++] = k;
   }
-  ptrs[n] = c->head.dw1;                                  // dense_1 and dense_2 kernels are adjacent (build_layout)
-  counts[n++] = 1024LL * 128 + 128 * 2;
   ptrs[n] = c->grads + c->layout.n_l2;
   counts[n++] = c->layout.n_params - c->layout.n_l2;
   return dp_allreduce_ranges(c->dp, c->stream, ptrs, counts, n, 0);
@@ -1222,6 +1228,7 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
     if (!rc) rc = release_slot(c, slot);
     if (!rc && c->dp) rc = dp_fire_metrics(c);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc && c->dp) rc = dp_fire_dense(c);
     if (!rc) rc = fork_streams(c);
     if (!rc) rc = towers_backward<bf16>(c, batch);
     if (!rc) rc = join_streams(c);
@@ -1230,6 +1237,7 @@ int l3_forward_backward(l3_ctx* c, const void* video, int video_fmt, const void*
     if (!rc) rc = release_slot(c, slot);
     if (!rc && c->dp) rc = dp_fire_metrics(c);
     if (!rc) rc = launch_head_bwd(c->head, batch, c->stream);
+    if (!rc && c->dp) rc = dp_fire_dense(c);
     if (!rc) rc = fork_streams(c);
     if (!rc) rc = towers_backward<float>(c, batch);
     if (!rc) rc = join_streams(c);

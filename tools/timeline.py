@@ -17,17 +17,26 @@ from l3embedding_b200.synthetic import synthetic_batch
 tag = sys.argv[1] if len(sys.argv) > 1 else "x"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 dtype = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 eng = Engine("cnn_L3_melspec2", B, dtype, training=True)
-v, a, l = (torch.from_numpy(x).cuda() for x in synthetic_batch(B, seed=1))
+if world > 1:      # under torchrun: the library's own data-parallel exchange (NCCL kernels show up in the timeline)
+    import torch.distributed as dist
+    from l3embedding_b200 import dp
+    dist.init_process_group("gloo")
+    dp.LibraryReplicas().attach(eng)
+v, a, l = (torch.from_numpy(x).cuda() for x in synthetic_batch(B, seed=1 + rank))
 for _ in range(5):
-    eng.forward_backward(v, a, l)
+    eng.forward_backward(v, a, l, global_batch=B * world)
     eng.adam_step(1e-5)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
-        eng.forward_backward(v, a, l)
+        eng.forward_backward(v, a, l, global_batch=B * world)
         eng.adam_step(1e-5)
     torch.cuda.synchronize()
+if rank != 0:
+    sys.exit(0)
 path = "gpurun_out/%s_trace.json" % tag
 prof.export_chrome_trace(path)
 ev = json.load(open(path))["traceEvents"]
