@@ -249,6 +249,7 @@ class TrainBench:
         self.B, self.G, self.world, self.rank, self.dev, self.lr, self.pool_n = B, B * world, world, rank, dev, lr, pool_n
         self.eng = Engine(model_type, B, dtype, training=True, device=dev, seed=20180123)
         par.attach(self.eng)          # N > 1: joins the library's NCCL communicator (collective)
+        self.exchange = par.world_size > 1
         # a pool of distinct synthetic batches, resident in HBM and pinned on the host for the e2e arm
         self.pool_dev, self.pool_host = [], []
         for i in range(pool_n):
@@ -270,7 +271,7 @@ class TrainBench:
     def step_e2e(self, i):
         # the fit loop's software pipeline: batch i was uploaded during step i-1; enqueue batch i+1, run step i
         self._upload(i + 1)
-        if self.world == 1:
+        if not self.exchange:
             return self.eng.train_step_staged(self.B, self.lr)
         return self.eng.dp_train_step_staged(self.B, self.G, self.lr)
 
@@ -313,7 +314,7 @@ class TrainBench:
 
     def drain_staged(self):
         """the e2e loop leaves one uploaded batch pending: consume it so the next phase starts clean"""
-        if self.world == 1:
+        if not self.exchange:
             self.eng.train_step_staged(self.B, self.lr)
         else:
             self.eng.dp_train_step_staged(self.B, self.G, self.lr)
@@ -416,7 +417,8 @@ def main_gpu(args):
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()
-        par = dp.LibraryReplicas() if world > 1 else dp.SingleReplica()
+        # --no-exchange (diagnostic): N independent replicas, same barrier / max-over-ranks timing, no gradient exchange
+        par = dp.LibraryReplicas() if (world > 1 and not args.no_exchange) else dp.SingleReplica()
         B = args.batch
         tb = TrainBench(MODEL_TYPE, B, args.dtype, world, rank, dev, par, args.pool)
     finally:
@@ -487,8 +489,9 @@ def main_gpu(args):
                                    "(224x224x3 u8 frame + 48000-sample i16 audio)",
                        "per_gpu_batch": B, "global_batch": G, "parallelism": "dp%d" % world,
                        "tensor_cores": uses_tc, "tower_streams": 2,
-                       "gradient_exchange": ("none" if world == 1 else "libl3b200 l3_dp_*: NCCL all-reduce in buckets on a "
-                                             "communication stream, overlapped with backward"),
+                       "gradient_exchange": ("none" if (world == 1 or args.no_exchange) else
+                                             "libl3b200 l3_dp_*: NCCL all-reduce in buckets on a communication stream, "
+                                             "overlapped with backward"),
                        "l2": "inputs rotate over a %d-batch pool; each step streams >5 GB of activations through the "
                              "126 MB L2, so no step sees a warm L2" % args.pool},
             "clocks": r["clocks"],
@@ -546,6 +549,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE-config records")
     ap.add_argument("--all-configs", action="store_true", help="run the config 4 / 5 records at any --gpus")
+    ap.add_argument("--no-exchange", action="store_true", help="diagnostic: N independent replicas (no gradient exchange)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = 3
