@@ -119,3 +119,17 @@ def test_embedding_matches_golden_fixture(mode):
             eng = _engine(mt, meta["batch"], mode, training=False, towers=("audio",), weights=w_np)
             assert np.abs(eng.embed_audio(audio, "short").cpu().numpy() - z[mt + "/embedding_short"]).max() <= 1e-3
             assert np.abs(eng.embed_audio(audio, "original").cpu().numpy() - z[mt + "/embedding_original"]).max() <= 1e-3
+
+
+def test_video_scaling_is_bit_exact():
+    """train.py:186: `2 * img_as_float(u8).astype('float32') - 1` -- the device's u8 -> float conversion (k_video_to_f32)
+    against the numpy expression, bit for bit (cnn_L3_orig has no input BN, so x0 is the scaled frame itself)."""
+    B = 2
+    video, audio, _ = O.synthetic_batch(B, seed=31)
+    video[0, 0, 0] = (0, 255, 128)                      # the range ends and the middle
+    eng = _engine("cnn_L3_orig", B, "f32", training=False)
+    eng.predict(video, audio)
+    got = eng.debug_read("vision/x0", B).reshape(B, 224, 224, 3)
+    want = O.scale_video(video)
+    assert got.dtype == want.dtype == np.float32 and np.array_equal(got, want)
+    assert got.min() == -1.0 and got.max() == 1.0

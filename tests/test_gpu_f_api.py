@@ -91,6 +91,12 @@ def test_train_function_writes_reference_files_and_resumes(tmp_path):
                        continue_model_dir=model_dir, **kw)
     assert len(hist2.history["loss"]) == 1                      # only epoch index 2 ran
     assert T.get_restart_info(os.path.join(model_dir, "history_csvlog.csv"))[0] == 2
+    # the Adam state travels with the checkpoints (the reference restarts the moments from zero on resume): 2 epochs x 2
+    # steps before the resume, 2 more after it -- the step count continues instead of restarting at 0
+    with np.load(T.optimizer_state_path(os.path.join(model_dir, "model_checkpoint.02.h5"))) as z:
+        assert int(z["t"]) == 4 and z["m"].shape == z["v"].shape and np.abs(z["m"]).max() > 0
+    with np.load(T.optimizer_state_path(os.path.join(model_dir, "model_latest.h5"))) as z:
+        assert int(z["t"]) == 6
 
 
 def test_reference_embedding_extraction_call_sequence(tmp_path):
@@ -141,3 +147,27 @@ def test_reference_embedding_extraction_call_sequence(tmp_path):
     ref4 = O.audio_embedding(torch.from_numpy(a[idx].reshape(n, 1, 48000)).double(), O.to_torch(w_np, dtype=torch.float64),
                              model_type, "original", F64).numpy()
     assert X4.shape == (n, 6144) and np.abs(X4 - ref4).max() <= 1e-3
+
+
+def test_embedding_predict_pipeline_equals_direct_calls():
+    """EmbeddingModel.predict streams host arrays through a three-stage pinned pipeline in device batches of 512
+    (keras' batch_size of 32 is a request, not a constraint: inference results do not depend on the batching).  Across
+    chunk boundaries and a ragged last chunk it returns exactly what direct engine calls on the same clips return, for
+    int16 and for float32 input."""
+    from l3embedding_b200 import model as M
+    m, _, _ = M.MODELS["cnn_L3_melspec2"]()
+    m.configure(dtype="bf16")
+    m.set_named_weights(O.init_weights("cnn_L3_melspec2", seed=5, randomize_bn=True))
+    e, _, _ = M.convert_audio_model_to_embedding(m.get_layer("audio_model"), m.inputs[1], "cnn_L3_melspec2", "short")
+    _, a64, _ = O.synthetic_batch(64, seed=9)
+    n = 1100                                                     # 512 + 512 + 76
+    x = np.concatenate([a64] * 18)[:n]
+    x[::7] //= 2                                                 # not all chunks alike
+    got = e.predict(x)
+    assert got.shape == (n, 512) and got.dtype == np.float32
+    eng = e._get_engine(512)
+    for s0 in (0, 512, 1024):
+        ref = eng.embed_audio(x[s0:s0 + 512], "short").cpu().numpy()
+        assert np.array_equal(got[s0:s0 + len(ref)], ref), s0
+    got_f = e.predict(O.pcm2float(x[:600], "float32"), batch_size=32)
+    assert np.array_equal(got_f, got[:600])                      # pcm2float is exact in fp32: same embeddings
