@@ -17,9 +17,14 @@
 
 namespace l3 {
 
-static const int kFramesPerCta = 8;   // 4 packed complex FFTs per CTA, transformed CONCURRENTLY (one barrier per pass)
+// 4 frames = 2 packed complex FFTs per CTA, transformed CONCURRENTLY (one barrier per pass).  Round 2: was 8 frames with
+// the Hann window and the mel weights staged in shared memory (137 KB: ONE 16-warp CTA per SM, and the kernel is bound
+// by barrier / shared-memory latency, not by issue slots); with 4 frames and those two tables read through L1
+// (__ldg: they are shared by every CTA) a CTA needs 57 KB and <= 40 registers, so THREE CTAs = 48 warps share an SM.
+static const int kFramesPerCta = 4;
 static const int kFePairs = kFramesPerCta / 2;
 static const int kFeThreads = 512;
+static const int kFeCtasPerSm = 3;
 
 // ---- host-side table construction (float64, cast to float32 as kapre stores them) ---------------------
 static void build_mel(int sr, int n_fft, int n_mels, std::vector<int>& start, std::vector<int>& count,
@@ -166,7 +171,7 @@ __device__ __forceinline__ void fft_dif_batched(float2* z, const float2* __restr
 // grid: (ceil(n_frames / kFramesPerCta), B).  Shared: clip window (staged by TMA bulk copy), FFT buffer, twiddles,
 // power spectra, output tile.
 template <int N, bool I16>
-__global__ void __launch_bounds__(kFeThreads)
+__global__ void __launch_bounds__(kFeThreads, kFeCtasPerSm)
 k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ raw, int* __restrict__ clip_max) {
   constexpr int NF = N / 2 + 1;
   constexpr int LOGN = (N == 2048) ? 11 : 9;
@@ -174,11 +179,11 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   constexpr int G = kFePairs, PWS = NF + 3;
   float2* zbuf = reinterpret_cast<float2*>(smem_raw);                       // G x N complex (frame pairs A + iB)
   float2* tw = zbuf + G * N;                                                // N/2 complex
-  float* win = reinterpret_cast<float*>(tw + N / 2);                        // N
-  float* pw = win + N;                                                      // kFramesPerCta power spectra of PWS floats
+  float* pw = reinterpret_cast<float*>(tw + N / 2);                         // kFramesPerCta power spectra of PWS floats
   float* tile = pw + kFramesPerCta * PWS;                                   // n_out * kFramesPerCta
-  float* melw = tile + p.n_out * kFramesPerCta;                             // mel_nnz packed filter weights
-  unsigned char* stage = reinterpret_cast<unsigned char*>(melw + p.mel_nnz);
+  const float* __restrict__ win = p.window;                                 // through L1 (shared by all CTAs)
+  const float* __restrict__ melw = p.mel_weight;
+  unsigned char* stage = reinterpret_cast<unsigned char*>(tile + p.n_out * kFramesPerCta);
   stage = reinterpret_cast<unsigned char*>(((uintptr_t)stage + 15) & ~(uintptr_t)15);
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float red[kFeThreads / 32];
@@ -211,9 +216,6 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   }
   // overlap: constant tables -> shared
   for (int i = threadIdx.x; i < N / 2; i += blockDim.x) tw[i] = p.twiddle[i];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) win[i] = p.window[i];
-  // the projection walks up to ~50 weights per (frame, band) item: from shared memory, not through L1/L2
-  for (int i = threadIdx.x; i < p.mel_nnz; i += blockDim.x) melw[i] = p.mel_weight[i];
   // wait for the clip window
   {
     uint32_t done = 0;
@@ -241,7 +243,7 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
     if (fb < nfr && ib >= 0 && ib < p.n_samples)
       xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
                : reinterpret_cast<const float*>(stage)[ib - a_lo];
-    const float w = win[t];
+    const float w = __ldg(win + t);
     zbuf[i] = make_float2(xa * w, xb * w);
   }
   __syncthreads();
@@ -270,7 +272,7 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
       const float* w = melw + p.mel_offset[m];
       float sa = 0.f, sb = 0.f;
       for (int k = 0; k < n; ++k) {
-        const float wk = w[k];
+        const float wk = __ldg(w + k);
         sa = fmaf(pw0[k0 + k], wk, sa);
         sb = fmaf(pw1[k0 + k], wk, sb);
       }
@@ -330,14 +332,14 @@ static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out
   constexpr int NF = N / 2 + 1;
   constexpr int ES = I16 ? 2 : 4;
   size_t stage_elems = (size_t)(kFramesPerCta - 1) * p.n_hop + N + 16;
-  size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + (size_t)N * 4 + kFramesPerCta * (size_t)(NF + 3) * 4 +
-                (size_t)p.n_out * kFramesPerCta * 4 + (size_t)p.mel_nnz * 4 + 16 + stage_elems * ES;
+  size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + kFramesPerCta * (size_t)(NF + 3) * 4 +
+                (size_t)p.n_out * kFramesPerCta * 4 + 16 + stage_elems * ES;
   static PerDeviceOnce once;
   if (once.needed()) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     once.mark();
   }
-  L3_REQUIRE(smem <= 200 * 1024, "frontend smem %zu too large", smem);
+  L3_REQUIRE(smem <= 100 * 1024, "frontend smem %zu too large", smem);
   dim3 grid(ceil_div(p.n_frames, kFramesPerCta), B);
   k_frontend<N, I16><<<grid, kFeThreads, smem, s>>>(p, audio, out, clip_max);
   L3_CHECK_LAUNCH();
