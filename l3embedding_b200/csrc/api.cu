@@ -471,13 +471,18 @@ static int conv_forward(l3_ctx* c, ConvLayer& L, int B, bool want_stats, bool* s
 template <typename T>
 static int tower_input(l3_ctx* c, Tower& tw, bool is_audio, const void* src, int fmt, int B, bool training) {
   cudaStream_t s = tw.stream;
+  // mode of the fused input pass (launch_input_stage): 0 = x0 is final, 1 = u8 video, 2 = dB map awaiting its reference
+  int mode = 0;
+  const uint8_t* u8 = nullptr;
   if (is_audio) {
     ProfScope ps(c, PROF_FRONTEND, s);
-    if (launch_frontend(c->fe, src, fmt == L3_AUDIO_I16, B, tw.x0, c->clip_max, s)) return -1;
+    if (launch_frontend(c->fe, src, fmt == L3_AUDIO_I16, B, tw.x0, c->clip_max, s, /*finish=*/0)) return -1;
+    if (c->fe.decibel) mode = 2;
   } else {
     long long n = (long long)B * 224 * 224 * 3;
     if (fmt == L3_VIDEO_U8) {
-      if (launch_video_to_f32((const uint8_t*)src, tw.x0, n, s)) return -1;
+      mode = 1;
+      u8 = (const uint8_t*)src;
     } else {
       L3_CHECK_CUDA(cudaMemcpyAsync(tw.x0, src, n * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -485,12 +490,18 @@ static int tower_input(l3_ctx* c, Tower& tw, bool is_audio, const void* src, int
   const float *sc = nullptr, *sh = nullptr;
   if (tw.has_bn0) {
     long long rows = (long long)B * tw.H0 * tw.W0;
-    if (training && launch_channel_stats<float>(tw.x0, rows, tw.C0, 0, tw.bn0.sum, s)) return -1;
+    if (training) {
+      // batch statistics first: pass 1 produces x0 and its sums, pass 2 (below) normalises
+      if (launch_input_stage<T>(mode, u8, tw.x0, (T*)nullptr, B, tw.H0, tw.W0, tw.C0, nullptr, nullptr, c->clip_max,
+                                tw.bn0.sum, s))
+        return -1;
+      mode = 0;
+    }
     if (launch_bn_finalize(tw.bn0, rows, training, kBnMomentum, kBnEps, kBnUnbiasedMoving, s)) return -1;
     sc = tw.bn0.scale;
     sh = tw.bn0.shift;
   }
-  return launch_affine_small<T>(tw.x0, (T*)tw.xin, B, tw.H0, tw.W0, tw.C0, sc, sh, s);
+  return launch_input_stage<T>(mode, u8, tw.x0, (T*)tw.xin, B, tw.H0, tw.W0, tw.C0, sc, sh, c->clip_max, nullptr, s);
 }
 
 // n_layers_act: layers [0, 7) always activate into the next input; the last conv's z is the embedding tap

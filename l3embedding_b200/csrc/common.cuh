@@ -114,6 +114,23 @@ __host__ __device__ __forceinline__ long long pad_off(long long b, int y, int x,
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// division of n < 2^31 by a launch-time constant d >= 2 (Granlund-Montgomery): q = umulhi(n, mul) >> shift.  The conv
+// epilogues turn a flattened padded pixel index into (image, row, column) once per tile row, the input stage once per
+// element; hardware-less 32-bit divisions cost ~30 dependent instructions each, 64-bit ones over a hundred.
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;               // ceil(log2 d), d >= 2 -> l >= 1
+  f.mul = (uint32_t)(((1ull << (31 + l)) / d) + 1);
+  f.shift = l - 1;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.shift; }
+
 // cudaFuncSetAttribute (opt-in to > 48 KB of dynamic shared memory) is per DEVICE: one flag per launcher and device,
 // so that a second context on another GPU of the same process gets its own opt-in.  Setting the attribute twice is
 // harmless, so the flag is only marked after the calls succeeded (two racing threads both set it).

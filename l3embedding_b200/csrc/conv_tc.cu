@@ -92,22 +92,6 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
 }
-// division of n < 2^31 by a launch-time constant d >= 2 (Granlund-Montgomery): q = umulhi(n, mul) >> shift.  The
-// epilogues turn a flattened padded pixel index into (image, row, column) once per tile row; two hardware-less 32-bit
-// divisions (~60 dependent instructions) sat on every epilogue warp's per-tile critical path.
-struct FastDiv {
-  uint32_t mul, shift, d;
-};
-static FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;               // ceil(log2 d), d >= 2 -> l >= 1
-  f.mul = (uint32_t)(((1ull << (31 + l)) / d) + 1);
-  f.shift = l - 1;
-  f.d = d;
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.shift; }
 // flattened padded pixel m -> output pixel index (b*H + y)*W + x of the un-padded tensor, or -1 for halo / out-of-range
 __device__ __forceinline__ int out_pixel(uint32_t m, long long Mp, int H, int W, const FastDiv& dHWp, const FastDiv& dWp) {
   const uint32_t b = fdiv(m, dHWp);

@@ -25,35 +25,6 @@ template <typename T> struct MergeT { typedef float type; };
 template <> struct MergeT<float> { typedef double type; };
 
 // --------------------------------------------------------------------------------------------
-// video u8 -> float : 2*(x/255) - 1      (train.py:186; divide in fp64 then fp32 affine, as skimage does)
-// --------------------------------------------------------------------------------------------
-__global__ void k_video_to_f32(const uint8_t* __restrict__ v, float* __restrict__ out, long long n4) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  const uchar4* v4 = reinterpret_cast<const uchar4*>(v);
-  float4* o4 = reinterpret_cast<float4*>(out);
-  for (; i < n4; i += stride) {
-    uchar4 u = v4[i];
-    float4 f;
-    f.x = 2.0f * (float)((double)u.x / 255.0) - 1.0f;
-    f.y = 2.0f * (float)((double)u.y / 255.0) - 1.0f;
-    f.z = 2.0f * (float)((double)u.z / 255.0) - 1.0f;
-    f.w = 2.0f * (float)((double)u.w / 255.0) - 1.0f;
-    o4[i] = f;
-  }
-}
-int launch_video_to_f32(const uint8_t* v, float* out, long long n, cudaStream_t s) {
-  L3_REQUIRE(n % 4 == 0, "video element count must be a multiple of 4");
-  long long n4 = n / 4;
-  int blocks = (int)((n4 + kThreads - 1) / kThreads);
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  if (blocks < 1) blocks = 1;
-  k_video_to_f32<<<blocks, kThreads, 0, s>>>(v, out, n4);
-  L3_CHECK_LAUNCH();
-  return 0;
-}
-
-// --------------------------------------------------------------------------------------------
 // per-channel sum / sum of squares over [rows][C]
 // --------------------------------------------------------------------------------------------
 template <typename T, bool RELU>
@@ -182,37 +153,82 @@ int launch_bn_finalize(const BnRef& bn, long long count, int training, float mom
 }
 
 // --------------------------------------------------------------------------------------------
-// input BN apply (C = 1 or 3), float (B,H,W,C) -> T in the zero-haloed layout (B,H+2,W+2,C) that every
-// convolution reads.  scale == nullptr: plain convert.
+// Input stage of a tower (C = 1 audio map, C = 3 video frame), ONE pass over the elements:
+//   MODE 0  v = x0[i]                                     (float input already in place)
+//   MODE 1  v = 2 * (u8 / 255) - 1  -> x0[i]              (train.py:186; divide in fp64, fp32 affine, as skimage does)
+//   MODE 2  v = max(x0[i] - clip max, -80) -> x0[i]       (kapre amplitude_to_decibel: per-clip maximum, 80 dB floor)
+//   sum  != null: per-channel sum / sum of squares of v   (training-mode input BatchNorm), fp64 accumulators
+//   xin  != null: v * scale[c] + shift[c] (or v) -> T in the zero-haloed layout (B,H+2,W+2,C) every convolution reads
+// Round 2: replaces four kernels (u8 -> float, dB finish, statistics, affine) that re-read the tensor three times and
+// decomposed every flat index with 64-bit divisions (the affine alone took 62 us per 64 frames: 15x its HBM time).
 // --------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void k_affine_small(const float* __restrict__ x, T* __restrict__ out, long long n, int H, int W, int C,
-                               const float* __restrict__ scale, const float* __restrict__ shift) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    float v = x[i];
-    int c = (int)(i % C);
-    long long p = i / C;
-    int xx = (int)(p % W);
-    int yy = (int)((p / W) % H);
-    long long b = p / ((long long)W * H);
-    if (scale) v = v * scale[c] + shift[c];
-    out[pad_off(b, yy, xx, H, W, C) + c] = from_f<T>(v);
+static const int kInThreads = 192;   // a multiple of 3: a thread's grid-stride elements all belong to ONE channel
+template <typename T, int C, int MODE>
+__global__ void __launch_bounds__(kInThreads)
+k_input_stage(const uint8_t* __restrict__ u8, float* __restrict__ x0, T* __restrict__ xin, unsigned n, int H, int W,
+              FastDiv d_row, FastDiv d_h, FastDiv d_clip, const float* __restrict__ scale, const float* __restrict__ shift,
+              const int* __restrict__ clip_max, double* __restrict__ sum) {
+  __shared__ double sh[2 * C];
+  if (threadIdx.x < 2 * C) sh[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int c = (C == 1) ? 0 : (int)(threadIdx.x % C);
+  float sc = 1.f, sf = 0.f;
+  if (xin != nullptr && scale != nullptr) { sc = scale[c]; sf = shift[c]; }
+  double s1 = 0.0, s2 = 0.0;
+  const unsigned stride = gridDim.x * kInThreads;   // multiple of C
+  for (unsigned i = blockIdx.x * kInThreads + threadIdx.x; i < n; i += stride) {
+    float v;
+    if (MODE == 1) {
+      v = 2.0f * (float)((double)u8[i] / 255.0) - 1.0f;
+      x0[i] = v;
+    } else if (MODE == 2) {
+      v = fmaxf(x0[i] - ordered_to_float(clip_max[fdiv(i, d_clip)]), -80.0f);
+      x0[i] = v;
+    } else {
+      v = x0[i];
+    }
+    if (sum != nullptr) {
+      s1 += (double)v;
+      s2 += (double)v * (double)v;
+    }
+    if (xin != nullptr) {
+      const unsigned row = fdiv(i, d_row), e = i - row * d_row.d;   // row = b * H + y, e = x * C + c
+      const unsigned b = fdiv(row, d_h), y = row - b * d_h.d;
+      const float o = (scale != nullptr) ? v * sc + sf : v;
+      xin[pad_off(b, (int)y, 0, H, W, C) + e] = from_f<T>(o);
+    }
+  }
+  if (sum != nullptr) {
+    atomicAdd(&sh[c], s1);
+    atomicAdd(&sh[C + c], s2);
+    __syncthreads();
+    if (threadIdx.x < 2 * C) atomicAdd(&sum[threadIdx.x], sh[threadIdx.x]);
   }
 }
 template <typename T>
-int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, const float* scale, const float* shift,
-                        cudaStream_t s) {
-  long long n = (long long)B * H * W * C;
-  long long want = (n + kThreads * 4 - 1) / (kThreads * 4);
-  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
-  k_affine_small<T><<<blocks, kThreads, 0, s>>>(x, out, n, H, W, C, scale, shift);
+int launch_input_stage(int mode, const uint8_t* u8, float* x0, T* xin, int B, int H, int W, int C, const float* scale,
+                       const float* shift, const int* clip_max, double* sum, cudaStream_t s) {
+  L3_REQUIRE(C == 1 || C == 3, "input stage: C=%d", C);
+  L3_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || u8 != nullptr) && (mode != 2 || clip_max != nullptr), "input stage: mode");
+  const long long n = (long long)B * H * W * C;
+  L3_REQUIRE(n < 0x7fffffffLL, "input stage: too many elements");
+  if (sum) L3_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * C, s));
+  long long want = (n + kInThreads * 4 - 1) / (kInThreads * 4);
+  const int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+  const FastDiv d_row = make_fastdiv((uint32_t)(W * C)), d_h = make_fastdiv((uint32_t)H);
+  const FastDiv d_clip = make_fastdiv((uint32_t)(H * W * C));
+#define L3_IN(c_, m_) k_input_stage<T, c_, m_><<<blocks, kInThreads, 0, s>>>(u8, x0, xin, (unsigned)n, H, W, d_row, d_h, d_clip, \
+                                                                          scale, shift, clip_max, sum)
+  if (C == 1) { if (mode == 0) L3_IN(1, 0); else if (mode == 1) L3_IN(1, 1); else L3_IN(1, 2); }
+  else { if (mode == 0) L3_IN(3, 0); else if (mode == 1) L3_IN(3, 1); else L3_IN(3, 2); }
+#undef L3_IN
   L3_CHECK_LAUNCH();
   return 0;
 }
-template int launch_affine_small<float>(const float*, float*, int, int, int, int, const float*, const float*, cudaStream_t);
-template int launch_affine_small<bf16>(const float*, bf16*, int, int, int, int, const float*, const float*, cudaStream_t);
+template int launch_input_stage<float>(int, const uint8_t*, float*, float*, int, int, int, int, const float*, const float*,
+                                       const int*, double*, cudaStream_t);
+template int launch_input_stage<bf16>(int, const uint8_t*, float*, bf16*, int, int, int, int, const float*, const float*,
+                                      const int*, double*, cudaStream_t);
 
 // zero the one-pixel halo of a padded (B,H+2,W+2,C) buffer (buffers re-used at several geometries); one 16-byte
 // store per thread when a pixel's channels are a multiple of 16 bytes (every layer with C >= 64)

@@ -14,17 +14,23 @@
 #include <math.h>
 #include <vector>
 #include "kernels.h"
+#include "frontend_fft.cuh"
 
 namespace l3 {
 
-// 4 frames = 2 packed complex FFTs per CTA, transformed CONCURRENTLY (one barrier per pass).  Round 2: was 8 frames with
-// the Hann window and the mel weights staged in shared memory (137 KB: ONE 16-warp CTA per SM, and the kernel is bound
-// by barrier / shared-memory latency, not by issue slots); with 4 frames and those two tables read through L1
-// (__ldg: they are shared by every CTA) a CTA needs 57 KB and <= 40 registers, so THREE CTAs = 48 warps share an SM.
-static const int kFramesPerCta = 4;
-static const int kFePairs = kFramesPerCta / 2;
-static const int kFeThreads = 512;
-static const int kFeCtasPerSm = 3;
+// One CTA = 128 threads = FR consecutive frames of one clip, two real frames packed into one complex transform that
+// lives in REGISTERS (frontend_fft.cuh: N = 16 x 16 x R3, three shared-memory exchanges).  N = 2048: one transform at a time
+// (T = 128 threads), two iterations; N = 512: four transforms side by side (T = 32), one iteration.  ~37 KB (50 KB) of
+// shared memory and <= 102 registers: five (four) CTAs per SM.
+static const int kFeThreads = 128;
+template <int N>
+struct FeCfg {
+  static const int T = FftGeom<N>::T;
+  static const int NC = kFeThreads / T;          // transforms in flight per CTA
+  static const int FR = (N == 2048) ? 4 : 8;     // frames per CTA
+  static const int ITERS = FR / (2 * NC);
+  static const int CTAS = (N == 2048) ? 5 : 4;   // resident CTAs per SM aimed at
+};
 
 // ---- host-side table construction (float64, cast to float32 as kapre stores them) ---------------------
 static void build_mel(int sr, int n_fft, int n_mels, std::vector<int>& start, std::vector<int>& count,
@@ -113,84 +119,32 @@ int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem,
 // ---- device ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// In-place DIF FFT of G independent length-N sequences z[g*N .. g*N+N) (shared memory), radix-4 passes (two radix-2
-// stages fused in registers) plus one final radix-2 pass (log2 N is odd for both 512 and 2048); output bit-reversed.
-// All G transforms advance together, so a pass costs ONE block barrier: the previous version ran 11 barriers per
-// 2048-point transform with four butterflies per thread between them and was barrier-latency bound.
-template <int N, int G>
-__device__ __forceinline__ void fft_dif_batched(float2* z, const float2* __restrict__ tw) {
-  static_assert(N == 512 || N == 2048, "log2(N) must be odd");
-  constexpr int TOTAL = G * (N / 4), IT = (TOTAL + kFeThreads - 1) / kFeThreads;   // quad-butterflies per thread and pass
-#pragma unroll 1
-  for (int h = N / 2; h >= 2; h >>= 2) {          // fused stages with halves h and h/2
-    const int ts1 = (N / 2) / h, hq = h >> 1;
-    // two phases -- all loads, then all math and stores (the quad-butterflies of a pass touch disjoint elements, which
-    // the compiler cannot know): with 16 warps per SM the passes were waiting on one LDS round trip per butterfly
-    float2 x[IT][4];
-    float2* zp[IT];
-    int jj[IT];
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const int i = threadIdx.x + it * kFeThreads;
-      const int q = i & (N / 4 - 1);
-      const int j = q & (hq - 1);
-      jj[it] = j;
-      zp[it] = z + (i / (N / 4)) * N + ((q - j) << 2) + j;
-      if (i < TOTAL) {
-        x[it][0] = zp[it][0]; x[it][1] = zp[it][hq]; x[it][2] = zp[it][h]; x[it][3] = zp[it][h + hq];
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      if (threadIdx.x + it * kFeThreads >= TOTAL) continue;
-      const int j = jj[it];
-      const float2 x0 = x[it][0], x1 = x[it][1], x2 = x[it][2], x3 = x[it][3];
-      const float2 wa = tw[j * ts1], wb = tw[(j + hq) * ts1], wc = tw[j * 2 * ts1];
-      const float2 y0 = make_float2(x0.x + x2.x, x0.y + x2.y), d0 = make_float2(x0.x - x2.x, x0.y - x2.y);
-      const float2 y1 = make_float2(x1.x + x3.x, x1.y + x3.y), d1 = make_float2(x1.x - x3.x, x1.y - x3.y);
-      const float2 y2 = make_float2(d0.x * wa.x - d0.y * wa.y, d0.x * wa.y + d0.y * wa.x);
-      const float2 y3 = make_float2(d1.x * wb.x - d1.y * wb.y, d1.x * wb.y + d1.y * wb.x);
-      const float2 e0 = make_float2(y0.x - y1.x, y0.y - y1.y), e1 = make_float2(y2.x - y3.x, y2.y - y3.y);
-      zp[it][0] = make_float2(y0.x + y1.x, y0.y + y1.y);
-      zp[it][hq] = make_float2(e0.x * wc.x - e0.y * wc.y, e0.x * wc.y + e0.y * wc.x);
-      zp[it][h] = make_float2(y2.x + y3.x, y2.y + y3.y);
-      zp[it][h + hq] = make_float2(e1.x * wc.x - e1.y * wc.y, e1.x * wc.y + e1.y * wc.x);
-    }
-    __syncthreads();
-  }
-  // last stage (half = 1): twiddle 1
-#pragma unroll
-  for (int i = threadIdx.x; i < G * (N / 2); i += kFeThreads) {
-    const float2 a = z[2 * i], b = z[2 * i + 1];
-    z[2 * i] = make_float2(a.x + b.x, a.y + b.y);
-    z[2 * i + 1] = make_float2(a.x - b.x, a.y - b.y);
-  }
-  __syncthreads();
-}
+struct LdgTw {
+  const float2* p;
+  __device__ __forceinline__ float2 operator()(int j) const { return __ldg(p + j); }
+};
 
-// grid: (ceil(n_frames / kFramesPerCta), B).  Shared: clip window (staged by TMA bulk copy), FFT buffer, twiddles,
-// power spectra, output tile.
+// grid: (ceil(n_frames / FR), B).  Shared: FFT exchange buffers (re | im), power spectra, output tile, clip window
+// (staged by a 1-D TMA bulk copy).
 template <int N, bool I16>
-__global__ void __launch_bounds__(kFeThreads, kFeCtasPerSm)
+__global__ void __launch_bounds__(kFeThreads, FeCfg<N>::CTAS)
 k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ raw, int* __restrict__ clip_max) {
-  constexpr int NF = N / 2 + 1;
-  constexpr int LOGN = (N == 2048) ? 11 : 9;
+  typedef FftGeom<N> G;
+  typedef FeCfg<N> F;
+  constexpr int NF = N / 2 + 1, PWS = NF + 3, T = G::T, NC = F::NC, FR = F::FR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int G = kFePairs, PWS = NF + 3;
-  float2* zbuf = reinterpret_cast<float2*>(smem_raw);                       // G x N complex (frame pairs A + iB)
-  float2* tw = zbuf + G * N;                                                // N/2 complex
-  float* pw = reinterpret_cast<float*>(tw + N / 2);                         // kFramesPerCta power spectra of PWS floats
-  float* tile = pw + kFramesPerCta * PWS;                                   // n_out * kFramesPerCta
-  const float* __restrict__ win = p.window;                                 // through L1 (shared by all CTAs)
-  const float* __restrict__ melw = p.mel_weight;
-  unsigned char* stage = reinterpret_cast<unsigned char*>(tile + p.n_out * kFramesPerCta);
+  float* const bre_all = reinterpret_cast<float*>(smem_raw);       // NC x BUF
+  float* const bim_all = bre_all + NC * G::BUF;                    // NC x BUF
+  float* const pw_all = bim_all + NC * G::BUF;                     // NC x 2 x PWS
+  float* const tile = pw_all + NC * 2 * PWS;                       // n_out x FR
+  unsigned char* stage = reinterpret_cast<unsigned char*>(tile + p.n_out * FR);
   stage = reinterpret_cast<unsigned char*>(((uintptr_t)stage + 15) & ~(uintptr_t)15);
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float red[kFeThreads / 32];
 
   const int b = blockIdx.y;
-  const int f0 = blockIdx.x * kFramesPerCta;
-  const int nfr = min(kFramesPerCta, p.n_frames - f0);
+  const int f0 = blockIdx.x * FR;
+  const int nfr = min(FR, p.n_frames - f0);
   // sample window needed by this CTA: [s_lo, s_hi) in clip coordinates (may exceed [0, n_samples))
   const int s_lo = f0 * p.n_hop - p.left_pad;
   const int s_hi = (f0 + nfr - 1) * p.n_hop - p.left_pad + N;
@@ -205,18 +159,13 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)),
         "l"(src), "r"(bytes), "r"(smem_u32(&bar))
         : "memory");
   }
-  // overlap: constant tables -> shared
-  for (int i = threadIdx.x; i < N / 2; i += blockDim.x) tw[i] = p.twiddle[i];
-  // wait for the clip window
+  __syncthreads();   // the barrier is initialised for everybody
   {
     uint32_t done = 0;
     while (!done) {
@@ -227,77 +176,96 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
           : "memory");
     }
   }
-  __syncthreads();
 
+  const int g = threadIdx.x / T, u = threadIdx.x % T;
+  float* const bre = bre_all + g * G::BUF;
+  float* const bim = bim_all + g * G::BUF;
+  float* const pw0 = pw_all + g * 2 * PWS;
+  float* const pw1 = pw0 + PWS;
+  const LdgTw tw{p.twiddle};
+  const float* __restrict__ win = p.window;      // through L1: shared by every CTA
+  const float* __restrict__ melw = p.mel_weight;
   float local_max = -INFINITY;
-  // pack frame 2g (real) and frame 2g+1 (imag) of every pair, windowed; zero outside the clip (TF SAME zero padding)
-  // and for frames past the end of the clip's frame range
-  for (int i = threadIdx.x; i < G * N; i += blockDim.x) {
-    const int g = i / N, t = i & (N - 1);
-    const int fa = 2 * g, fb = 2 * g + 1;
-    const int ia = (f0 + fa) * p.n_hop - p.left_pad + t, ib = ia + p.n_hop;
-    float xa = 0.f, xb = 0.f;
-    if (fa < nfr && ia >= 0 && ia < p.n_samples)
-      xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] * (1.0f / 32768.0f)
-               : reinterpret_cast<const float*>(stage)[ia - a_lo];
-    if (fb < nfr && ib >= 0 && ib < p.n_samples)
-      xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
-               : reinterpret_cast<const float*>(stage)[ib - a_lo];
-    const float w = __ldg(win + t);
-    zbuf[i] = make_float2(xa * w, xb * w);
-  }
-  __syncthreads();
-  fft_dif_batched<N, G>(zbuf, tw);
-  // separate the two real spectra: XA[k] = (Z[k] + conj(Z[N-k]))/2 ; XB[k] = (Z[k] - conj(Z[N-k]))/(2i)
-  for (int i = threadIdx.x; i < G * NF; i += blockDim.x) {
-    const int g = i / NF, k = i - g * NF;
-    const int rk = __brev((unsigned)k) >> (32 - LOGN);
-    const int rnk = __brev((unsigned)((N - k) & (N - 1))) >> (32 - LOGN);
-    const float2 zk = zbuf[g * N + rk], zn = zbuf[g * N + rnk];
-    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-    const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
-    pw[(2 * g) * PWS + k] = ar * ar + ai * ai;
-    pw[(2 * g + 1) * PWS + k] = br * br + bi * bi;
-  }
-  __syncthreads();
-  // projection + log: one (frame pair, output bin) item per thread-iteration
-  for (int i = threadIdx.x; i < G * p.n_out; i += blockDim.x) {
-    const int g = i / p.n_out, m = i - g * p.n_out;
-    const float* pw0 = pw + (2 * g) * PWS;
-    const float* pw1 = pw0 + PWS;
-    const bool has_a = 2 * g < nfr, has_b = 2 * g + 1 < nfr;
-    float va, vb;
-    if (p.mel) {
-      const int k0 = p.mel_start[m], n = p.mel_count[m];
-      const float* w = melw + p.mel_offset[m];
-      float sa = 0.f, sb = 0.f;
-      for (int k = 0; k < n; ++k) {
-        const float wk = __ldg(w + k);
-        sa = fmaf(pw0[k0 + k], wk, sa);
-        sb = fmaf(pw1[k0 + k], wk, sb);
+
+#pragma unroll 1
+  for (int it = 0; it < F::ITERS; ++it) {
+    const int fa = 2 * (it * NC + g), fb = fa + 1;   // frame fa -> real part, fb -> imaginary part
+    Cx v[16];
+    // windowed samples x[u + T r]; zero outside the clip (TF SAME zero padding) and for frames past the clip's last one
+    {
+      const int ia0 = (f0 + fa) * p.n_hop - p.left_pad + u;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int ia = ia0 + T * r, ib = ia + p.n_hop;
+        float xa = 0.f, xb = 0.f;
+        if (fa < nfr && ia >= 0 && ia < p.n_samples)
+          xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] * (1.0f / 32768.0f)
+                   : reinterpret_cast<const float*>(stage)[ia - a_lo];
+        if (fb < nfr && ib >= 0 && ib < p.n_samples)
+          xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
+                   : reinterpret_cast<const float*>(stage)[ib - a_lo];
+        const float w = __ldg(win + u + T * r);
+        v[r] = cx(xa * w, xb * w);
       }
-      va = sqrtf(sa);
-      vb = sqrtf(sb);
-    } else {
-      va = sqrtf(pw0[m]);
-      vb = sqrtf(pw1[m]);
     }
-    if (p.decibel) {
-      va = 10.0f * (logf(fmaxf(va, 1e-10f)) / 2.302585092994046f);
-      vb = 10.0f * (logf(fmaxf(vb, 1e-10f)) / 2.302585092994046f);
-      if (has_a) local_max = fmaxf(local_max, va);
-      if (has_b) local_max = fmaxf(local_max, vb);
-    } else {
-      va = logf(fmaxf(va, 1e-12f)) / 5.0f;
-      vb = logf(fmaxf(vb, 1e-12f)) / 5.0f;
+    fft_step1<N>(v, u, bre, bim, tw);
+    __syncthreads();
+    fft_step2_load<N>(v, u, bre, bim);
+    __syncthreads();   // S1 fully read before S2 overwrites the buffer
+    fft_step2_store<N>(v, u, bre, bim, tw);
+    __syncthreads();
+    fft_step3_load<N>(v, u, bre, bim);
+    __syncthreads();
+    fft_step3_store<N>(v, u, bre, bim);
+    __syncthreads();
+    // separate the two real spectra: XA[k] = (Z[k] + conj(Z[N-k]))/2 ; XB[k] = (Z[k] - conj(Z[N-k]))/(2i)
+    for (int k = u; k < NF; k += T) {
+      const int nk = (N - k) & (N - 1);
+      const float zkx = bre[k], zky = bim[k], znx = bre[nk], zny = bim[nk];
+      const float ar = 0.5f * (zkx + znx), ai = 0.5f * (zky - zny);
+      const float br = 0.5f * (zky + zny), bi = -0.5f * (zkx - znx);
+      pw0[k] = ar * ar + ai * ai;
+      pw1[k] = br * br + bi * bi;
     }
-    tile[m * kFramesPerCta + 2 * g] = va;
-    tile[m * kFramesPerCta + 2 * g + 1] = vb;
+    __syncthreads();
+    // projection + log: one output bin (both frames of the pair) per thread-iteration
+    const bool has_a = fa < nfr, has_b = fb < nfr;
+    for (int m = u; m < p.n_out; m += T) {
+      float va, vb;
+      if (p.mel) {
+        const int k0 = __ldg(p.mel_start + m), n = __ldg(p.mel_count + m);
+        const float* w = melw + __ldg(p.mel_offset + m);
+        float sa = 0.f, sb = 0.f;
+        for (int k = 0; k < n; ++k) {
+          const float wk = __ldg(w + k);
+          sa = fmaf(pw0[k0 + k], wk, sa);
+          sb = fmaf(pw1[k0 + k], wk, sb);
+        }
+        va = sqrtf(sa);
+        vb = sqrtf(sb);
+      } else {
+        va = sqrtf(pw0[m]);
+        vb = sqrtf(pw1[m]);
+      }
+      if (p.decibel) {
+        va = 10.0f * (logf(fmaxf(va, 1e-10f)) / 2.302585092994046f);
+        vb = 10.0f * (logf(fmaxf(vb, 1e-10f)) / 2.302585092994046f);
+        if (has_a) local_max = fmaxf(local_max, va);
+        if (has_b) local_max = fmaxf(local_max, vb);
+      } else {
+        va = logf(fmaxf(va, 1e-12f)) / 5.0f;
+        vb = logf(fmaxf(vb, 1e-12f)) / 5.0f;
+      }
+      tile[m * FR + fa] = va;
+      tile[m * FR + fb] = vb;
+    }
+    // (the next iteration's first shared-memory write -- step 1 into bre / bim -- is ordered after this iteration's last
+    // read of them by the barrier above; pw is rewritten only after three more barriers)
   }
   __syncthreads();
   // write the tile: rows of nfr contiguous floats
-  for (int i = threadIdx.x; i < p.n_out * kFramesPerCta; i += blockDim.x) {
-    int m = i / kFramesPerCta, f = i % kFramesPerCta;
+  for (int i = threadIdx.x; i < p.n_out * FR; i += blockDim.x) {
+    int m = i / FR, f = i % FR;
     if (f < nfr) raw[((size_t)b * p.n_out + m) * p.n_frames + f0 + f] = tile[i];
   }
   if (p.decibel) {
@@ -329,25 +297,28 @@ __global__ void k_frontend_finish(float* __restrict__ x, const int* __restrict__
 
 template <int N, bool I16>
 static int launch_fe(const FrontendPlan& p, const void* audio, int B, float* out, int* clip_max, cudaStream_t s) {
+  typedef FftGeom<N> G;
+  typedef FeCfg<N> F;
   constexpr int NF = N / 2 + 1;
   constexpr int ES = I16 ? 2 : 4;
-  size_t stage_elems = (size_t)(kFramesPerCta - 1) * p.n_hop + N + 16;
-  size_t smem = (size_t)kFePairs * N * 8 + (size_t)(N / 2) * 8 + kFramesPerCta * (size_t)(NF + 3) * 4 +
-                (size_t)p.n_out * kFramesPerCta * 4 + 16 + stage_elems * ES;
+  size_t stage_elems = (size_t)(F::FR - 1) * p.n_hop + N + 16;
+  size_t smem = (size_t)F::NC * G::BUF * 8 + (size_t)F::NC * 2 * (NF + 3) * 4 + (size_t)p.n_out * F::FR * 4 + 16 + stage_elems * ES;
   static PerDeviceOnce once;
   if (once.needed()) {
-    L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    L3_CHECK_CUDA(cudaFuncSetAttribute(k_frontend<N, I16>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
     once.mark();
   }
-  L3_REQUIRE(smem <= 100 * 1024, "frontend smem %zu too large", smem);
-  dim3 grid(ceil_div(p.n_frames, kFramesPerCta), B);
+  L3_REQUIRE(smem <= 64 * 1024, "frontend smem %zu too large", smem);
+  dim3 grid(ceil_div(p.n_frames, F::FR), B);
   k_frontend<N, I16><<<grid, kFeThreads, smem, s>>>(p, audio, out, clip_max);
   L3_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_frontend(const FrontendPlan& p, const void* audio, int is_i16, int B, float* out, int* clip_max,
-                    cudaStream_t s) {
+                    cudaStream_t s, int finish) {
   L3_REQUIRE(p.n_dft == 512 || p.n_dft == 2048, "frontend: n_dft %d", p.n_dft);
   L3_REQUIRE((p.clip_stride * (is_i16 ? 2 : 4)) % 16 == 0, "frontend: clip stride %lld breaks 16-byte alignment", p.clip_stride);
   if (p.decibel) {
@@ -360,7 +331,7 @@ int launch_frontend(const FrontendPlan& p, const void* audio, int is_i16, int B,
   else
     rc = is_i16 ? launch_fe<512, true>(p, audio, B, out, clip_max, s) : launch_fe<512, false>(p, audio, B, out, clip_max, s);
   if (rc) return rc;
-  if (p.decibel) {
+  if (p.decibel && finish) {
     long long per_clip = (long long)p.n_out * p.n_frames, total = per_clip * B;
     int blocks = (int)((total + 1023) / 1024);
     if (blocks > 148 * 8) blocks = 148 * 8;

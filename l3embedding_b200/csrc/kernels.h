@@ -30,18 +30,22 @@ size_t frontend_table_bytes(int n_dft, int n_mels);
 int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem, cudaStream_t s);
 // audio: int16 (is_i16=1) or float (B, n_samples). raw: (B, n_out, n_frames) float scratch; clip_max: int[B].
 // out: (B, n_out, n_frames) float final.
+// finish = 0 (decibel plans): stop after the per-clip maximum; `out` then holds the un-referenced dB map and the caller
+// applies max(x - clip max, -80) itself (launch_input_stage mode 2 fuses it with the input BatchNorm's passes)
 int launch_frontend(const FrontendPlan& p, const void* audio, int is_i16, int B, float* out, int* clip_max,
-                    cudaStream_t s);
+                    cudaStream_t s, int finish = 1);
 
 // ---- elementwise / reductions (elementwise.cu) ------------------------------------------
-int launch_video_to_f32(const uint8_t* v, float* out, long long n, cudaStream_t s);
 template <typename T>
 int launch_channel_stats(const T* x, long long rows, int C, int relu, double* sum2C, cudaStream_t s);
 int launch_bn_finalize(const BnRef& bn, long long count, int training, float momentum, float eps, int unbiased,
                        cudaStream_t s);
+// input stage of a tower in one pass (C = 1 | 3).  mode 0: x0 holds the float input; 1: u8 video -> 2*(x/255)-1 -> x0;
+// 2: dB finish of the front-end's raw map in place (x0 = max(x0 - clip max, -80)).  sum != null: per-channel sum / sum of
+// squares (fp64, zeroed here).  xin != null: (scale ? v*scale+shift : v) -> zero-haloed padded (B,H+2,W+2,C).
 template <typename T>
-int launch_affine_small(const float* x, T* out, int B, int H, int W, int C, const float* scale, const float* shift,
-                        cudaStream_t s);   // out: zero-haloed padded (B,H+2,W+2,C)
+int launch_input_stage(int mode, const uint8_t* u8, float* x0, T* xin, int B, int H, int W, int C, const float* scale,
+                       const float* shift, const int* clip_max, double* sum, cudaStream_t s);
 template <typename T>
 int launch_zero_halo(T* buf, int B, int H, int W, int C, cudaStream_t s);
 // zsel / sel (optional, pooled layers in training): the winning pre-activation (B,H/2,W/2,C) and one byte per pooled

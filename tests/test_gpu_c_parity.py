@@ -122,7 +122,7 @@ def test_embedding_matches_golden_fixture(mode):
 
 
 def test_video_scaling_is_bit_exact():
-    """train.py:186: `2 * img_as_float(u8).astype('float32') - 1` -- the device's u8 -> float conversion (k_video_to_f32)
+    """train.py:186: `2 * img_as_float(u8).astype('float32') - 1` -- the device's u8 -> float conversion (k_input_stage mode 1)
     against the numpy expression, bit for bit (cnn_L3_orig has no input BN, so x0 is the scaled frame itself)."""
     B = 2
     video, audio, _ = O.synthetic_batch(B, seed=31)

@@ -535,3 +535,21 @@ def test_framing_equals_the_reference_function_executed():
         assert a.x.shape == b.x.shape and np.array_equal(a.x, b.x), n
         padded, hop, n_frames = F.frame_signal(audio)
         assert n_frames == a.x.shape[0] and hop == 4800
+
+
+def test_frontend_register_fft_on_the_host(tmp_path):
+    """The front-end's FFT (csrc/frontend_fft.cuh: 16 x 16 x R3 in registers, three shared-memory exchanges) is
+    __host__ __device__: the harness runs the kernel's own per-thread phases on the CPU against a float64 DFT."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "fe_fft_host.cu")
+    exe = str(tmp_path / "fe_fft_host")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True,
+                   capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    errs = dict(line.split() for line in r.stdout.strip().splitlines())
+    assert r.returncode == 0, r.stdout
+    assert all(float(v) < 5e-7 for v in errs.values()), errs

@@ -1,5 +1,5 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list into per-kernel time for ONE step
-(the launches between two consecutive k_video_to_f32, i.e. one l3_forward_backward + Adam)."""
+(the launches between two consecutive k_pack_weights_batch, the first kernel of l3_forward_backward, i.e. one step + Adam)."""
 import collections
 import csv
 import re
@@ -14,7 +14,7 @@ def load(path):
 
 def main(path, which=3, detail=False):
     rows = load(path)
-    idx = [i for i, (n, t, g) in enumerate(rows) if "k_video_to_f32" in n]
+    idx = [i for i, (n, t, g) in enumerate(rows) if "k_pack_weights_batch" in n]
     step = rows[idx[which]:idx[which + 1]]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, t, g in step:
