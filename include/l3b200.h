@@ -163,7 +163,7 @@ int l3_conv3x3_fwd_stats(const void* in, const float* w, const float* bias, void
 int l3_conv3x3_dgrad(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, int dtype,
                      int use_tc, void* scratch, void* stream);
 /* the tensor-core data gradient with pass 1 of the BN/ReLU backward of the layer below fused into its epilogue (what
- * the training step runs for un-pooled Conv -> BN -> ReLU layers): as l3_conv3x3_dgrad with dtype bf16 / use_tc 1, plus
+ * the training step runs for un-pooled Conv -> BN -> ReLU layers of 128 channels and more): as l3_conv3x3_dgrad with dtype bf16 / use_tc 1, plus
  * z_below (B,H,W,Cin) bf16, scale / shift (Cin floats: bn(z) = scale*z + shift) and
  * sums: device double[2*Cin] <- sum(dy), sum(dy*z_below) per channel, dy = da where bn(z_below) > 0, else 0. */
 int l3_conv3x3_dgrad_stats(const void* dz, const float* w, void* da, int B, int H, int W, int Cin, int Cout, void* scratch,

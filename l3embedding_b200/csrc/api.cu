@@ -679,11 +679,20 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
   }
   // data gradient: da = conv(dz, flip/transpose(w))
   ConvLayer& Lp = tw.L[l - 1];
+  // Pass 1 of the BN/ReLU backward of the layer below (sum dy, sum dy*z) rides in the data gradient's epilogue where that
+  // pays: measured at B = 64 (tools/run_op.py dgrad vs dgrad_stats) the fused launch costs +14 / +19 / +55 us at 512 / 256 /
+  // 128 channels against 38 / 80 / 110 us for the stand-alone pass it replaces (which re-reads da and z from HBM); at 64
+  // channels (N = 64 tiles, shared-memory bound) it is neutral, and pooled layers take their sums from the recorded routing.
+  const bool fuse_stats = L.tc && c->use_tc && conv_tc_fuses_bwd_stats(Lp.Cout) && !Lp.pool && !Lp.relu_first;
   {
     ProfScope ps(c, PROF_CONV_DGRAD, s);
     if (L.tcs && c->use_tc) {
       // sp_z holds the bf16 parts of dz (split for the weight gradient above, same stream)
       if (launch_conv3x3_tc_split(tw.sp_z, L.wt_pk, nullptr, (float*)da, B, L.H, L.W, L.Cout, L.Cin, 0, 1.f, s)) return -1;
+    } else if (fuse_stats) {
+      if (launch_dgrad3x3_tc_bwdstats((const bf16*)dz, L.wt_pk, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, (const bf16*)Lp.z,
+                                      Lp.bn.scale, Lp.bn.shift, Lp.bn.sum, s))
+        return -1;
     } else if (L.tc && c->use_tc) {
       if (launch_conv3x3_tc((const bf16*)dz, L.wt_pk, nullptr, (bf16*)da, B, L.H, L.W, L.Cout, L.Cin, nullptr, 0, s)) return -1;
     } else {
@@ -693,8 +702,8 @@ static int tower_backward_layer(l3_ctx* c, Tower& tw, int B, int l) {
   }
   // activation + BN backward of layer l-1: da (at its pooled resolution) -> dz(l-1) (padded, full resolution)
   long long rows_p = (long long)B * Lp.H * Lp.W;
-  if (launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s, (const T*)Lp.zsel,
-                          Lp.sel))
+  if (!fuse_stats && launch_bwd_stats<T>(da, (const T*)Lp.z, B, Lp.H, Lp.W, Lp.Cout, Lp.bn, Lp.pool, Lp.relu_first, s,
+                                         (const T*)Lp.zsel, Lp.sel))
     return -1;
   if (launch_bn_bwd_finalize(Lp.bn, rows_p, sizeof(T) == 4 ? 2 : 1, s)) return -1;
   // dz(l-1) goes into the buffer the weight gradient of layer l+1 read

@@ -974,10 +974,11 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
   return launch_conv3_any(BN, in, packed_w, bias, out, H, W, Cin, Cout, Mp, nullptr, relu_first, s, bf);
 }
 
-// Pass 1 of the BN/ReLU backward in the dgrad epilogue (EPI_BWD) measured neutral at B = 64 (356 us fused vs 210 + 135 us
-// separate at 64 channels: the extra z loads sit on the epilogue's critical path), so the step keeps the separate pass;
-// the fused launch stays available as a stand-alone, tested op (l3_conv3x3_dgrad_stats).
-int conv_tc_fuses_bwd_stats() { return 0; }
+// Pass 1 of the BN/ReLU backward in the dgrad epilogue (EPI_BWD): the z loads sit on the epilogue's critical path, so it
+// pays only where the main loop is long enough to hide them -- 128 channels and up (api.cu tower_backward_layer has the
+// measured numbers); at 64 channels (356 us fused vs 210 + 135 us separate) the step keeps the separate pass.
+// `channels_below` = channels of the layer whose statistics would be fused (= the data gradient's output channels).
+int conv_tc_fuses_bwd_stats(int channels_below) { return channels_below >= 128 ? 1 : 0; }
 
 // Parity mode on tensor cores: `in` holds 16-bit SPLIT operands concatenated along the channel axis,
 //   [hi | lo | hi] (3*Cin channels, zero-haloed padded) x packed weights [hi ; hi ; lo]  ->  a_hi w_hi + a_lo w_hi + a_hi w_lo

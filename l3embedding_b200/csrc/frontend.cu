@@ -21,7 +21,7 @@ namespace l3 {
 // One CTA = 128 threads = FR consecutive frames of one clip, two real frames packed into one complex transform that
 // lives in REGISTERS (frontend_fft.cuh: N = 16 x 16 x R3, three shared-memory exchanges).  N = 2048: one transform at a time
 // (T = 128 threads), two iterations; N = 512: four transforms side by side (T = 32), one iteration.  ~37 KB (50 KB) of
-// shared memory and <= 102 registers: five (four) CTAs per SM.
+// shared memory and <= 85 registers: six (four) CTAs per SM.
 static const int kFeThreads = 128;
 template <int N>
 struct FeCfg {
@@ -29,7 +29,7 @@ struct FeCfg {
   static const int NC = kFeThreads / T;          // transforms in flight per CTA
   static const int FR = (N == 2048) ? 4 : 8;     // frames per CTA
   static const int ITERS = FR / (2 * NC);
-  static const int CTAS = (N == 2048) ? 5 : 4;   // resident CTAs per SM aimed at
+  static const int CTAS = (N == 2048) ? 6 : 4;   // resident CTAs per SM aimed at (registers allow it; int16 input: 37 KB each)
 };
 
 // ---- host-side table construction (float64, cast to float32 as kapre stores them) ---------------------
@@ -74,20 +74,22 @@ static void build_mel(int sr, int n_fft, int n_mels, std::vector<int>& start, st
 
 size_t frontend_table_bytes(int n_dft, int n_mels) {
   size_t nf = n_dft / 2 + 1;
-  // twiddle + window + 3 int tables + weights (upper bound: 2 non-zeros per bin + slack)
-  return (size_t)(n_dft / 2) * sizeof(float2) + (size_t)n_dft * sizeof(float) + 3 * (size_t)(n_mels + 1) * sizeof(int) +
-         (4 * nf + 64) * sizeof(float) + 256;
+  // twiddles (step 1: 16 x n_dft/16, step 2: 16 x n_dft/256) + 2 windows + 3 int tables + weights (upper bound: 2
+  // non-zeros per bin + slack)
+  return (size_t)(n_dft + n_dft / 16 + 16) * sizeof(float2) + 2 * (size_t)n_dft * sizeof(float) +
+         3 * (size_t)(n_mels + 1) * sizeof(int) + (4 * nf + 64) * sizeof(float) + 256;
 }
 
 int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem, cudaStream_t s) {
   const int N = plan->n_dft;
-  std::vector<float2> tw(N / 2);
-  for (int j = 0; j < N / 2; ++j) {
-    double a = -2.0 * M_PI * j / N;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
+  std::vector<float2> tw1(N), tw2(N / 16);
+  if (N == 2048) fft_build_twiddles<2048>(tw1.data(), tw2.data());
+  else fft_build_twiddles<512>(tw1.data(), tw2.data());
+  std::vector<float> win(N), win16(N);
+  for (int t = 0; t < N; ++t) {
+    win[t] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * t / N));
+    win16[t] = win[t] * (1.0f / 32768.0f);   // exact: a power of two
   }
-  std::vector<float> win(N);
-  for (int t = 0; t < N; ++t) win[t] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * t / N));
   char* p = reinterpret_cast<char*>(dev_mem);
   auto put = [&](const void* src, size_t bytes) -> void* {
     void* dst = p;
@@ -95,8 +97,10 @@ int frontend_build_tables(FrontendPlan* plan, int sr, int n_mels, void* dev_mem,
     p += (bytes + 15) / 16 * 16;
     return dst;
   };
-  plan->twiddle = (const float2*)put(tw.data(), tw.size() * sizeof(float2));
+  plan->tw1 = (const float2*)put(tw1.data(), tw1.size() * sizeof(float2));
+  plan->tw2 = (const float2*)put(tw2.data(), tw2.size() * sizeof(float2));
   plan->window = (const float*)put(win.data(), win.size() * sizeof(float));
+  plan->window_i16 = (const float*)put(win16.data(), win16.size() * sizeof(float));
   if (plan->mel) {
     std::vector<int> st, ct, of;
     std::vector<float> wt;
@@ -182,8 +186,8 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   float* const bim = bim_all + g * G::BUF;
   float* const pw0 = pw_all + g * 2 * PWS;
   float* const pw1 = pw0 + PWS;
-  const LdgTw tw{p.twiddle};
-  const float* __restrict__ win = p.window;      // through L1: shared by every CTA
+  const LdgTw tw1{p.tw1}, tw2{p.tw2};             // tables through L1: shared by every CTA
+  const float* __restrict__ win = I16 ? p.window_i16 : p.window;
   const float* __restrict__ melw = p.mel_weight;
   float local_max = -INFINITY;
 
@@ -191,28 +195,46 @@ k_frontend(FrontendPlan p, const void* __restrict__ audio, float* __restrict__ r
   for (int it = 0; it < F::ITERS; ++it) {
     const int fa = 2 * (it * NC + g), fb = fa + 1;   // frame fa -> real part, fb -> imaginary part
     Cx v[16];
-    // windowed samples x[u + T r]; zero outside the clip (TF SAME zero padding) and for frames past the clip's last one
+    // windowed samples x[u + T r]; zero outside the clip (TF SAME zero padding) and for frames past the clip's last one.
+    // int16 samples: (float)s * (w * 2^-15) == ((float)s * 2^-15) * w bit for bit (pcm2float, audio.py:21-31)
     {
       const int ia0 = (f0 + fa) * p.n_hop - p.left_pad + u;
+      if (fb < nfr && ia0 - u >= 0 && ia0 - u + p.n_hop + N <= p.n_samples) {
+        // both frames of the pair lie inside the clip (all but the first and last few frames): no bounds checks
+        if (I16) {
+          const short* sp = reinterpret_cast<const short*>(stage) + (ia0 - a_lo);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int ia = ia0 + T * r, ib = ia + p.n_hop;
-        float xa = 0.f, xb = 0.f;
-        if (fa < nfr && ia >= 0 && ia < p.n_samples)
-          xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] * (1.0f / 32768.0f)
-                   : reinterpret_cast<const float*>(stage)[ia - a_lo];
-        if (fb < nfr && ib >= 0 && ib < p.n_samples)
-          xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] * (1.0f / 32768.0f)
-                   : reinterpret_cast<const float*>(stage)[ib - a_lo];
-        const float w = __ldg(win + u + T * r);
-        v[r] = cx(xa * w, xb * w);
+          for (int r = 0; r < 16; ++r) {
+            const float w = __ldg(win + u + T * r);
+            v[r] = cx((float)sp[T * r] * w, (float)sp[T * r + p.n_hop] * w);
+          }
+        } else {
+          const float* sp = reinterpret_cast<const float*>(stage) + (ia0 - a_lo);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float w = __ldg(win + u + T * r);
+            v[r] = cx(sp[T * r] * w, sp[T * r + p.n_hop] * w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int ia = ia0 + T * r, ib = ia + p.n_hop;
+          float xa = 0.f, xb = 0.f;
+          if (fa < nfr && ia >= 0 && ia < p.n_samples)
+            xa = I16 ? (float)reinterpret_cast<const short*>(stage)[ia - a_lo] : reinterpret_cast<const float*>(stage)[ia - a_lo];
+          if (fb < nfr && ib >= 0 && ib < p.n_samples)
+            xb = I16 ? (float)reinterpret_cast<const short*>(stage)[ib - a_lo] : reinterpret_cast<const float*>(stage)[ib - a_lo];
+          const float w = __ldg(win + u + T * r);
+          v[r] = cx(xa * w, xb * w);
+        }
       }
     }
-    fft_step1<N>(v, u, bre, bim, tw);
+    fft_step1<N>(v, u, bre, bim, tw1);
     __syncthreads();
     fft_step2_load<N>(v, u, bre, bim);
     __syncthreads();   // S1 fully read before S2 overwrites the buffer
-    fft_step2_store<N>(v, u, bre, bim, tw);
+    fft_step2_store<N>(v, u, bre, bim, tw2);
     __syncthreads();
     fft_step3_load<N>(v, u, bre, bim);
     __syncthreads();

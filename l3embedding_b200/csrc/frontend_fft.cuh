@@ -11,6 +11,7 @@
 // thread by thread, against a float64 DFT (no GPU in the build container).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 
 namespace l3 {
 
@@ -82,14 +83,6 @@ L3_HD void dft8(Cx (&v)[8]) {
   for (int k = 0; k < 8; ++k) v[k] = o[k];
 }
 
-// W_N^j for j in [0, N) from the half table tw[0 .. N/2) = exp(-2 pi i j / N)
-template <int N, typename TwLoad>
-L3_HD Cx twiddle(const TwLoad& tw, int j) {
-  const bool neg = j >= N / 2;
-  const float2 w = tw(neg ? j - N / 2 : j);
-  return neg ? cx(-w.x, -w.y) : cx(w.x, w.y);
-}
-
 template <int N>
 struct FftGeom {
   static const int T = N / 16;           // threads per transform
@@ -99,14 +92,23 @@ struct FftGeom {
   static const int BUF = (16 * LD1 > 256 * LD2) ? (16 * LD1 > N ? 16 * LD1 : N) : (256 * LD2 > N ? 256 * LD2 : N);
 };
 
+// Twiddle tables, laid out the way the threads read them (consecutive threads -> consecutive entries, no index arithmetic):
+//   tw1[q * T + t]    = W_N^(t q)         q in [0,16), t  in [0,T)      (step 1)
+//   tw2[q2 * R3 + t2] = W_N^(16 t2 q2)    q2 in [0,16), t2 in [0,R3)    (step 2)
+// `Tw` is a functor int -> float2 over such a table (device: __ldg; host test: plain load).
+
 // step 1 (after the caller filled v[r] = x[t + T r]): DFT, twiddle, store
-template <int N, typename TwLoad>
-L3_HD void fft_step1(Cx (&v)[16], int t, float* re, float* im, const TwLoad& tw) {
+template <int N, typename Tw>
+L3_HD void fft_step1(Cx (&v)[16], int t, float* re, float* im, const Tw& tw1) {
   typedef FftGeom<N> G;
   dft16(v);
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    const Cx y = q == 0 ? v[0] : cmul(v[q], twiddle<N>(tw, t * q));
+    Cx y = v[0];
+    if (q != 0) {
+      const float2 w = tw1(q * G::T + t);
+      y = cmul(v[q], cx(w.x, w.y));
+    }
     re[q * G::LD1 + t] = y.x;
     im[q * G::LD1 + t] = y.y;
   }
@@ -119,14 +121,18 @@ L3_HD void fft_step2_load(Cx (&v)[16], int u, const float* re, const float* im) 
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = cx(re[q * G::LD1 + t2 + G::R3 * r], im[q * G::LD1 + t2 + G::R3 * r]);
 }
-template <int N, typename TwLoad>
-L3_HD void fft_step2_store(Cx (&v)[16], int u, float* re, float* im, const TwLoad& tw) {
+template <int N, typename Tw>
+L3_HD void fft_step2_store(Cx (&v)[16], int u, float* re, float* im, const Tw& tw2) {
   typedef FftGeom<N> G;
   const int q = u / G::R3, t2 = u % G::R3;
   dft16(v);
 #pragma unroll
   for (int q2 = 0; q2 < 16; ++q2) {
-    const Cx y = q2 == 0 ? v[0] : cmul(v[q2], twiddle<N>(tw, 16 * t2 * q2));
+    Cx y = v[0];
+    if (q2 != 0) {
+      const float2 w = tw2(q2 * G::R3 + t2);
+      y = cmul(v[q2], cx(w.x, w.y));
+    }
     re[(q2 * 16 + q) * G::LD2 + t2] = y.x;
     im[(q2 * 16 + q) * G::LD2 + t2] = y.y;
   }
@@ -167,6 +173,23 @@ L3_HD void fft_step3_store(Cx (&v)[16], int u, float* re, float* im) {
       re[p + 256] = d.x;   im[p + 256] = d.y;
     }
   }
+}
+
+// host: fill the two tables (float64 angles, rounded once)
+template <int N>
+inline void fft_build_twiddles(float2* tw1, float2* tw2) {
+  typedef FftGeom<N> G;
+  const double kTwoPi = 6.283185307179586476925286766559;
+  for (int q = 0; q < 16; ++q)
+    for (int t = 0; t < G::T; ++t) {
+      const double a = -kTwoPi * (double)((q * t) % N) / N;
+      tw1[q * G::T + t] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int q2 = 0; q2 < 16; ++q2)
+    for (int t2 = 0; t2 < G::R3; ++t2) {
+      const double a = -kTwoPi * (double)((16 * t2 * q2) % N) / N;
+      tw2[q2 * G::R3 + t2] = make_float2((float)cos(a), (float)sin(a));
+    }
 }
 
 }  // namespace l3

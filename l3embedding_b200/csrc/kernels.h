@@ -16,13 +16,15 @@ struct FrontendPlan {
   int n_samples;    // 48000
   long long clip_stride;  // samples between the starts of consecutive clips (n_samples; the hop when framing on device)
   // device constants (built once per ctx by frontend_build_tables)
-  const float2* twiddle;    // n_dft/2 entries exp(-2 pi i j / n_dft)
+  const float2* tw1;        // FFT step-1 twiddles [16][n_dft/16]   (frontend_fft.cuh)
+  const float2* tw2;        // FFT step-2 twiddles [16][n_dft/256]
   const float* window;      // n_dft periodic hann
+  const float* window_i16;  // the same times 2^-15 (exact): int16 samples are windowed and scaled by one multiply
   const int* mel_start;     // [n_mels]
   const int* mel_count;     // [n_mels]
   const int* mel_offset;    // [n_mels] into mel_weight
   const float* mel_weight;  // packed non-zeros
-  int mel_nnz;              // number of packed non-zeros (staged into shared memory by the kernel)
+  int mel_nnz;              // number of packed non-zeros
 };
 // bytes of device memory needed for the tables
 size_t frontend_table_bytes(int n_dft, int n_mels);
@@ -171,7 +173,7 @@ int launch_conv3x3_tc_act(const bf16* in, const bf16* packed_w, const float* bia
 // Parity mode on tensor cores (split 16-bit operands, fp32 accumulate and output): see conv_tc.cu
 int launch_conv3x3_tc_split(const void* in_split, const void* packed_w_split, const float* bias, float* out, int B, int H, int W,
                             int Cin, int Cout, int fp16, float out_scale, cudaStream_t s);
-int conv_tc_fuses_bwd_stats();   // 0: measured neutral, the step keeps the separate statistics pass (stand-alone op only)
+int conv_tc_fuses_bwd_stats(int channels_below);   // 1 where the fused epilogue beats the stand-alone statistics pass
 int launch_dgrad3x3_tc_bwdstats(const bf16* dz, const bf16* packed_wt, bf16* da, int B, int H, int W, int Cout, int Cin,
                                 const bf16* z_below, const float* scale_below, const float* shift_below, double* sums,
                                 cudaStream_t s);

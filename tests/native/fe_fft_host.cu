@@ -15,12 +15,9 @@ struct HostTw {
 template <int N>
 static double run(unsigned seed) {
   typedef FftGeom<N> G;
-  std::vector<float2> tw(N / 2);
-  for (int j = 0; j < N / 2; ++j) {
-    double a = -2.0 * M_PI * j / N;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
-  }
-  const HostTw twl{tw.data()};
+  std::vector<float2> tw1(16 * G::T), tw2(16 * G::R3);
+  fft_build_twiddles<N>(tw1.data(), tw2.data());
+  const HostTw twl1{tw1.data()}, twl2{tw2.data()};
   std::vector<double> xr(N), xi(N);
   srand(seed);
   for (int n = 0; n < N; ++n) { xr[n] = rand() / (double)RAND_MAX - 0.5; xi[n] = rand() / (double)RAND_MAX - 0.5; }
@@ -30,10 +27,10 @@ static double run(unsigned seed) {
   for (int t = 0; t < G::T; ++t) {
     Cx(&v)[16] = R(t);
     for (int r = 0; r < 16; ++r) v[r] = cx((float)xr[t + G::T * r], (float)xi[t + G::T * r]);
-    fft_step1<N>(v, t, re.data(), im.data(), twl);
+    fft_step1<N>(v, t, re.data(), im.data(), twl1);
   }
   for (int u = 0; u < G::T; ++u) fft_step2_load<N>(R(u), u, re.data(), im.data());
-  for (int u = 0; u < G::T; ++u) fft_step2_store<N>(R(u), u, re.data(), im.data(), twl);
+  for (int u = 0; u < G::T; ++u) fft_step2_store<N>(R(u), u, re.data(), im.data(), twl2);
   for (int u = 0; u < G::T; ++u) fft_step3_load<N>(R(u), u, re.data(), im.data());
   for (int u = 0; u < G::T; ++u) fft_step3_store<N>(R(u), u, re.data(), im.data());
   double worst = 0, scale = 0;

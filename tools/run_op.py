@@ -1,7 +1,7 @@
 """Run ONE convolution op of the C ABI at a real layer size (for `ncu -k regex:...` captures and quick timing).
 
     python tools/run_op.py --op fwd_stats --shape 64,224,224,3,64 --iters 5
-    ops: fwd | fwd_stats | dgrad | wgrad       shape: B,H,W,Cin,Cout
+    ops: fwd | fwd_stats | dgrad | dgrad_stats | wgrad       shape: B,H,W,Cin,Cout
 """
 import argparse
 import ctypes as C
@@ -38,6 +38,10 @@ def main():
     p = lambda t: C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    zb = torch.randn(B, H, W, Ci, generator=g, device="cuda").bfloat16()      # z of the layer below (dgrad_stats)
+    sc = torch.rand(Ci, generator=g, device="cuda") + 0.5
+    sh = torch.randn(Ci, generator=g, device="cuda") * 0.1
+    sums = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
 
     def run():
         if a.op == "fwd":
@@ -46,6 +50,8 @@ def main():
             rc = lib.l3_conv3x3_fwd_stats(p(xp), p(w), p(b), p(out), B, H, W, Ci, Co, p(scratch), p(stats), 0, st)
         elif a.op == "dgrad":
             rc = lib.l3_conv3x3_dgrad(p(dzp), p(w), p(da), B, H, W, Ci, Co, 1, 1, p(scratch), st)
+        elif a.op == "dgrad_stats":   # dgrad with pass 1 of the BN/ReLU backward of the layer below in its epilogue
+            rc = lib.l3_conv3x3_dgrad_stats(p(dzp), p(w), p(da), B, H, W, Ci, Co, p(scratch), p(zb), p(sc), p(sh), p(sums), st)
         else:
             rc = lib.l3_conv3x3_wgrad(p(xp), p(dzp), p(dw), p(db), B, H, W, Ci, Co, 1, 1, st)
         _lib.check(rc, a.op)
