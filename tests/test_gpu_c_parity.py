@@ -121,6 +121,25 @@ def test_embedding_matches_golden_fixture(mode):
             assert np.abs(eng.embed_audio(audio, "original").cpu().numpy() - z[mt + "/embedding_original"]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("model_type", ["cnn_L3_melspec2", "cnn_L3_kapredbinputbn", "cnn_L3_orig"])
+def test_fused_input_stage_equals_the_standalone_front_end(model_type):
+    """Inside a tower the dB reference (max(x - clip max, -80)) is applied by the fused input pass (k_input_stage mode 2,
+    together with the input BatchNorm), the stand-alone front-end op applies it with its own finish kernel: the tower's
+    x0 must equal the front-end output bit for bit -- in inference (one pass) and in training (statistics pass first)."""
+    B = 3
+    video, audio, label = O.synthetic_batch(B, seed=77)
+    audio[1, 0, 20000:] = 0
+    for training in (False, True):
+        eng = _engine(model_type, B, "f32", training=training)
+        want = eng.frontend(audio).cpu().numpy()
+        if training:
+            eng.train_step_host(video, audio, label, 0.0)
+        else:
+            eng.predict(video, audio)
+        got = eng.debug_read("audio/x0", B).reshape(want.shape)
+        assert np.array_equal(got, want), (training, np.abs(got - want).max())
+
+
 def test_video_scaling_is_bit_exact():
     """train.py:186: `2 * img_as_float(u8).astype('float32') - 1` -- the device's u8 -> float conversion (k_input_stage mode 1)
     against the numpy expression, bit for bit (cnn_L3_orig has no input BN, so x0 is the scaled frame itself)."""

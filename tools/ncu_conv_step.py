@@ -17,7 +17,8 @@ def klass(name):
         return "conv_fwd"
     m = re.search(r"k_conv3x3_tc3<\d+, \d+, (\d+)>", name)
     if m:
-        return "conv_dgrad" if m.group(1) == "0" else "conv_fwd"   # EPI_NONE = no statistics = dgrad in a training step
+        # EPI_NONE (0) = no statistics, EPI_BWD (5) = BN-backward statistics of the layer below: data gradients
+        return "conv_dgrad" if m.group(1) in ("0", "5") else "conv_fwd"
     return None
 
 
