@@ -176,26 +176,40 @@ k_input_stage(const uint8_t* __restrict__ u8, float* __restrict__ x0, T* __restr
   if (xin != nullptr && scale != nullptr) { sc = scale[c]; sf = shift[c]; }
   double s1 = 0.0, s2 = 0.0;
   const unsigned stride = gridDim.x * kInThreads;   // multiple of C
-  for (unsigned i = blockIdx.x * kInThreads + threadIdx.x; i < n; i += stride) {
-    float v;
-    if (MODE == 1) {
-      v = 2.0f * (float)((double)u8[i] / 255.0) - 1.0f;
-      x0[i] = v;
-    } else if (MODE == 2) {
-      v = fmaxf(x0[i] - ordered_to_float(clip_max[fdiv(i, d_clip)]), -80.0f);
-      x0[i] = v;
-    } else {
-      v = x0[i];
+  constexpr int U = 4;                              // independent loads in flight per thread
+  for (unsigned i0 = blockIdx.x * kInThreads + threadIdx.x; i0 < n; i0 += U * stride) {
+    float v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const unsigned i = i0 + k * stride;
+      v[k] = 0.f;
+      if (i < n) {
+        if (MODE == 1) v[k] = (float)u8[i];
+        else v[k] = x0[i];
+      }
     }
-    if (sum != nullptr) {
-      s1 += (double)v;
-      s2 += (double)v * (double)v;
-    }
-    if (xin != nullptr) {
-      const unsigned row = fdiv(i, d_row), e = i - row * d_row.d;   // row = b * H + y, e = x * C + c
-      const unsigned b = fdiv(row, d_h), y = row - b * d_h.d;
-      const float o = (scale != nullptr) ? v * sc + sf : v;
-      xin[pad_off(b, (int)y, 0, H, W, C) + e] = from_f<T>(o);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const unsigned i = i0 + k * stride;
+      if (i >= n) continue;
+      float x = v[k];
+      if (MODE == 1) {
+        x = 2.0f * (float)((double)x / 255.0) - 1.0f;
+        x0[i] = x;
+      } else if (MODE == 2) {
+        x = fmaxf(x - ordered_to_float(clip_max[fdiv(i, d_clip)]), -80.0f);
+        x0[i] = x;
+      }
+      if (sum != nullptr) {
+        s1 += (double)x;
+        s2 += (double)x * (double)x;
+      }
+      if (xin != nullptr) {
+        const unsigned row = fdiv(i, d_row), e = i - row * d_row.d;   // row = b * H + y, e = x * C + c
+        const unsigned b = fdiv(row, d_h), y = row - b * d_h.d;
+        const float o = (scale != nullptr) ? x * sc + sf : x;
+        xin[pad_off(b, (int)y, 0, H, W, C) + e] = from_f<T>(o);
+      }
     }
   }
   if (sum != nullptr) {
@@ -213,7 +227,7 @@ int launch_input_stage(int mode, const uint8_t* u8, float* x0, T* xin, int B, in
   const long long n = (long long)B * H * W * C;
   L3_REQUIRE(n < 0x7fffffffLL, "input stage: too many elements");
   if (sum) L3_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * C, s));
-  long long want = (n + kInThreads * 4 - 1) / (kInThreads * 4);
+  long long want = (n + kInThreads * 8 - 1) / (kInThreads * 8);
   const int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
   const FastDiv d_row = make_fastdiv((uint32_t)(W * C)), d_h = make_fastdiv((uint32_t)H);
   const FastDiv d_clip = make_fastdiv((uint32_t)(H * W * C));
