@@ -58,59 +58,19 @@ __global__ void k_channel_stats_vec(const T* __restrict__ x, long long rows, int
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sum[i], (double)sh[i]);
 }
 
-// small C (1..4): one thread per row-strided pixel.  Always merged in fp64 (the input of this kernel is the float
-// front-end / video tensor in both modes, a few hundred values per thread).
-template <typename T>
-__global__ void k_channel_stats_small(const T* __restrict__ x, long long rows, int C, double* __restrict__ sum) {
-  __shared__ double sh[8];
-  if (threadIdx.x < 8) sh[threadIdx.x] = 0.0;
-  __syncthreads();
-  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
-    for (int c = 0; c < C; ++c) {
-      double t = (double)to_f(x[r * C + c]);
-      s1[c] += t;
-      s2[c] += t * t;
-    }
-  for (int c = 0; c < C; ++c) {
-    double a = s1[c], b = s2[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&sh[c], a);
-      atomicAdd(&sh[4 + c], b);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < C) {
-    atomicAdd(&sum[threadIdx.x], sh[threadIdx.x]);
-    atomicAdd(&sum[C + threadIdx.x], sh[4 + threadIdx.x]);
-  }
-}
-
 template <typename T>
 int launch_channel_stats(const T* x, long long rows, int C, int relu, double* sum, cudaStream_t s) {
+  // (the 1- and 3-channel input tensors take their statistics inside launch_input_stage)
+  L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "channel_stats: unsupported C=%d", C);
   L3_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * C, s));
-  if (C <= 4) {
-    L3_REQUIRE(!relu, "relu stats unsupported for small C");
-    int blocks = (int)((rows + kThreads * 8 - 1) / (kThreads * 8));
-    if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-    if (blocks < 1) blocks = 1;
-    k_channel_stats_small<T><<<blocks, kThreads, 0, s>>>(x, rows, C, sum);
-  } else {
-    L3_REQUIRE(C % 8 == 0 && kThreads % (C / 8) == 0, "channel_stats: unsupported C=%d", C);
-    int lanes = kThreads / (C / 8);
-    long long want = (rows + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
-    int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
-    const size_t shb = 2 * C * sizeof(typename MergeT<T>::type);
-    if (relu)
-      k_channel_stats_vec<T, true><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
-    else
-      k_channel_stats_vec<T, false><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
-  }
+  int lanes = kThreads / (C / 8);
+  long long want = (rows + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+  int blocks = (int)(want > kMaxBlocks ? kMaxBlocks : (want < 1 ? 1 : want));
+  const size_t shb = 2 * C * sizeof(typename MergeT<T>::type);
+  if (relu)
+    k_channel_stats_vec<T, true><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
+  else
+    k_channel_stats_vec<T, false><<<blocks, kThreads, shb, s>>>(x, rows, C, sum);
   L3_CHECK_LAUNCH();
   return 0;
 }
