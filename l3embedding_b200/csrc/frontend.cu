@@ -6,11 +6,12 @@
 //   l3embedding/audio_model.py:367-369 (melspec2:      n_dft 2048, same, 256 mels htk, dB)
 // and pcm2float (l3embedding/audio.py:21-31).  kapre evaluates the STFT as two dense strided convolutions
 // (1.67 GFLOP/clip); algebraically that is |rfft(frame*hann)|^2, which is what is computed here with an
-// fp32 in-shared-memory FFT (two real frames packed into one complex transform).  The mel projection uses the
-// <=2-non-zeros-per-bin structure of the librosa filterbank (band lists) instead of a dense GEMM.
+// fp32 FFT held in registers (frontend_fft.cuh; two real frames packed into one complex transform).  The mel
+// projection uses the <=2-non-zeros-per-bin structure of the librosa filterbank (band lists) instead of a dense GEMM.
 //
-// HBM traffic per clip: 96 KB in (int16) + n_out*n_frames*4 B out; the whole clip is staged into shared memory
-// once with a 1-D TMA bulk copy (cp.async.bulk) so the 8.5x frame overlap (2048/242) never re-reads HBM.
+// HBM traffic per clip: 96 KB in (int16) + n_out*n_frames*4 B out; each CTA stages the sample window of its frames
+// into shared memory with one 1-D TMA bulk copy (cp.async.bulk); the 8.5x frame overlap (2048/242) between CTAs is
+// served by L2.
 #include <math.h>
 #include <vector>
 #include "kernels.h"
